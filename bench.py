@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- domain pixel*GN-evaluations / s of the DIC hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c4] [--impl ours|reference]
+
+A *step* is one correlate() of the workload's domain from the zero initial guess: every pyramid
+level, every LM iteration, reduction and solve (correlation_class.cpp:349-640 semantics), on image
+pyramids already resident in HBM.  Work per step = sum over levels of N_level x evaluations_level
+(SURVEY.md section 8d), reported by the engine itself.
+
+  value     pixel*evaluations / s, device-resident inputs, all ranks (weak scaling: every rank
+            solves its own independent domain, no data-path collective)
+  e2e       same metric through the C-ABI with HOST (pinned) images: per step H2D of the image
+            pair, both pyramid builds, correlate, D2H of the result record
+  roofline  the fused GN kernel against the measured HBM copy bandwidth, with SURVEY 8d's
+            10 algorithmic bytes per pixel*evaluation
+  cpu_baseline / --impl reference
+            the reference CPU algorithm on this box's host cores: oracle/_ref (unmodified
+            reference, 6-parameter workloads) or the oracle port (12-parameter workload, which the
+            reference does not have), all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_PIXEL_EVAL = 10.0  # 8 B coordinates + 1 B und + 1 B def
+
+
+# ------------------------------------------------------------------------------ workloads
+
+def workload(name):
+    two_pi = 2.0 * np.pi
+    if name == "c1":  # BASELINE config 1 (the reference's CPU-runnable case)
+        return dict(name="c1: 1024^2 pair, 511x511 rect, affine 6-param, bicubic, pyramid 0/1/2",
+                    rows=1024, cols=1024, seed=1, model="affine", pyramid=(0, 1, 2),
+                    truth=(1.75, -0.6, .004, -.003, .002, .005), center=(512.0, 512.0),
+                    domain=("rect", 257, 257, 767, 767))
+    if name == "c2":  # BASELINE config 2: the configuration the metric is quoted on
+        return dict(name="c2: 4096^2 pair, annulus ri=600 ro=1800, quadratic 12-param, bicubic, pyramid 0..3",
+                    rows=4096, cols=4096, seed=2, model="quad", pyramid=(0, 1, 3),
+                    truth=(2.5, -1.75, .002, -.0015, .001, .0025, 1e-6, -5e-7, 8e-7, -1e-6, 6e-7, 4e-7),
+                    center=(2048.0, 2048.0), domain=("annulus", 600.0, 1200.0, 0.0, two_pi, 2048.0, 2048.0, 1))
+    if name == "c4":  # BASELINE config 4: 4096 subsets of 125^2
+        return dict(name="c4: 8192^2 pair, 64x64 subsets of 125^2, affine, pyramid 0/1/2",
+                    rows=8192, cols=8192, seed=4, model="affine", pyramid=(0, 1, 2),
+                    truth=(1.25, -0.75, .0004, -.0003, .0002, .0005), center=(4096.0, 4096.0),
+                    domain=("subsets", 64, 8128, 64))
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_images(w, device):
+    """(und, def) as torch uint8 CUDA tensors; synthetic analytic speckle, SURVEY 8d."""
+    from correlation_b200 import synth
+    und = synth.make_image(w["rows"], w["cols"], w["seed"], None, w["center"], device=device)
+    dfm = synth.make_image(w["rows"], w["cols"], w["seed"], w["truth"], w["center"], device=device)
+    return und, dfm
+
+
+def subset_boxes(lo, hi, n):
+    """n x n sectors of a rectangle, manager_class.cpp:274-310 arithmetic."""
+    fdim = (abs(hi - lo) / n - 1.0) / 2.0
+    dim = (abs(hi - lo) // n - 1) // 2
+    boxes = []
+    for i in range(n):
+        cx = int(0.5 + lo + fdim + (2.0 * fdim + 1.0) * i)
+        for j in range(n):
+            cy = int(0.5 + lo + fdim + (2.0 * fdim + 1.0) * j)
+            boxes.append((cx - dim, cy - dim, cx + dim, cy + dim))
+    return boxes
+
+
+# ------------------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+
+def cpu_run(w, und, dfm, threads, sample_levels=None):
+    """One 'step' of the reference CPU algorithm: both pyramid builds + Newton_Raphson (cold cache).
+    Returns (pixel_evaluations, seconds, kind, result)."""
+    import oracle
+    use_ref = oracle.have_ref() and w["model"] == "affine"
+    pyr = w["pyramid"]
+    if use_ref:
+        eng = oracle.RefEngine(model=oracle.FM_AFFINE, n_threads=threads, pyramid=pyr)
+        counter = oracle.OracleEngine(model=oracle.FM_AFFINE, n_threads=threads, pyramid=pyr, real_threads=True)
+    else:
+        model = oracle.FM_QUAD if w["model"] == "quad" else oracle.FM_AFFINE
+        eng = oracle.OracleEngine(model=model, n_threads=threads, pyramid=pyr, real_threads=True)
+        counter = None
+    d = w["domain"]
+    if d[0] == "rect":
+        xy, center = oracle.rect_points(*d[1:]), ((d[1] + d[3]) / 2.0, (d[2] + d[4]) / 2.0)
+    elif d[0] == "annulus":
+        xy, center = oracle.annulus_points(*d[1:]), None
+    else:  # subsets: a bounded sample of the 4096 subsets, run one after the other like the manager
+        boxes = subset_boxes(d[1], d[2], d[3])[:: max(1, (d[3] * d[3]) // 64)]
+        xy, center = None, None
+    n_par = 12 if w["model"] == "quad" else 6
+    t0 = time.perf_counter()
+    eng.set_image("und", und)
+    eng.set_image("def", dfm)
+    if counter is not None:
+        counter.set_image("und", und)
+        counter.set_image("def", dfm)
+    t_pyr = time.perf_counter() - t0
+    work, secs, res = 0.0, t_pyr, None
+    if xy is not None:
+        t1 = time.perf_counter()
+        res = eng.correlate(np.zeros(n_par, np.float32), xy, center=center)
+        secs += time.perf_counter() - t1
+        work = res.get("pixel_evaluations") or counter.correlate(np.zeros(n_par, np.float32), xy, center=center)["pixel_evaluations"]
+        sample = "whole workload, one cold step (pyramids + Newton_Raphson)"
+    else:
+        for bx in boxes:
+            pts = oracle.rect_points(*bx)
+            c = ((bx[0] + bx[2]) / 2.0, (bx[1] + bx[3]) / 2.0)
+            t1 = time.perf_counter()
+            res = eng.correlate(np.zeros(n_par, np.float32), pts, center=c)
+            secs += time.perf_counter() - t1
+            work += res.get("pixel_evaluations") or counter.correlate(np.zeros(n_par, np.float32), pts, center=c)["pixel_evaluations"]
+        sample = f"{len(boxes)} of {d[3] * d[3]} subsets, one cold step"
+    return work, secs, ("reference" if use_ref else "port"), res, sample, t_pyr
+
+
+# ------------------------------------------------------------------------------ main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = workload(args.workload)
+    n_par = 12 if w["model"] == "quad" else 6
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.impl == "reference" and rank != 0:
+            return 0
+        if args.impl == "ours":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.impl == "reference":
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else None
+        und_t, dfm_t = make_images(w, dev) if dev is not None else (None, None)
+        if dev is None:
+            from correlation_b200 import synth
+            und = synth.make_image(w["rows"], w["cols"], w["seed"], None, w["center"])
+            dfm = synth.make_image(w["rows"], w["cols"], w["seed"], w["truth"], w["center"])
+        else:
+            und, dfm = und_t.cpu().numpy(), dfm_t.cpu().numpy()
+        threads = os.cpu_count() or 1
+        vals = []
+        for i in range(args.warmup + args.steps):
+            work, secs, kind, res, sample, _ = cpu_run(w, und, dfm, threads)
+            if i >= args.warmup:
+                vals.append((work, secs))
+        tot_w, tot_s = sum(v[0] for v in vals), sum(v[1] for v in vals)
+        v = tot_w / tot_s
+        line = {"impl": "reference", "metric": "domain pixel*GN-evaluations/s", "value": v,
+                "unit": "pixel*evaluations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic analytic speckle (SURVEY 8d)",
+                "config": {"workload": w["name"]},
+                "cpu_baseline": {"value": v, "unit": "pixel*evaluations/s", "cores": threads, "kind": kind,
+                                 "sample": sample},
+                "e2e": {"value": v, "unit": "pixel*evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    from correlation_b200 import engine
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    und_t, dfm_t = make_images(w, dev)
+    und_pin = torch.empty(und_t.shape, dtype=torch.uint8, pin_memory=True)
+    dfm_pin = torch.empty(dfm_t.shape, dtype=torch.uint8, pin_memory=True)
+    und_pin.copy_(und_t)
+    dfm_pin.copy_(dfm_t)
+    torch.cuda.synchronize()
+    mode = engine.MODE_PARITY if args.mode == "parity" else engine.MODE_FAST
+    eng = engine.CudaEngine(local_rank, fitting_model=engine.FM_QUADRATIC if w["model"] == "quad" else engine.FM_UVUxUyVxVy,
+                            arith_mode=mode)
+    rows, cols = w["rows"], w["cols"]
+    eng.resetImagePyramidsDevice(und_t.data_ptr(), dfm_t.data_ptr(), None, rows, cols, cols, pyramid=w["pyramid"])
+    d = w["domain"]
+    t_dom = time.perf_counter()
+    if d[0] == "rect":
+        eng.resetPolygon(0, *d[1:])
+        n_sectors = 1
+    elif d[0] == "annulus":
+        eng.resetPolygon(0, *d[1:])
+        n_sectors = 1
+    else:
+        boxes = subset_boxes(d[1], d[2], d[3])
+        for k, bx in enumerate(boxes):
+            eng.resetPolygon(k, *bx)
+        n_sectors = len(boxes)
+    eng.synchronize()
+    t_dom = time.perf_counter() - t_dom
+    zero = np.zeros((n_sectors, n_par), np.float32)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        if n_sectors == 1:
+            r = eng.correlate(0, zero[0])
+            return r["pixel_evaluations"], eng.last_correlate_ms(), r
+        rs = eng.correlate_batch(0, zero)
+        return sum(r["pixel_evaluations"] for r in rs), eng.last_correlate_ms(), rs[0]
+
+    def step_e2e():
+        eng.lib.dic_reset_image_pyramids(eng.h, und_pin.data_ptr(), dfm_pin.data_ptr(), None, rows, cols, 1, *w["pyramid"])
+        return step_resident()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = eng.kernel_launches()
+    barrier()
+    work = kern_ms = wall = 0.0
+    with ClockSampler(local_rank) as clk:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            wk, ms, last = step_resident()
+            wall += time.perf_counter() - t0
+            work += wk
+            kern_ms += ms
+    barrier()
+    launches = eng.kernel_launches() - launches0
+    # e2e: host buffers, copies inside the timed region
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_work, t0 = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        wk, _, _ = step_e2e()
+        e2e_work += wk
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+
+    stats = torch.tensor([wall, e2e_wall, work, e2e_work, kern_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall, e2e_wall = mx[0].item(), mx[1].item()
+        work, e2e_work = sm[2].item(), sm[3].item()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    my_work = stats[2].item()
+    achieved = ALGO_BYTES_PER_PIXEL_EVAL * my_work / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    value = work / wall
+    line = {
+        "metric": "domain pixel*GN-evaluations/s", "value": value, "unit": "pixel*evaluations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic analytic speckle (SURVEY 8d), random phases seeded",
+        "config": {"workload": w["name"], "arith_mode": args.mode, "sectors": n_sectors,
+                   "pixel_evaluations_per_step": my_work / args.steps,
+                   "evaluations_per_level": last["evaluations"][: w["pyramid"][2] + 1],
+                   "points_per_level": last["points_per_level"][: w["pyramid"][2] + 1],
+                   "l2": "flushed between steps (512 MiB write); evaluations inside a step re-read the domain by design",
+                   "domain_build_s": t_dom, "parallelism": f"{world} independent domain(s), one per GPU"},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_work / e2e_wall, "unit": "pixel*evaluations/s",
+                "h2d_bytes_per_step": 2 * rows * cols, "d2h_bytes_per_step": 176 * n_sectors,
+                "ms_per_step": 1e3 * e2e_wall / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "kernel": "gn_solve_kernel", "kernel_ms_per_step": kern_ms / args.steps,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "algorithmic_bytes_per_pixel_evaluation": ALGO_BYTES_PER_PIXEL_EVAL},
+    }
+    if not args.no_cpu_baseline:
+        try:
+            und, dfm = und_pin.numpy(), dfm_pin.numpy()
+            threads = os.cpu_count() or 1
+            cw, cs, kind, cres, sample, t_pyr = cpu_run(w, und, dfm, threads)
+            line["cpu_baseline"] = {"value": cw / cs, "unit": "pixel*evaluations/s", "cores": threads, "kind": kind,
+                                    "sample": sample, "seconds": cs, "pyramid_seconds": t_pyr}
+            gp, cp = last["params"], cres["params"]
+            line["config"]["parity_vs_cpu"] = {
+                "max_abs_duv": float(np.abs(gp[:2] - cp[:2]).max()), "max_abs_dgrad": float(np.abs(gp[2:6] - cp[2:6]).max()),
+                "rel_dchi": float(abs(last["chi"] - cres["chi"]) / max(abs(cres["chi"]), 1e-30)),
+                "iterations": [int(last["iterations"]), int(cres["iterations"])]}
+        except Exception as ex:  # the baseline is reported, never allowed to sink the bench line
+            line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

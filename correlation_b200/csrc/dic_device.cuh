@@ -1,0 +1,446 @@
+// dic_device.cuh -- device-side building blocks of the B200 DIC engine (sm_100a).
+//
+// Everything on the Gauss-Newton hot path of the reference CPU engine, fused per pixel:
+//   warp      model_class.cpp:150-202 (+ U/UV/UVQ :48-148, + 12-parameter extension)
+//   bicubic   interpolation_class.cpp:79-138 / :243-336 (bilinear :140-195, nearest :197-226)
+//   residual  interpolation_class.cpp:671-764  (V, H = grad w . dT/dp, A += H H^T, b += H V, chi += V^2)
+//   solve     correlation_class.cpp:642-768    (scale, damp, solve) -- single-warp Cholesky here
+//   LM loop   correlation_class.cpp:349-640    -- on-device state machine, never returns to host
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dic_b200.h"
+
+namespace dic {
+
+constexpr int kMaxLevels = DIC_MAX_LEVELS;
+constexpr int kMaxParams = DIC_MAX_PARAMS;
+constexpr int kThreads = 256; // threads per CTA of the GN kernels
+
+// ------------------------------------------------------------------ descriptors
+
+struct LevelImage {
+  const uint8_t *ptr; // u8, row-major, `pitch` bytes per row (multiple of 128, >= cols + 16)
+  int rows, cols, pitch;
+};
+
+// Per-sector device record (one per domain / subdivision subset).
+struct SectorDev {
+  const float2 *xy[kMaxLevels]; // per-level pixel list (x, y) in level units
+  int n[kMaxLevels];
+  float cx, cy; // level-0 centre
+};
+
+enum Phase { PH_INIT = 0, PH_REDO = 1, PH_TENT = 2 };
+
+// Levenberg-Marquardt state of one sector (global memory in grid mode, shared in batch mode).
+struct LMState {
+  float p[kMaxParams];         // parameters the next evaluation uses (level units)
+  float mp[kMaxParams];        // the reference's `model_parameters` (what it would return)
+  float last_good[kMaxParams]; // correlation_class.cpp:369-371
+  float tentative[kMaxParams];
+  float saved[kMaxParams];
+  float lambda, last_good_chi, scaling;
+  int level, level_old, iteration, use_saved, phase, done;
+  int error_code, reached_iterations;
+  int evals[kMaxLevels], iters[kMaxLevels];
+};
+
+// Grid-wide reduction / barrier scratch (grid mode).
+struct GridWork {
+  unsigned int arrive;     // tickets of the current evaluation
+  unsigned int generation; // bumped by the last CTA after the LM step
+  LMState state;
+};
+
+struct SolveSettings {
+  LevelImage und[kMaxLevels];
+  LevelImage def[kMaxLevels];
+  int start, step, stop;
+  int max_iters;
+  float precision;
+};
+
+// ------------------------------------------------------------------ small helpers
+
+template <int NP> struct Acc {
+  static constexpr int kA = NP * (NP + 1) / 2;
+  static constexpr int kB = kA;          // offset of b
+  static constexpr int kChi = kA + NP;   // offset of chi
+  static constexpr int kOob = kChi + 1;  // offset of the out-of-image counter
+  static constexpr int kN = kOob + 1;
+};
+
+__host__ __device__ constexpr int model_nparams(int model) {
+  return model == DIC_FM_U ? 1 : model == DIC_FM_UV ? 2 : model == DIC_FM_UVQ ? 3
+       : model == DIC_FM_UVUxUyVxVy ? 6 : 12;
+}
+
+__device__ __forceinline__ float u8_to_float(uint32_t word, int byte) {
+  // PRMT builds 0x4B0000bb = 2^23 + bb, one FADD removes the bias: no I2F on the hot path
+  uint32_t r = __byte_perm(word, 0x4B000000u, 0x7650u | byte);
+  return __uint_as_float(r) - 8388608.0f;
+}
+
+// 4 consecutive pixels starting at byte address (row + x), any alignment: two aligned 32-bit
+// loads + funnel shift. Rows are padded so the second word is always readable.
+__device__ __forceinline__ uint32_t load4_u8(const uint8_t *row, int x) {
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(row + (x & ~3));
+  uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+  return __funnelshift_r(lo, hi, (x & 3) * 8);
+}
+
+// ------------------------------------------------------------------ interpolation
+
+// Reference arithmetic (parity mode): monomial bicubic in dx = 1 + frac, coefficients
+// a = (B (x) B) v with B the integer inverse of the 1-D Hermite constraint matrix
+// (M of interpolation_class.cpp:539-558 equals that Kronecker product exactly; every
+// intermediate is a multiple of 1/4 below 2^22, so the coefficient stage is exact in fp32 in any
+// order), then the 40 terms of :108-126 in the reference's order with unfused mul/add.
+__device__ __forceinline__ void hermite_to_monomial(float f1, float f2, float d1, float d2,
+                                                    float c[4]) {
+  c[0] = -4.f * f1 + 5.f * f2 - 4.f * d1 - 2.f * d2;
+  c[1] = 12.f * f1 - 12.f * f2 + 8.f * d1 + 5.f * d2;
+  c[2] = -9.f * f1 + 9.f * f2 - 5.f * d1 - 4.f * d2;
+  c[3] = 2.f * f1 - 2.f * f2 + d1 + d2;
+}
+
+__device__ __forceinline__ void bicubic_parity(const float p[4][4], float xdef, float ydef, int ix,
+                                               int iy, float &w, float &wx, float &wy) {
+  // x pass: for each image row r, cubic in x through columns 1,2 with central-difference slopes
+  float cx[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    hermite_to_monomial(p[r][1], p[r][2], (p[r][2] - p[r][0]) * 0.5f, (p[r][3] - p[r][1]) * 0.5f,
+                        cx[r]);
+  // y pass: a[jk][ik]
+  float a[4][4];
+#pragma unroll
+  for (int ik = 0; ik < 4; ++ik) {
+    float c[4];
+    hermite_to_monomial(cx[1][ik], cx[2][ik], (cx[2][ik] - cx[0][ik]) * 0.5f,
+                        (cx[3][ik] - cx[1][ik]) * 0.5f, c);
+#pragma unroll
+    for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
+  }
+  float dx = __fadd_rn(__fsub_rn(xdef, (float)ix), 1.f);
+  float dy = __fadd_rn(__fsub_rn(ydef, (float)iy), 1.f);
+  float px[4], py[4];
+  px[0] = 1.f; px[1] = dx; px[2] = __fmul_rn(dx, dx); px[3] = __fmul_rn(px[2], dx);
+  py[0] = 1.f; py[1] = dy; py[2] = __fmul_rn(dy, dy); py[3] = __fmul_rn(py[2], dy);
+  float rw = 0.f, rx = 0.f, ry = 0.f;
+#pragma unroll
+  for (int jk = 0; jk < 4; ++jk) {
+#pragma unroll
+    for (int ik = 0; ik < 4; ++ik) {
+      float c = a[jk][ik];
+      // w += (a * py[jk]) * px[ik]
+      float u = jk == 0 ? c : __fmul_rn(c, py[jk]);
+      rw = __fadd_rn(rw, ik == 0 ? u : __fmul_rn(u, px[ik]));
+      if (ik > 0) { // wx += ((ik * a) * py[jk]) * px[ik-1]
+        float t = __fmul_rn((float)ik, c);
+        t = jk == 0 ? t : __fmul_rn(t, py[jk]);
+        t = ik == 1 ? t : __fmul_rn(t, px[ik - 1]);
+        rx = __fadd_rn(rx, t);
+      }
+      if (jk > 0) { // wy += ((jk * a) * py[jk-1]) * px[ik]
+        float t = __fmul_rn((float)jk, c);
+        t = jk == 1 ? t : __fmul_rn(t, py[jk - 1]);
+        t = ik == 0 ? t : __fmul_rn(t, px[ik]);
+        ry = __fadd_rn(ry, t);
+      }
+    }
+  }
+  w = rw; wx = rx; wy = ry;
+}
+
+// Fast mode: the same interpolant (Keys a = -1/2, Catmull-Rom) in weight form.
+__device__ __forceinline__ void cr_weights(float t, float w[4], float d[4]) {
+  float t2 = t * t;
+  w[0] = ((-0.5f * t + 1.0f) * t - 0.5f) * t;
+  w[1] = (1.5f * t - 2.5f) * t2 + 1.0f;
+  w[2] = ((-1.5f * t + 2.0f) * t + 0.5f) * t;
+  w[3] = (0.5f * t - 0.5f) * t2;
+  d[0] = (-1.5f * t + 2.0f) * t - 0.5f;
+  d[1] = (4.5f * t - 5.0f) * t;
+  d[2] = (-4.5f * t + 4.0f) * t + 0.5f;
+  d[3] = (1.5f * t - 1.0f) * t;
+}
+
+__device__ __forceinline__ void bicubic_fast(const float p[4][4], float tx, float ty, float &w,
+                                             float &wx, float &wy) {
+  float wxw[4], wxd[4], wyw[4], wyd[4];
+  cr_weights(tx, wxw, wxd);
+  cr_weights(ty, wyw, wyd);
+  float rw = 0.f, rx = 0.f, ry = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float s = p[r][0] * wxw[0] + p[r][1] * wxw[1] + p[r][2] * wxw[2] + p[r][3] * wxw[3];
+    float sd = p[r][0] * wxd[0] + p[r][1] * wxd[1] + p[r][2] * wxd[2] + p[r][3] * wxd[3];
+    rw += wyw[r] * s;
+    rx += wyw[r] * sd;
+    ry += wyd[r] * s;
+  }
+  w = rw; wx = rx; wy = ry;
+}
+
+// One deformed-image sample. Returns false (and w = wx = wy = 0) when out of image, with the
+// reference's own bounds tests.
+template <int INTERP, int MODE>
+__device__ __forceinline__ bool sample_def(const LevelImage &img, float xdef, float ydef, float &w,
+                                           float &wx, float &wy) {
+  if (INTERP == DIC_IM_BICUBIC) {
+    // interpolation_class.cpp:82-83
+    if (!(xdef > 1.f && ydef > 1.f && xdef < (float)img.cols - 2.f && ydef < (float)img.rows - 2.f)) {
+      w = wx = wy = 0.f;
+      return false;
+    }
+    int ix = (int)xdef, iy = (int)ydef;
+    float p[4][4];
+    const uint8_t *row = img.ptr + (size_t)(iy - 1) * img.pitch;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t v = load4_u8(row + (size_t)r * img.pitch, ix - 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) p[r][c] = u8_to_float(v, c);
+    }
+    if (MODE == DIC_MODE_PARITY) bicubic_parity(p, xdef, ydef, ix, iy, w, wx, wy);
+    else bicubic_fast(p, xdef - (float)ix, ydef - (float)iy, w, wx, wy);
+    return true;
+  } else if (INTERP == DIC_IM_BILINEAR) {
+    // interpolation_class.cpp:143-144, :338-374
+    if (!(xdef > 0.f && ydef > 0.f && xdef < (float)(img.cols - 1) && ydef < (float)(img.rows - 1))) {
+      w = wx = wy = 0.f;
+      return false;
+    }
+    int ix = (int)xdef, iy = (int)ydef;
+    const uint8_t *r0 = img.ptr + (size_t)iy * img.pitch + ix;
+    float w00 = (float)__ldg(r0), w10 = (float)__ldg(r0 + 1);
+    float w01 = (float)__ldg(r0 + img.pitch), w11 = (float)__ldg(r0 + img.pitch + 1);
+    float a0 = w00, a1 = __fsub_rn(w10, w00), a2 = __fsub_rn(w01, w00);
+    float a3 = __fadd_rn(__fsub_rn(__fsub_rn(w11, w10), w01), w00);
+    float dx = __fsub_rn(xdef, (float)ix), dy = __fsub_rn(ydef, (float)iy);
+    // reference order: (jk,ik) = (0,0),(0,1),(1,0),(1,1); w += a*py*px
+    float rw = a0;
+    rw = __fadd_rn(rw, __fmul_rn(a1, dx));
+    rw = __fadd_rn(rw, __fmul_rn(a2, dy));
+    rw = __fadd_rn(rw, __fmul_rn(__fmul_rn(a3, dy), dx));
+    float rx = __fadd_rn(a1, __fmul_rn(a3, dy));
+    float ry = __fadd_rn(a2, __fmul_rn(a3, dx));
+    w = rw; wx = rx; wy = ry;
+    return true;
+  } else {
+    // interpolation_class.cpp:200-201, :376-406
+    if (!(xdef > 0.f && ydef > 0.f && xdef < (float)(img.cols - 1) && ydef < (float)(img.rows - 1))) {
+      w = wx = wy = 0.f;
+      return false;
+    }
+    int ix = (int)(xdef + 0.5f), iy = (int)(ydef + 0.5f);
+    const uint8_t *r0 = img.ptr + (size_t)iy * img.pitch + ix;
+    float w00 = (float)__ldg(r0), w10 = (float)__ldg(r0 + 1), w01 = (float)__ldg(r0 + img.pitch);
+    w = w00; wx = __fsub_rn(w10, w00); wy = __fsub_rn(w01, w00);
+    return true;
+  }
+}
+
+// ------------------------------------------------------------------ warp + residual row
+
+// Deformed position and steepest-descent row H = wx * dTx/dp + wy * dTy/dp for one pixel.
+// Parity mode keeps the reference's left-to-right fp32 evaluation of the warp.
+template <int MODEL, int MODE>
+__device__ __forceinline__ void warp_point(const float *p, float x, float y, float cx, float cy,
+                                           float &xd, float &yd, float &dx, float &dy) {
+  dx = __fsub_rn(x, cx);
+  dy = __fsub_rn(y, cy);
+  if (MODEL == DIC_FM_U) {
+    xd = __fadd_rn(x, p[0]); yd = y;
+  } else if (MODEL == DIC_FM_UV) {
+    xd = __fadd_rn(x, p[0]); yd = __fadd_rn(y, p[1]);
+  } else if (MODEL == DIC_FM_UVQ) {
+    xd = __fsub_rn(__fadd_rn(x, p[0]), __fmul_rn(p[2], dy));
+    yd = __fadd_rn(__fadd_rn(y, p[1]), __fmul_rn(p[2], dx));
+  } else if (MODEL == DIC_FM_UVUxUyVxVy) {
+    if (MODE == DIC_MODE_PARITY) {
+      xd = __fadd_rn(__fadd_rn(__fadd_rn(x, p[0]), __fmul_rn(p[2], dx)), __fmul_rn(p[3], dy));
+      yd = __fadd_rn(__fadd_rn(__fadd_rn(y, p[1]), __fmul_rn(p[4], dx)), __fmul_rn(p[5], dy));
+    } else {
+      xd = fmaf(p[3], dy, fmaf(p[2], dx, x + p[0]));
+      yd = fmaf(p[5], dy, fmaf(p[4], dx, y + p[1]));
+    }
+  } else {
+    if (MODE == DIC_MODE_PARITY) {
+      float t = __fadd_rn(__fadd_rn(__fadd_rn(x, p[0]), __fmul_rn(p[2], dx)), __fmul_rn(p[3], dy));
+      t = __fadd_rn(t, __fmul_rn(__fmul_rn(__fmul_rn(0.5f, p[6]), dx), dx));
+      t = __fadd_rn(t, __fmul_rn(__fmul_rn(p[7], dx), dy));
+      xd = __fadd_rn(t, __fmul_rn(__fmul_rn(__fmul_rn(0.5f, p[8]), dy), dy));
+      t = __fadd_rn(__fadd_rn(__fadd_rn(y, p[1]), __fmul_rn(p[4], dx)), __fmul_rn(p[5], dy));
+      t = __fadd_rn(t, __fmul_rn(__fmul_rn(__fmul_rn(0.5f, p[9]), dx), dx));
+      t = __fadd_rn(t, __fmul_rn(__fmul_rn(p[10], dx), dy));
+      yd = __fadd_rn(t, __fmul_rn(__fmul_rn(__fmul_rn(0.5f, p[11]), dy), dy));
+    } else {
+      float hxx = 0.5f * dx * dx, hxy = dx * dy, hyy = 0.5f * dy * dy;
+      xd = x + p[0] + p[2] * dx + p[3] * dy + p[6] * hxx + p[7] * hxy + p[8] * hyy;
+      yd = y + p[1] + p[4] * dx + p[5] * dy + p[9] * hxx + p[10] * hxy + p[11] * hyy;
+    }
+  }
+}
+
+template <int MODEL>
+__device__ __forceinline__ void descent_row(float wx, float wy, float dx, float dy, float *H) {
+  if (MODEL == DIC_FM_U) {
+    H[0] = wx;
+  } else if (MODEL == DIC_FM_UV) {
+    H[0] = wx; H[1] = wy;
+  } else if (MODEL == DIC_FM_UVQ) {
+    H[0] = wx; H[1] = wy; H[2] = wy * dx - wx * dy;
+  } else {
+    H[0] = wx; H[1] = wy; H[2] = wx * dx; H[3] = wx * dy; H[4] = wy * dx; H[5] = wy * dy;
+    if (MODEL == DIC_FM_QUADRATIC) {
+      float hxx = 0.5f * dx * dx, hxy = dx * dy, hyy = 0.5f * dy * dy;
+      H[6] = wx * hxx; H[7] = wx * hxy; H[8] = wx * hyy;
+      H[9] = wy * hxx; H[10] = wy * hxy; H[11] = wy * hyy;
+    }
+  }
+}
+
+// One pixel of one evaluation, accumulated into acc[] (upper-triangular A, b, chi, oob count).
+template <int MODEL, int INTERP, int MODE>
+__device__ __forceinline__ void accumulate_pixel(const LevelImage &und, const LevelImage &def,
+                                                 const float *p, float cx, float cy, float x, float y,
+                                                 float *acc) {
+  constexpr int NP = model_nparams(MODEL);
+  using L = Acc<NP>;
+  float xd, yd, dx, dy, w, wx, wy;
+  warp_point<MODEL, MODE>(p, x, y, cx, cy, xd, yd, dx, dy);
+  bool inside = sample_def<INTERP, MODE>(def, xd, yd, w, wx, wy);
+  // nearest reference-image pixel, interpolation_class.cpp:701-714
+  int uix = (int)(x + 0.5f), uiy = (int)(y + 0.5f);
+  float und_w = (float)__ldg(und.ptr + (size_t)uiy * und.pitch + uix);
+  float V = und_w - w;
+  acc[L::kChi] = fmaf(V, V, acc[L::kChi]);
+  if (!inside) acc[L::kOob] += 1.f;
+  float H[NP];
+  descent_row<MODEL>(wx, wy, dx, dy, H);
+  int k = 0;
+#pragma unroll
+  for (int p1 = 0; p1 < NP; ++p1) {
+    acc[L::kB + p1] = fmaf(H[p1], V, acc[L::kB + p1]);
+#pragma unroll
+    for (int p2 = p1; p2 < NP; ++p2) {
+      acc[k] = fmaf(H[p1], H[p2], acc[k]);
+      ++k;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ reductions
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block reduction of N per-thread accumulators into out[0..N) (shared). red: [warps][N] scratch.
+template <int N>
+__device__ __forceinline__ void block_reduce(float *acc, float *red, float *out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float v = warp_sum(acc[k]);
+    if (lane == 0) red[warp * N + k] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < N; k += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * N + k];
+    out[k] = s;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ solve (one warp)
+
+// Damped normal equations of correlation_class.cpp:642-688: A, b scaled by 1/N, diagonal times
+// (1 + lambda). Solved by a Jacobi-equilibrated Cholesky factorisation run by one warp in shared
+// memory (replaces the reference's cuSOLVER potrf/potrs, cuda_solver.cu:119-149, and the CPU's
+// Eigen QR). tot: packed upper A, then b. Returns false when a pivot is not positive.
+template <int NP>
+__device__ bool warp_solve(const float *tot, float scaling, float lambda, float *M /*NP*(NP+1)*/,
+                           float *dp /*NP*/) {
+  const int lane = threadIdx.x & 31;
+  float *S = M + NP * NP; // NP scale factors
+  // unpack, scale, damp
+  for (int idx = lane; idx < NP * NP; idx += 32) {
+    int i = idx / NP, j = idx % NP;
+    int r = i < j ? i : j, c = i < j ? j : i;
+    int k = r * NP - r * (r - 1) / 2 + (c - r);
+    float v = tot[k] * scaling;
+    if (i == j) v *= (1.f + lambda);
+    M[idx] = v;
+  }
+  __syncwarp();
+  if (lane < NP) {
+    float d = M[lane * NP + lane];
+    S[lane] = d > 0.f ? rsqrtf(d) : 0.f;
+  }
+  __syncwarp();
+  bool ok = true;
+  for (int i = 0; i < NP; ++i) ok = ok && (S[i] > 0.f);
+  if (!ok) return false;
+  for (int idx = lane; idx < NP * NP; idx += 32) {
+    int i = idx / NP, j = idx % NP;
+    M[idx] *= S[i] * S[j];
+  }
+  __syncwarp();
+  // right-looking Cholesky, lower triangle in place
+  for (int k = 0; k < NP; ++k) {
+    float d = M[k * NP + k];
+    if (!(d > 1e-12f)) return false;
+    float inv = rsqrtf(d);
+    __syncwarp();
+    if (lane >= k && lane < NP) M[lane * NP + k] *= inv; // column k (diag becomes sqrt(d))
+    __syncwarp();
+    for (int idx = lane; idx < NP * NP; idx += 32) {
+      int i = idx / NP, j = idx % NP;
+      if (j > k && i >= j) M[idx] -= M[i * NP + k] * M[j * NP + k];
+    }
+    __syncwarp();
+  }
+  // forward / backward substitution by lane 0 (n <= 12: ~150 dependent FMAs)
+  if (lane == 0) {
+    const float *bvec = tot + NP * (NP + 1) / 2;
+    float yv[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float s = bvec[i] * scaling * S[i];
+      for (int j = 0; j < i; ++j) s -= M[i * NP + j] * yv[j];
+      yv[i] = s / M[i * NP + i];
+    }
+#pragma unroll
+    for (int i = NP - 1; i >= 0; --i) {
+      float s = yv[i];
+      for (int j = i + 1; j < NP; ++j) s -= M[j * NP + i] * yv[j];
+      yv[i] = s / M[i * NP + i];
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) dp[i] = yv[i] * S[i];
+  }
+  __syncwarp();
+  return true;
+}
+
+// pyramid_class.cpp:260-287: only u, v scale between levels; the quadratic extension scales its
+// second-order terms by the inverse factor.
+template <int MODEL>
+__device__ __forceinline__ float translate_param(float v, int idx, int src, int dst) {
+  float mag = dst > src ? 1.f / (float)(1 << (dst - src)) : (float)(1 << (src - dst));
+  if (idx < 2) return v * mag;
+  if (MODEL == DIC_FM_QUADRATIC && idx >= 6) return v * (1.f / mag);
+  return v;
+}
+
+} // namespace dic

@@ -1,0 +1,1129 @@
+// dic_engine.cu -- host side of libdic_b200.so: the C-ABI of include/dic_b200.h.
+//
+// Replaces the reference's cuda_class / cuda_pyramid / cuda_polygon / cuda_solver host code.
+// One engine = one CUDA device, one correlation stream, one image stream; device memory is owned
+// here: three image pyramids (und / def / nxt, rotated by index like pyramid_class.cpp:211-258),
+// per-sector pixel lists for every used pyramid level, and a few hundred bytes of LM state.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dic_kernels.cuh"
+#include "dic_polygon.hpp"
+
+using namespace dic;
+
+namespace {
+
+enum SectorKind { SK_NONE = 0, SK_RECT, SK_ANNULAR, SK_BLOB, SK_POINTS };
+
+struct Sector {
+  SectorKind kind = SK_NONE;
+  float2 *buf = nullptr; // one allocation for all levels
+  size_t cap = 0;        // in float2
+  float2 *xy[kMaxLevels] = {};
+  long n[kMaxLevels] = {};
+  float cx = 0.f, cy = 0.f;
+  bool integer_grid = true;
+  // geometry kept for reference-order regeneration
+  int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+  bool pending = false; // an async correlate is in flight
+};
+
+struct PyramidSlot {
+  uint8_t *base = nullptr;
+  size_t cap = 0;
+  LevelImage lev[kMaxLevels] = {};
+  int rows = 0, cols = 0;
+  bool valid = false;
+};
+
+} // namespace
+
+struct dic_engine {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr, img_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_img = nullptr;
+  PyramidSlot pyr[3];
+  int role[3] = {0, 1, 2}; // role (0 und, 1 def, 2 nxt) -> slot
+  int start = 0, step = 1, stop = 0;
+  int max_iters = 50;
+  float precision = 1e-3f;
+  int model = DIC_FM_UVUxUyVxVy, interp = DIC_IM_BICUBIC, mode = DIC_MODE_PARITY;
+  int center_mode = DIC_CENTER_REFERENCE;
+  std::vector<Sector> sectors;
+  SectorDev *d_sectors = nullptr;
+  float *d_guess = nullptr;
+  dic_result *d_results = nullptr;
+  dic_result *h_results = nullptr; // pinned
+  float *h_guess = nullptr;        // pinned
+  int cap_sectors = 0;
+  GridWork *d_work = nullptr;
+  float *d_partials = nullptr;
+  int max_grid = 0;
+  float *d_scratch = nullptr; // 256 floats + ints for small kernels
+  unsigned int *d_counts = nullptr;
+  unsigned long long *d_offsets = nullptr;
+  size_t cap_counts = 0;
+  uint8_t *d_stage = nullptr;
+  size_t cap_stage = 0;
+  uint8_t *d_stage_img = nullptr; // staging owned by the image stream (nxt uploads)
+  size_t cap_stage_img = 0;
+  float last_ms = 0.f;
+  bool timing_pending = false;
+  std::atomic<long long> launches{0};
+  std::string err;
+  std::mutex err_mutex;
+};
+
+namespace {
+
+#define CU_TRY(e, call)                                                                   \
+  do {                                                                                    \
+    cudaError_t _r = (call);                                                              \
+    if (_r != cudaSuccess) {                                                              \
+      set_error(e, std::string(#call) + ": " + cudaGetErrorString(_r));                   \
+      return DIC_ERROR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+void set_error(dic_engine *e, const std::string &msg) {
+  std::lock_guard<std::mutex> g(e->err_mutex);
+  e->err = msg;
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+int np_of(const dic_engine *e) { return model_nparams(e->model); }
+
+PyrWeights pyramid_weights() {
+  // pyramid_class.cpp:83-90: fp32 products of the 1-D taps, formed at run time
+  const float km[5] = {0.05f, 0.25f, 0.4f, 0.25f, 0.05f};
+  PyrWeights w;
+  for (int dj = 0; dj < 5; ++dj)
+    for (int di = 0; di < 5; ++di) {
+      volatile float p = km[di] * km[dj];
+      w.w[dj * 5 + di] = p;
+    }
+  return w;
+}
+
+// (Re)shape a pyramid slot for rows x cols, levels 0..stop.
+int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
+  size_t total = 0;
+  size_t off[kMaxLevels];
+  int r = rows, c = cols;
+  LevelImage lev[kMaxLevels] = {};
+  for (int l = 0; l <= stop; ++l) {
+    int pitch = align_up(c + 16, 128);
+    off[l] = total;
+    lev[l].rows = r; lev[l].cols = c; lev[l].pitch = pitch;
+    total += (size_t)pitch * (r + 8);
+    total = (total + 255) / 256 * 256;
+    r /= 2; c /= 2;
+  }
+  if (total > s.cap) {
+    if (s.base) CU_TRY(e, cudaFree(s.base));
+    s.base = nullptr; s.cap = 0;
+    CU_TRY(e, cudaMalloc(&s.base, total));
+    s.cap = total;
+  }
+  for (int l = 0; l <= stop; ++l) { lev[l].ptr = s.base + off[l]; s.lev[l] = lev[l]; }
+  for (int l = stop + 1; l < kMaxLevels; ++l) s.lev[l] = LevelImage{};
+  s.rows = rows; s.cols = cols;
+  return DIC_OK;
+}
+
+// Level 0 -> levels 1..stop on `st`.
+int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st) {
+  static const PyrWeights kw = pyramid_weights();
+  for (int l = 1; l <= stop; ++l) {
+    const LevelImage &src = s.lev[l - 1];
+    const LevelImage &dst = s.lev[l];
+    if (dst.rows <= 0 || dst.cols <= 0) break;
+    dim3 block(kPyrTX, kPyrTY);
+    dim3 grid((dst.cols + kPyrTX - 1) / kPyrTX, (dst.rows + kPyrTY - 1) / kPyrTY);
+    pyramid_level_kernel<<<grid, block, 0, st>>>(src, const_cast<uint8_t *>(dst.ptr), dst.rows,
+                                                 dst.cols, dst.pitch, kw);
+    e->launches++;
+  }
+  CU_TRY(e, cudaGetLastError());
+  s.valid = true;
+  return DIC_OK;
+}
+
+int upload_level0(dic_engine *e, PyramidSlot &s, const void *src, int rows, int cols, int spitch,
+                  bool src_on_device, cudaStream_t st) {
+  uint8_t *dst = const_cast<uint8_t *>(s.lev[0].ptr);
+  CU_TRY(e, cudaMemcpy2DAsync(dst, s.lev[0].pitch, src, spitch, cols, rows,
+                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return DIC_OK;
+}
+
+int set_image(dic_engine *e, int role, const void *src, int rows, int cols, int spitch,
+              bool on_device, cudaStream_t st) {
+  PyramidSlot &s = e->pyr[e->role[role]];
+  int rc = shape_slot(e, s, rows, cols, e->stop);
+  if (rc) return rc;
+  rc = upload_level0(e, s, src, rows, cols, spitch, on_device, st);
+  if (rc) return rc;
+  return build_levels(e, s, e->stop, st);
+}
+
+int ensure_sector_capacity(dic_engine *e, int n) {
+  if (n <= e->cap_sectors) return DIC_OK;
+  int cap = std::max(n, std::max(16, e->cap_sectors * 2));
+  SectorDev *ds = nullptr; float *dg = nullptr; dic_result *dr = nullptr;
+  dic_result *hr = nullptr; float *hg = nullptr;
+  CU_TRY(e, cudaMalloc(&ds, sizeof(SectorDev) * cap));
+  CU_TRY(e, cudaMalloc(&dg, sizeof(float) * kMaxParams * cap));
+  CU_TRY(e, cudaMalloc(&dr, sizeof(dic_result) * cap));
+  CU_TRY(e, cudaMallocHost(&hr, sizeof(dic_result) * cap));
+  CU_TRY(e, cudaMallocHost(&hg, sizeof(float) * kMaxParams * cap));
+  CU_TRY(e, cudaMemset(ds, 0, sizeof(SectorDev) * cap));
+  CU_TRY(e, cudaMemset(dg, 0, sizeof(float) * kMaxParams * cap));
+  CU_TRY(e, cudaMemset(dr, 0, sizeof(dic_result) * cap));
+  memset(hr, 0, sizeof(dic_result) * cap);
+  memset(hg, 0, sizeof(float) * kMaxParams * cap);
+  if (e->cap_sectors) {
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    CU_TRY(e, cudaMemcpy(ds, e->d_sectors, sizeof(SectorDev) * e->cap_sectors, cudaMemcpyDeviceToDevice));
+    CU_TRY(e, cudaMemcpy(dg, e->d_guess, sizeof(float) * kMaxParams * e->cap_sectors, cudaMemcpyDeviceToDevice));
+    CU_TRY(e, cudaMemcpy(dr, e->d_results, sizeof(dic_result) * e->cap_sectors, cudaMemcpyDeviceToDevice));
+    memcpy(hr, e->h_results, sizeof(dic_result) * e->cap_sectors);
+    memcpy(hg, e->h_guess, sizeof(float) * kMaxParams * e->cap_sectors);
+    cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results);
+    cudaFreeHost(e->h_results); cudaFreeHost(e->h_guess);
+  }
+  e->d_sectors = ds; e->d_guess = dg; e->d_results = dr; e->h_results = hr; e->h_guess = hg;
+  e->cap_sectors = cap;
+  e->sectors.resize(cap);
+  return DIC_OK;
+}
+
+int ensure_counts(dic_engine *e, size_t nblocks) {
+  if (nblocks + 1 <= e->cap_counts) return DIC_OK;
+  if (e->d_counts) cudaFree(e->d_counts);
+  if (e->d_offsets) cudaFree(e->d_offsets);
+  size_t cap = nblocks + 1 + 1024;
+  CU_TRY(e, cudaMalloc(&e->d_counts, sizeof(unsigned int) * cap));
+  CU_TRY(e, cudaMalloc(&e->d_offsets, sizeof(unsigned long long) * cap));
+  e->cap_counts = cap;
+  return DIC_OK;
+}
+
+// Levels the LM loop visits (correlation_class.cpp:373) == levels that own a list
+// (pyramid_class.cpp:299-301) when (stop - start) % step == 0, which dic_reset_image_pyramids enforces.
+bool level_used(const dic_engine *e, int l) {
+  if (l == 0) return true;
+  return l >= e->start && l <= e->stop && (l - e->start) % e->step == 0 && l >= (e->start == 0 ? e->step : e->start);
+}
+
+int sector_reserve(dic_engine *e, Sector &s, size_t total) {
+  if (total > s.cap) {
+    if (s.buf) CU_TRY(e, cudaFree(s.buf));
+    s.buf = nullptr; s.cap = 0;
+    CU_TRY(e, cudaMalloc(&s.buf, sizeof(float2) * std::max<size_t>(total, 1)));
+    s.cap = std::max<size_t>(total, 1);
+  }
+  return DIC_OK;
+}
+
+int push_sector(dic_engine *e, int id) {
+  Sector &s = e->sectors[id];
+  SectorDev d;
+  memset(&d, 0, sizeof(d));
+  for (int l = 0; l < kMaxLevels; ++l) { d.xy[l] = s.xy[l]; d.n[l] = (int)s.n[l]; }
+  d.cx = s.cx; d.cy = s.cy;
+  CU_TRY(e, cudaMemcpyAsync(e->d_sectors + id, &d, sizeof(SectorDev), cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream)); // `d` lives on this stack frame
+  return DIC_OK;
+}
+
+// Runs an order-preserving compaction of `ncand` candidates; first call (out == nullptr) returns
+// the number kept, second call emits.
+template <class Pred>
+int compact_count(dic_engine *e, const Pred &pred, long ncand, long *kept) {
+  size_t nblocks = (size_t)((ncand + kCompactChunk - 1) / kCompactChunk);
+  if (nblocks == 0) { *kept = 0; return DIC_OK; }
+  int rc = ensure_counts(e, nblocks);
+  if (rc) return rc;
+  compact_kernel<Pred, false><<<(unsigned)nblocks, kCompactThreads, 0, e->stream>>>(
+      pred, ncand, e->d_counts, nullptr, nullptr);
+  scan_counts_kernel<<<1, 1024, 0, e->stream>>>(e->d_counts, (int)nblocks, e->d_offsets);
+  e->launches += 2;
+  unsigned long long total = 0;
+  CU_TRY(e, cudaMemcpyAsync(&total, e->d_offsets + nblocks, sizeof(total), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  *kept = (long)total;
+  return DIC_OK;
+}
+template <class Pred>
+int compact_emit(dic_engine *e, const Pred &pred, long ncand, float2 *out) {
+  size_t nblocks = (size_t)((ncand + kCompactChunk - 1) / kCompactChunk);
+  if (nblocks == 0) return DIC_OK;
+  compact_kernel<Pred, true><<<(unsigned)nblocks, kCompactThreads, 0, e->stream>>>(
+      pred, ncand, nullptr, e->d_offsets, out);
+  e->launches++;
+  CU_TRY(e, cudaGetLastError());
+  return DIC_OK;
+}
+
+// Derive the coarser lists of a sector from its level-0 list by the reference's successive
+// decimation (pyramid_class.cpp:298-322). Level 0 must already sit at s.buf[0 .. n0).
+int decimate_levels(dic_engine *e, Sector &s) {
+  // pass 1: counts (needs temporary storage per level: decimate into scratch after level 0)
+  // Lists shrink ~4x per level, so reserve n0/2 extra and emit level by level.
+  long n0 = s.n[0];
+  int prev = 0;
+  size_t used = (size_t)n0;
+  int first = (e->start == 0 ? e->step : e->start);
+  for (int l = first; l <= e->stop; l += e->step) {
+    DecimatePred pred{s.xy[prev], 1 << (l - prev)};
+    long kept = 0;
+    int rc = compact_count(e, pred, s.n[prev], &kept);
+    if (rc) return rc;
+    if (used + (size_t)kept > s.cap) {
+      // grow, preserving what is already there
+      size_t ncap = used + (size_t)kept + (size_t)n0 / 2 + 16;
+      float2 *nb = nullptr;
+      CU_TRY(e, cudaMalloc(&nb, sizeof(float2) * ncap));
+      CU_TRY(e, cudaMemcpyAsync(nb, s.buf, sizeof(float2) * used, cudaMemcpyDeviceToDevice, e->stream));
+      CU_TRY(e, cudaStreamSynchronize(e->stream));
+      for (int k = 0; k < kMaxLevels; ++k)
+        if (s.xy[k]) s.xy[k] = nb + (s.xy[k] - s.buf);
+      cudaFree(s.buf);
+      s.buf = nb; s.cap = ncap;
+      pred.src = s.xy[prev];
+    }
+    s.xy[l] = s.buf + used;
+    s.n[l] = kept;
+    rc = compact_emit(e, pred, s.n[prev], s.xy[l]);
+    if (rc) return rc;
+    used += (size_t)kept;
+    prev = l;
+  }
+  return DIC_OK;
+}
+
+void clear_levels(Sector &s) {
+  for (int l = 0; l < kMaxLevels; ++l) { s.xy[l] = nullptr; s.n[l] = 0; }
+}
+
+int check_levels_nonempty(dic_engine *e, const Sector &s) {
+  for (int l = e->stop; l >= e->start; l -= e->step)
+    if (s.n[l] <= 0) return DIC_ERROR_BAD_DOMAIN;
+  return DIC_OK;
+}
+
+// pyramid_class.cpp:325-347 on a host copy of the list, in the order given.
+void seq_mean(const std::vector<float2> &pts, float &cx, float &cy) {
+  volatile float sx = 0.f, sy = 0.f;
+  for (const float2 &q : pts) { sx = sx + q.x; sy = sy + q.y; }
+  cx = sx / (float)pts.size();
+  cy = sy / (float)pts.size();
+}
+
+int exact_center(dic_engine *e, Sector &s) {
+  unsigned long long *d = reinterpret_cast<unsigned long long *>(e->d_scratch);
+  CU_TRY(e, cudaMemsetAsync(d, 0, 16, e->stream));
+  int grid = std::max(1, std::min(e->num_sms * 8, (int)((s.n[0] + 255) / 256)));
+  sum_xy_kernel<<<grid, 256, 0, e->stream>>>(s.xy[0], s.n[0], d);
+  e->launches++;
+  long long h[2];
+  CU_TRY(e, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  s.cx = (float)((double)h[0] / 1024.0 / (double)s.n[0]);
+  s.cy = (float)((double)h[1] / 1024.0 / (double)s.n[0]);
+  return DIC_OK;
+}
+
+template <int MODEL, int INTERP, int MODE>
+int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
+  SolveSettings cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
+  for (int l = 0; l < kMaxLevels; ++l) { cfg.und[l] = u.lev[l]; cfg.def[l] = d.lev[l]; }
+  cfg.start = e->start; cfg.step = e->step; cfg.stop = e->stop;
+  cfg.max_iters = e->max_iters; cfg.precision = e->precision;
+  const SectorDev *sectors = e->d_sectors;
+  const float *guesses = e->d_guess;
+  dic_result *results = e->d_results;
+  GridWork *work = e->d_work;
+  float *partials = e->d_partials;
+  if (grid_mode) {
+    auto kern = gn_solve_kernel<MODEL, INTERP, MODE, true>;
+    int per_sm = 0;
+    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    if (per_sm < 1) { set_error(e, "gn_solve_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }
+    // enough CTAs for ~4 pixels per thread at the finest level, never more than co-resident
+    long n0 = e->sectors[first].n[e->start];
+    int want = (int)std::min<long>((n0 + kThreads * 4 - 1) / (kThreads * 4), (long)per_sm * e->num_sms);
+    int grid = std::max(1, std::min(want, e->max_grid));
+    int one = 1;
+    void *args[] = {&cfg, &sectors, &guesses, &results, &first, &one, &work, &partials};
+    CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, 0, e->stream));
+  } else {
+    auto kern = gn_solve_kernel<MODEL, INTERP, MODE, false>;
+    int per_sm = 0;
+    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
+    kern<<<grid, kThreads, 0, e->stream>>>(cfg, sectors, guesses, results, first, count, work, partials);
+    CU_TRY(e, cudaGetLastError());
+  }
+  e->launches++;
+  return DIC_OK;
+}
+
+template <int MODEL, int INTERP>
+int launch_solve_mode(dic_engine *e, bool grid_mode, int first, int count) {
+  if (e->mode == DIC_MODE_FAST) return launch_solve<MODEL, INTERP, DIC_MODE_FAST>(e, grid_mode, first, count);
+  return launch_solve<MODEL, INTERP, DIC_MODE_PARITY>(e, grid_mode, first, count);
+}
+template <int MODEL>
+int launch_solve_interp(dic_engine *e, bool grid_mode, int first, int count) {
+  switch (e->interp) {
+  case DIC_IM_NEAREST: return launch_solve<MODEL, DIC_IM_NEAREST, DIC_MODE_PARITY>(e, grid_mode, first, count);
+  case DIC_IM_BILINEAR: return launch_solve<MODEL, DIC_IM_BILINEAR, DIC_MODE_PARITY>(e, grid_mode, first, count);
+  default: return launch_solve_mode<MODEL, DIC_IM_BICUBIC>(e, grid_mode, first, count);
+  }
+}
+int launch_solve_any(dic_engine *e, bool grid_mode, int first, int count) {
+  switch (e->model) {
+  case DIC_FM_U: return launch_solve_interp<DIC_FM_U>(e, grid_mode, first, count);
+  case DIC_FM_UV: return launch_solve_interp<DIC_FM_UV>(e, grid_mode, first, count);
+  case DIC_FM_UVQ: return launch_solve_interp<DIC_FM_UVQ>(e, grid_mode, first, count);
+  case DIC_FM_UVUxUyVxVy: return launch_solve_interp<DIC_FM_UVUxUyVxVy>(e, grid_mode, first, count);
+  default: return launch_solve_interp<DIC_FM_QUADRATIC>(e, grid_mode, first, count);
+  }
+}
+
+template <int MODEL, int INTERP, int MODE>
+int launch_eval(dic_engine *e, int id, int level, const float *d_params, int grid) {
+  SolveSettings cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
+  for (int l = 0; l < kMaxLevels; ++l) { cfg.und[l] = u.lev[l]; cfg.def[l] = d.lev[l]; }
+  cfg.start = e->start; cfg.step = e->step; cfg.stop = e->stop;
+  gn_eval_kernel<MODEL, INTERP, MODE><<<grid, kThreads, 0, e->stream>>>(cfg, e->d_sectors + id, level,
+                                                                      d_params, e->d_partials);
+  e->launches++;
+  CU_TRY(e, cudaGetLastError());
+  return DIC_OK;
+}
+template <int MODEL>
+int launch_eval_model(dic_engine *e, int id, int level, const float *d_params, int grid) {
+  if (e->interp == DIC_IM_NEAREST) return launch_eval<MODEL, DIC_IM_NEAREST, DIC_MODE_PARITY>(e, id, level, d_params, grid);
+  if (e->interp == DIC_IM_BILINEAR) return launch_eval<MODEL, DIC_IM_BILINEAR, DIC_MODE_PARITY>(e, id, level, d_params, grid);
+  if (e->mode == DIC_MODE_FAST) return launch_eval<MODEL, DIC_IM_BICUBIC, DIC_MODE_FAST>(e, id, level, d_params, grid);
+  return launch_eval<MODEL, DIC_IM_BICUBIC, DIC_MODE_PARITY>(e, id, level, d_params, grid);
+}
+
+bool sector_ok(const dic_engine *e, int id) {
+  return id >= 0 && id < e->cap_sectors && e->sectors[id].kind != SK_NONE;
+}
+
+int images_ready(dic_engine *e) {
+  const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
+  if (!u.valid || !d.valid) { set_error(e, "image pyramids not set"); return DIC_ERROR_BAD_ARGUMENT; }
+  return DIC_OK;
+}
+
+} // namespace
+
+// =============================================================================== C ABI
+
+extern "C" {
+
+int dic_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+dic_engine *dic_create(int device) {
+  int n = dic_device_count();
+  if (device < 0 || device >= n) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  dic_engine *e = new dic_engine;
+  e->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return nullptr; }
+  e->num_sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&e->img_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming) == cudaSuccess;
+  e->max_grid = e->num_sms * 8;
+  ok = ok && cudaMalloc(&e->d_work, sizeof(GridWork)) == cudaSuccess &&
+       cudaMemset(e->d_work, 0, sizeof(GridWork)) == cudaSuccess &&
+       cudaMalloc(&e->d_partials, sizeof(float) * kAccStride * (size_t)e->max_grid) == cudaSuccess &&
+       cudaMalloc(&e->d_scratch, 4096) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); dic_destroy(e); return nullptr; }
+  return e;
+}
+
+void dic_destroy(dic_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->img_stream) cudaStreamSynchronize(e->img_stream);
+  for (auto &s : e->sectors) if (s.buf) cudaFree(s.buf);
+  for (auto &p : e->pyr) if (p.base) cudaFree(p.base);
+  cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results);
+  if (e->h_results) cudaFreeHost(e->h_results);
+  if (e->h_guess) cudaFreeHost(e->h_guess);
+  cudaFree(e->d_work); cudaFree(e->d_partials); cudaFree(e->d_scratch);
+  cudaFree(e->d_counts); cudaFree(e->d_offsets); cudaFree(e->d_stage); cudaFree(e->d_stage_img);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev_img) cudaEventDestroy(e->ev_img);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->img_stream) cudaStreamDestroy(e->img_stream);
+  delete e;
+}
+
+const char *dic_last_error(const dic_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int dic_set_max_iters(dic_engine *e, int v) { if (!e) return DIC_ERROR_BAD_ARGUMENT; e->max_iters = v; return DIC_OK; }
+int dic_set_precision(dic_engine *e, float v) { if (!e) return DIC_ERROR_BAD_ARGUMENT; e->precision = v; return DIC_OK; }
+int dic_set_fitting_model(dic_engine *e, int m) {
+  if (!e || m < DIC_FM_U || m > DIC_FM_QUADRATIC) return DIC_ERROR_BAD_ARGUMENT;
+  e->model = m; return DIC_OK;
+}
+int dic_set_interpolation_model(dic_engine *e, int m) {
+  if (!e || m < DIC_IM_NEAREST || m > DIC_IM_BICUBIC) return DIC_ERROR_BAD_ARGUMENT;
+  e->interp = m; return DIC_OK;
+}
+int dic_set_arith_mode(dic_engine *e, int m) {
+  if (!e || (m != DIC_MODE_PARITY && m != DIC_MODE_FAST)) return DIC_ERROR_BAD_ARGUMENT;
+  e->mode = m; return DIC_OK;
+}
+int dic_set_center_mode(dic_engine *e, int m) {
+  if (!e || (m != DIC_CENTER_REFERENCE && m != DIC_CENTER_EXACT)) return DIC_ERROR_BAD_ARGUMENT;
+  e->center_mode = m; return DIC_OK;
+}
+
+static int set_pyramid_range(dic_engine *e, int start, int step, int stop) {
+  if (step < 1) step = 1;
+  if (start < 0 || stop < start || stop >= kMaxLevels || (stop - start) % step != 0) {
+    set_error(e, "pyramid start/step/stop must satisfy 0 <= start <= stop < 8 and (stop-start) % step == 0");
+    return DIC_ERROR_BAD_ARGUMENT;
+  }
+  if (e->start != start || e->step != step || e->stop != stop) {
+    // level layout changes: every sector list has to be rebuilt by the caller (the reference GUI
+    // re-runs resetPolygon after a pyramid change as well, mainapp.cpp:900-912)
+    for (auto &s : e->sectors) { s.kind = SK_NONE; clear_levels(s); }
+    for (auto &p : e->pyr) p.valid = false;
+  }
+  e->start = start; e->step = step; e->stop = stop;
+  return DIC_OK;
+}
+
+static int reset_pyramids_common(dic_engine *e, const void *und, const void *def, const void *nxt,
+                                 int rows, int cols, int pitch, bool on_device, int start, int step,
+                                 int stop) {
+  if (!e || !und || !def || rows < 8 || cols < 8) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = set_pyramid_range(e, start, step, stop);
+  if (rc) return rc;
+  if ((rc = set_image(e, 0, und, rows, cols, pitch, on_device, e->stream))) return rc;
+  if ((rc = set_image(e, 1, def, rows, cols, pitch, on_device, e->stream))) return rc;
+  if (nxt && (rc = set_image(e, 2, nxt, rows, cols, pitch, on_device, e->stream))) return rc;
+  if (!on_device) CU_TRY(e, cudaStreamSynchronize(e->stream)); // caller may reuse its buffers
+  return DIC_OK;
+}
+
+int dic_reset_image_pyramids(dic_engine *e, const uint8_t *und, const uint8_t *def, const uint8_t *nxt,
+                             int rows, int cols, int channels, int start, int step, int stop) {
+  if (channels != 1) { if (e) set_error(e, "only monochrome images are implemented"); return DIC_ERROR_BAD_ARGUMENT; }
+  return reset_pyramids_common(e, und, def, nxt, rows, cols, cols, false, start, step, stop);
+}
+int dic_reset_image_pyramids_device(dic_engine *e, const void *und, const void *def, const void *nxt,
+                                    int rows, int cols, int pitch, int start, int step, int stop) {
+  return reset_pyramids_common(e, und, def, nxt, rows, cols, pitch, true, start, step, stop);
+}
+
+int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols) {
+  if (!e || !nxt) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = set_image(e, 2, nxt, rows, cols, cols, false, e->img_stream);
+  if (rc) return rc;
+  CU_TRY(e, cudaStreamSynchronize(e->img_stream));
+  return DIC_OK;
+}
+int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt, int rows, int cols, int pitch) {
+  if (!e || !nxt) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = set_image(e, 2, nxt, rows, cols, pitch, true, e->img_stream);
+  if (rc) return rc;
+  CU_TRY(e, cudaEventRecord(e->ev_img, e->img_stream));
+  CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_img, 0));
+  return DIC_OK;
+}
+int dic_reset_def_pyramid(dic_engine *e, const uint8_t *def, int rows, int cols) {
+  if (!e || !def) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = set_image(e, 1, def, rows, cols, cols, false, e->stream);
+  if (rc) return rc;
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return DIC_OK;
+}
+int dic_reset_def_pyramid_device(dic_engine *e, const void *def, int rows, int cols, int pitch) {
+  if (!e || !def) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  return set_image(e, 1, def, rows, cols, pitch, true, e->stream);
+}
+
+int dic_make_und_pyramid_from_def(dic_engine *e) {
+  if (!e) return DIC_ERROR_BAD_ARGUMENT;
+  // pyramid_class.cpp:211-226: und takes def's images, def becomes empty
+  std::swap(e->role[0], e->role[1]);
+  e->pyr[e->role[1]].valid = false;
+  return DIC_OK;
+}
+int dic_make_def_pyramid_from_nxt(dic_engine *e) {
+  if (!e) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  // pyramid_class.cpp:228-243
+  CU_TRY(e, cudaEventRecord(e->ev_img, e->img_stream));
+  CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_img, 0));
+  std::swap(e->role[1], e->role[2]);
+  e->pyr[e->role[2]].valid = false;
+  return DIC_OK;
+}
+
+// ------------------------------------------------------------------ domains
+
+static int begin_sector(dic_engine *e, int id, Sector **out) {
+  if (!e || id < 0 || id > (1 << 24)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = ensure_sector_capacity(e, id + 1);
+  if (rc) return rc;
+  Sector &s = e->sectors[id];
+  s.kind = SK_NONE;
+  s.pending = false;
+  clear_levels(s);
+  *out = &s;
+  return DIC_OK;
+}
+
+int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1) {
+  Sector *sp;
+  int rc = begin_sector(e, id, &sp);
+  if (rc) return rc;
+  Sector &s = *sp;
+  if (x1 < x0 || y1 < y0) return DIC_ERROR_BAD_DOMAIN;
+  // per level: multiples of 2^l inside [x0, x1] x [y0, y1] (successive decimation of integer
+  // points by pyramid_class.cpp:306-316 is exactly that)
+  struct Lv { int l, xs, ys, nx, ny, mag; } lv[kMaxLevels];
+  int nl = 0;
+  size_t total = 0;
+  for (int l = 0; l <= e->stop; ++l) {
+    if (!level_used(e, l)) continue;
+    int mag = 1 << l;
+    auto first_mult = [mag](int a) { int q = a / mag; if (q * mag < a) ++q; return q * mag; };
+    auto last_mult = [mag](int a) { int q = a / mag; if (q * mag > a) --q; return q * mag; };
+    int xs = first_mult(x0), xe = last_mult(x1), ys = first_mult(y0), ye = last_mult(y1);
+    int nx = xe >= xs ? (xe - xs) / mag + 1 : 0, ny = ye >= ys ? (ye - ys) / mag + 1 : 0;
+    lv[nl++] = Lv{l, xs, ys, nx, ny, mag};
+    total += (size_t)nx * ny;
+  }
+  if ((rc = sector_reserve(e, s, total))) return rc;
+  size_t used = 0;
+  for (int k = 0; k < nl; ++k) {
+    long n = (long)lv[k].nx * lv[k].ny;
+    s.xy[lv[k].l] = s.buf + used;
+    s.n[lv[k].l] = n;
+    if (n > 0) {
+      rect_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(s.xy[lv[k].l], n, lv[k].xs,
+                                                                          lv[k].ys, lv[k].nx, lv[k].mag);
+      e->launches++;
+    }
+    used += (size_t)n;
+  }
+  CU_TRY(e, cudaGetLastError());
+  s.cx = (float)(x0 + x1) * 0.5f; // what the manager passes: the sector's integer centre
+  s.cy = (float)(y0 + y1) * 0.5f;
+  s.rx0 = x0; s.ry0 = y0; s.rx1 = x1; s.ry1 = y1;
+  s.integer_grid = true;
+  if ((rc = check_levels_nonempty(e, s))) return rc;
+  s.kind = SK_RECT;
+  return push_sector(e, id);
+}
+
+// Host restatement of the box / corner set-up of manager_class.cpp:838-895 (fp32, same order).
+struct AnnulusGeom {
+  int x0, y0, x1, y1;
+  float c00x = 0, c01x = 0, c10x = 0, c11x = 0, c00y = 0, c01y = 0, c10y = 0, c11y = 0;
+  float ri2, ro2;
+};
+static AnnulusGeom annulus_geom(float r, float dr, float a, float da, float cx, float cy, int as) {
+  AnnulusGeom g;
+  if (as == 1) {
+    g.x0 = (int)(cx - (r + dr)); g.x1 = (int)(cx + (r + dr));
+    g.y0 = (int)(cy - (r + dr)); g.y1 = (int)(cy + (r + dr));
+  } else {
+    float sin0 = (float)std::sin((double)a), cos0 = (float)std::cos((double)a);
+    float sin1 = (float)std::sin((double)(a + da)), cos1 = (float)std::cos((double)(a + da));
+    float sin2 = (float)std::sin((double)(a + da / 2.f)), cos2 = (float)std::cos((double)(a + da / 2.f));
+    volatile float t;
+    t = r * cos0; g.c00x = cx + t;
+    t = r * cos1; g.c01x = cx + t;
+    t = (r + dr) * cos0; t = t * 1.2f; g.c10x = cx + t;
+    t = (r + dr) * cos1; t = t * 1.2f; g.c11x = cx + t;
+    t = r * sin0; g.c00y = cy + t;
+    t = r * sin1; g.c01y = cy + t;
+    t = (r + dr) * sin0; t = t * 1.2f; g.c10y = cy + t;
+    t = (r + dr) * sin1; t = t * 1.2f; g.c11y = cy + t;
+    t = (r + dr) * cos2; float arc_x = cx + t;
+    t = (r + dr) * sin2; float arc_y = cy + t;
+    g.x0 = (int)std::min(arc_x, std::min(std::min(g.c00x, g.c01x), std::min(g.c10x, g.c11x)));
+    g.x1 = (int)std::max(arc_x, std::max(std::max(g.c00x, g.c01x), std::max(g.c10x, g.c11x)));
+    g.y0 = (int)std::min(arc_y, std::min(std::min(g.c00y, g.c01y), std::min(g.c10y, g.c11y)));
+    g.y1 = (int)std::max(arc_y, std::max(std::max(g.c00y, g.c01y), std::max(g.c10y, g.c11y)));
+  }
+  volatile float ro = r + dr;
+  g.ro2 = ro * ro;
+  g.ri2 = r * r;
+  return g;
+}
+
+// The sequential fp32 centre of the CPU engine for an annulus: its list order is x outer,
+// y inner (manager_class.cpp:902-919), so walk the box that way with the same predicate.
+static void annulus_reference_center(const AnnulusGeom &g, float cx, float cy, int as, float &ocx,
+                                     float &ocy, long &count) {
+  volatile float sx = 0.f, sy = 0.f;
+  long n = 0;
+  for (float i = (float)g.x0; i < (float)g.x1; ++i)
+    for (int j = g.y0; j < g.y1; ++j) {
+      volatile float ax = i - cx, ay = (float)j - cy;
+      volatile float ax2 = ax * ax, ay2 = ay * ay;
+      float r2 = ax2 + ay2;
+      if (r2 > g.ri2 && r2 < g.ro2) {
+        bool in = true;
+        if (as != 1) {
+          volatile float a1 = g.c11x - i, b1 = g.c01y - g.c11y, a2 = g.c11y - (float)j, b2 = g.c01x - g.c11x;
+          volatile float m1 = a1 * b1, m2 = a2 * b2;
+          float cross1 = m1 - m2;
+          volatile float a3 = g.c00x - i, b3 = g.c10y - g.c00y, a4 = g.c00y - (float)j, b4 = g.c10x - g.c00x;
+          volatile float m3 = a3 * b3, m4 = a4 * b4;
+          float cross2 = m3 - m4;
+          volatile float pr = cross1 * cross2;
+          in = pr > 0.f;
+        }
+        if (in) { sx = sx + i; sy = sy + (float)j; ++n; }
+      }
+    }
+  count = n;
+  ocx = n ? sx / (float)n : cx;
+  ocy = n ? sy / (float)n : cy;
+}
+
+int dic_reset_polygon_annular(dic_engine *e, int id, float r, float dr, float a, float da, float cx,
+                              float cy, int as) {
+  Sector *sp;
+  int rc = begin_sector(e, id, &sp);
+  if (rc) return rc;
+  Sector &s = *sp;
+  if (as < 1 || dr <= 0.f) return DIC_ERROR_BAD_DOMAIN;
+  AnnulusGeom g = annulus_geom(r, dr, a, da, cx, cy, as);
+  if (g.x1 <= g.x0 || g.y1 <= g.y0) return DIC_ERROR_BAD_DOMAIN;
+  AnnulusPred pred[kMaxLevels];
+  long ncand[kMaxLevels] = {}, kept[kMaxLevels] = {};
+  int lvl[kMaxLevels], nl = 0;
+  size_t total = 0;
+  for (int l = 0; l <= e->stop; ++l) {
+    if (!level_used(e, l)) continue;
+    int mag = 1 << l;
+    auto first_mult = [mag](int v) { int q = v / mag; if (q * mag < v) ++q; return q * mag; };
+    int xs = first_mult(g.x0), ys = first_mult(g.y0);
+    int nxc = xs < g.x1 ? (g.x1 - 1 - xs) / mag + 1 : 0;
+    int nyc = ys < g.y1 ? (g.y1 - 1 - ys) / mag + 1 : 0;
+    AnnulusPred p;
+    p.xs = xs; p.ys = ys; p.nxc = std::max(nxc, 1); p.mag = mag; p.as = as;
+    p.cx = cx; p.cy = cy; p.ri2 = g.ri2; p.ro2 = g.ro2;
+    p.c00x = g.c00x; p.c01x = g.c01x; p.c10x = g.c10x; p.c11x = g.c11x;
+    p.c00y = g.c00y; p.c01y = g.c01y; p.c10y = g.c10y; p.c11y = g.c11y;
+    pred[nl] = p; ncand[nl] = (long)nxc * nyc; lvl[nl] = l;
+    if ((rc = compact_count(e, p, ncand[nl], &kept[nl]))) return rc;
+    total += (size_t)kept[nl];
+    ++nl;
+  }
+  if ((rc = sector_reserve(e, s, total))) return rc;
+  size_t used = 0;
+  for (int k = 0; k < nl; ++k) {
+    s.xy[lvl[k]] = s.buf + used;
+    s.n[lvl[k]] = kept[k];
+    if (kept[k] > 0) {
+      // offsets of this level's count pass were overwritten by later levels: recount, then emit
+      long again = 0;
+      if ((rc = compact_count(e, pred[k], ncand[k], &again))) return rc;
+      if ((rc = compact_emit(e, pred[k], ncand[k], s.xy[lvl[k]]))) return rc;
+    }
+    used += (size_t)kept[k];
+  }
+  s.integer_grid = true;
+  if ((rc = check_levels_nonempty(e, s))) return rc;
+  if (e->center_mode == DIC_CENTER_REFERENCE) {
+    long cnt = 0;
+    annulus_reference_center(g, cx, cy, as, s.cx, s.cy, cnt);
+    if (cnt != s.n[0]) { set_error(e, "annulus: host/device membership mismatch"); return DIC_ERROR_BAD_DOMAIN; }
+  } else if ((rc = exact_center(e, s))) {
+    return rc;
+  }
+  s.kind = SK_ANNULAR;
+  return push_sector(e, id);
+}
+
+static int finish_list_sector(dic_engine *e, int id, Sector &s, SectorKind kind, int use_center, float cx,
+                              float cy, const std::vector<float2> *host_list) {
+  int rc = decimate_levels(e, s);
+  if (rc) return rc;
+  if ((rc = check_levels_nonempty(e, s))) return rc;
+  if (use_center) {
+    s.cx = cx; s.cy = cy;
+  } else if (e->center_mode == DIC_CENTER_REFERENCE) {
+    std::vector<float2> tmp;
+    if (!host_list) {
+      tmp.resize(s.n[0]);
+      CU_TRY(e, cudaMemcpyAsync(tmp.data(), s.xy[0], sizeof(float2) * s.n[0], cudaMemcpyDeviceToHost, e->stream));
+      CU_TRY(e, cudaStreamSynchronize(e->stream));
+      host_list = &tmp;
+    }
+    seq_mean(*host_list, s.cx, s.cy);
+  } else if ((rc = exact_center(e, s))) {
+    return rc;
+  }
+  s.kind = kind;
+  return push_sector(e, id);
+}
+
+int dic_reset_polygon_blob(dic_engine *e, int id, const float *contour_xy, int n_vertices) {
+  Sector *sp;
+  int rc = begin_sector(e, id, &sp);
+  if (rc) return rc;
+  Sector &s = *sp;
+  if (!contour_xy || n_vertices < 3) return DIC_ERROR_BAD_DOMAIN;
+  BlobPolygon poly(contour_xy, n_vertices);
+  if (poly.bad()) return DIC_ERROR_BAD_DOMAIN; // manager_class.cpp:1026-1030
+  std::vector<HostSpan> hs = poly.spans();
+  std::vector<Span> spans(hs.size());
+  long total = 0;
+  for (size_t i = 0; i < hs.size(); ++i) {
+    spans[i] = Span{hs[i].y, hs[i].xb, hs[i].xe, total};
+    total += hs[i].xe - hs[i].xb;
+  }
+  if (total <= 0) return DIC_ERROR_BAD_DOMAIN;
+  if ((rc = sector_reserve(e, s, (size_t)total + (size_t)total / 2 + 16))) return rc;
+  size_t bytes = sizeof(Span) * spans.size();
+  if (bytes > e->cap_stage) {
+    if (e->d_stage) cudaFree(e->d_stage);
+    e->d_stage = nullptr; e->cap_stage = 0;
+    CU_TRY(e, cudaMalloc(&e->d_stage, bytes * 2));
+    e->cap_stage = bytes * 2;
+  }
+  CU_TRY(e, cudaMemcpyAsync(e->d_stage, spans.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+  s.xy[0] = s.buf; s.n[0] = total;
+  expand_spans_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
+      reinterpret_cast<const Span *>(e->d_stage), (int)spans.size(), total, s.buf);
+  e->launches++;
+  CU_TRY(e, cudaGetLastError());
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  s.integer_grid = true;
+  if (e->center_mode == DIC_CENTER_REFERENCE) {
+    // sequential fp32 mean in emission order, straight from the spans (no list download)
+    volatile float sx = 0.f, sy = 0.f;
+    for (const HostSpan &h : hs)
+      for (int i = h.xb; i < h.xe; ++i) { sx = sx + (float)i; sy = sy + (float)h.y; }
+    return finish_list_sector(e, id, s, SK_BLOB, 1, sx / (float)total, sy / (float)total, nullptr);
+  }
+  return finish_list_sector(e, id, s, SK_BLOB, 0, 0.f, 0.f, nullptr);
+}
+
+int dic_reset_polygon_points(dic_engine *e, int id, const float *xy, int64_t n, int use_center, float cx,
+                             float cy) {
+  Sector *sp;
+  int rc = begin_sector(e, id, &sp);
+  if (rc) return rc;
+  Sector &s = *sp;
+  if (!xy || n <= 0) return DIC_ERROR_BAD_DOMAIN;
+  if ((rc = sector_reserve(e, s, (size_t)n + (size_t)n / 2 + 16))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(s.buf, xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  s.xy[0] = s.buf; s.n[0] = (long)n;
+  s.integer_grid = false;
+  std::vector<float2> host;
+  if (!use_center && e->center_mode == DIC_CENTER_REFERENCE)
+    host.assign(reinterpret_cast<const float2 *>(xy), reinterpret_cast<const float2 *>(xy) + n);
+  return finish_list_sector(e, id, s, SK_POINTS, use_center, cx, cy, host.empty() ? nullptr : &host);
+}
+
+int dic_set_polygon_center(dic_engine *e, int id, float cx, float cy) {
+  if (!e || !sector_ok(e, id)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  e->sectors[id].cx = cx; e->sectors[id].cy = cy;
+  return push_sector(e, id);
+}
+
+int dic_update_polygon(dic_engine *e, int id, int deformation_description) {
+  if (!e || !sector_ok(e, id)) return DIC_ERROR_BAD_ARGUMENT;
+  if (deformation_description == DIC_DEF_EULERIAN) return DIC_OK; // cuda_polygon.cu:268-275
+  set_error(e, "Lagrangian domain updates are not implemented yet (SURVEY 8f rank 1)");
+  return DIC_ERROR_BAD_ARGUMENT;
+}
+
+// ------------------------------------------------------------------ correlate
+
+static int enqueue_correlate(dic_engine *e, int first, int count, const float *guesses, bool grid_mode) {
+  int rc = images_ready(e);
+  if (rc) return rc;
+  const int np = np_of(e);
+  for (int i = 0; i < count; ++i) {
+    if (!sector_ok(e, first + i)) { set_error(e, "unknown sector"); return DIC_ERROR_BAD_ARGUMENT; }
+    float *g = e->h_guess + (size_t)(first + i) * kMaxParams;
+    for (int k = 0; k < kMaxParams; ++k) g[k] = k < np ? guesses[(size_t)i * np + k] : 0.f;
+    e->sectors[first + i].pending = true;
+  }
+  CU_TRY(e, cudaMemcpyAsync(e->d_guess + (size_t)first * kMaxParams, e->h_guess + (size_t)first * kMaxParams,
+                            sizeof(float) * kMaxParams * count, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  rc = launch_solve_any(e, grid_mode, first, count);
+  if (rc) return rc;
+  CU_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  e->timing_pending = true;
+  CU_TRY(e, cudaMemcpyAsync(e->h_results + first, e->d_results + first, sizeof(dic_result) * count,
+                            cudaMemcpyDeviceToHost, e->stream));
+  return DIC_OK;
+}
+
+static int collect(dic_engine *e, int first, int count, float *guesses_out, dic_result *results) {
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (e->timing_pending) {
+    cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+    e->timing_pending = false;
+  }
+  const int np = np_of(e);
+  int worst = DIC_OK;
+  for (int i = 0; i < count; ++i) {
+    const dic_result &r = e->h_results[first + i];
+    e->sectors[first + i].pending = false;
+    if (results) results[i] = r;
+    if (guesses_out)
+      for (int k = 0; k < np; ++k) guesses_out[(size_t)i * np + k] = r.resultingParameters[k];
+    if (r.errorCode != DIC_OK && worst == DIC_OK) worst = r.errorCode;
+  }
+  return worst;
+}
+
+int dic_correlate_async(dic_engine *e, int id, const float *guess) {
+  if (!e || !guess) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  return enqueue_correlate(e, id, 1, guess, true);
+}
+int dic_correlate_wait(dic_engine *e, int id, float *guess_out, dic_result *out) {
+  if (!e || !sector_ok(e, id)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  return collect(e, id, 1, guess_out, out);
+}
+int dic_correlate(dic_engine *e, int id, float *guess_inout, dic_result *out) {
+  int rc = dic_correlate_async(e, id, guess_inout);
+  if (rc) return rc;
+  return collect(e, id, 1, guess_inout, out);
+}
+int dic_correlate_batch(dic_engine *e, int first, int n, float *guesses_inout, dic_result *results) {
+  if (!e || !guesses_inout || n <= 0) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = enqueue_correlate(e, first, n, guesses_inout, false);
+  if (rc) return rc;
+  return collect(e, first, n, guesses_inout, results);
+}
+
+// ------------------------------------------------------------------ read-back / introspection
+
+static int download_list(dic_engine *e, const float2 *d, long n, std::vector<float2> &h) {
+  h.resize((size_t)n);
+  if (n == 0) return DIC_OK;
+  CU_TRY(e, cudaMemcpyAsync(h.data(), d, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return DIC_OK;
+}
+
+static void to_reference_order(const Sector &s, std::vector<float2> &h) {
+  // rect / annulus lists are stored row-major for coalescing; the CPU engine builds them x-outer,
+  // y-inner (manager_class.cpp:1607-1611, :902-919)
+  if (s.kind == SK_RECT || s.kind == SK_ANNULAR)
+    std::stable_sort(h.begin(), h.end(), [](const float2 &a, const float2 &b) {
+      return a.x < b.x || (a.x == b.x && a.y < b.y);
+    });
+}
+
+int dic_get_level_points(dic_engine *e, int id, int level, float *xy, int64_t cap, int64_t *n_needed) {
+  if (!e || !sector_ok(e, id) || level < 0 || level >= kMaxLevels) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  const Sector &s = e->sectors[id];
+  if (n_needed) *n_needed = s.n[level];
+  if (!xy || cap <= 0) return DIC_OK;
+  std::vector<float2> h;
+  int rc = download_list(e, s.xy[level], s.n[level], h);
+  if (rc) return rc;
+  to_reference_order(s, h);
+  memcpy(xy, h.data(), sizeof(float2) * (size_t)std::min<int64_t>(cap, s.n[level]));
+  return DIC_OK;
+}
+int dic_get_und_xy0(dic_engine *e, int id, float *xy, int64_t cap, int64_t *n_needed) {
+  return dic_get_level_points(e, id, 0, xy, cap, n_needed);
+}
+
+int dic_get_def_xy0(dic_engine *e, int id, float *xy, int64_t cap, int64_t *n_needed) {
+  if (!e || !sector_ok(e, id)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  const Sector &s = e->sectors[id];
+  if (n_needed) *n_needed = s.n[0];
+  if (!xy || cap <= 0) return DIC_OK;
+  // correlation_class.cpp:884-896: the model applied to the level-0 list with the last result
+  const int np = np_of(e);
+  float *d_params = e->d_scratch + 512;
+  CU_TRY(e, cudaMemcpyAsync(d_params, e->h_results[id].resultingParameters, sizeof(float) * np,
+                            cudaMemcpyHostToDevice, e->stream));
+  float2 *tmp = nullptr;
+  CU_TRY(e, cudaMalloc(&tmp, sizeof(float2) * (size_t)s.n[0]));
+  unsigned grid = (unsigned)((s.n[0] + 255) / 256);
+  switch (e->model) {
+  case DIC_FM_U: warp_list_kernel<DIC_FM_U><<<grid, 256, 0, e->stream>>>(s.xy[0], s.n[0], d_params, s.cx, s.cy, tmp); break;
+  case DIC_FM_UV: warp_list_kernel<DIC_FM_UV><<<grid, 256, 0, e->stream>>>(s.xy[0], s.n[0], d_params, s.cx, s.cy, tmp); break;
+  case DIC_FM_UVQ: warp_list_kernel<DIC_FM_UVQ><<<grid, 256, 0, e->stream>>>(s.xy[0], s.n[0], d_params, s.cx, s.cy, tmp); break;
+  case DIC_FM_UVUxUyVxVy: warp_list_kernel<DIC_FM_UVUxUyVxVy><<<grid, 256, 0, e->stream>>>(s.xy[0], s.n[0], d_params, s.cx, s.cy, tmp); break;
+  default: warp_list_kernel<DIC_FM_QUADRATIC><<<grid, 256, 0, e->stream>>>(s.xy[0], s.n[0], d_params, s.cx, s.cy, tmp); break;
+  }
+  e->launches++;
+  // keep the pairing with the reference-ordered und list: sort by the und key
+  std::vector<float2> hu, hd;
+  int rc = download_list(e, s.xy[0], s.n[0], hu);
+  if (!rc) rc = download_list(e, tmp, s.n[0], hd);
+  cudaFree(tmp);
+  if (rc) return rc;
+  if (s.kind == SK_RECT || s.kind == SK_ANNULAR) {
+    std::vector<size_t> idx(hu.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+      return hu[a].x < hu[b].x || (hu[a].x == hu[b].x && hu[a].y < hu[b].y);
+    });
+    std::vector<float2> t(hd.size());
+    for (size_t i = 0; i < idx.size(); ++i) t[i] = hd[idx[i]];
+    hd.swap(t);
+  }
+  memcpy(xy, hd.data(), sizeof(float2) * (size_t)std::min<int64_t>(cap, s.n[0]));
+  return DIC_OK;
+}
+
+int dic_get_level_center(dic_engine *e, int id, int level, float *cx, float *cy) {
+  if (!e || !sector_ok(e, id) || level < 0 || level >= kMaxLevels) return DIC_ERROR_BAD_ARGUMENT;
+  float inv = 1.f / (float)(1 << level);
+  if (cx) *cx = e->sectors[id].cx * inv;
+  if (cy) *cy = e->sectors[id].cy * inv;
+  return DIC_OK;
+}
+
+int dic_get_pyramid_level(dic_engine *e, int which, int level, uint8_t *out, int *rows, int *cols) {
+  if (!e || which < 0 || which > 2 || level < 0 || level > e->stop) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  const PyramidSlot &s = e->pyr[e->role[which]];
+  if (!s.valid) return DIC_ERROR_BAD_ARGUMENT;
+  const LevelImage &li = s.lev[level];
+  if (rows) *rows = li.rows;
+  if (cols) *cols = li.cols;
+  if (!out) return DIC_OK;
+  cudaStream_t st = which == 2 ? e->img_stream : e->stream;
+  CU_TRY(e, cudaMemcpy2DAsync(out, li.cols, li.ptr, li.pitch, li.cols, li.rows, cudaMemcpyDeviceToHost, st));
+  CU_TRY(e, cudaStreamSynchronize(st));
+  return DIC_OK;
+}
+
+int dic_evaluate(dic_engine *e, int id, int level, const float *params, float *A, float *b, float *chi,
+                 int *n_oob) {
+  if (!e || !sector_ok(e, id) || !params || level < 0 || level > e->stop) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  int rc = images_ready(e);
+  if (rc) return rc;
+  const Sector &s = e->sectors[id];
+  if (s.n[level] <= 0) return DIC_ERROR_BAD_DOMAIN;
+  const int np = np_of(e);
+  const int nacc = np * (np + 1) / 2 + np + 2;
+  float *d_params = e->d_scratch + 512;
+  float *d_out = e->d_scratch;
+  CU_TRY(e, cudaMemcpyAsync(d_params, params, sizeof(float) * np, cudaMemcpyHostToDevice, e->stream));
+  int grid = (int)std::max<long>(1, std::min<long>((s.n[level] + kThreads * 4 - 1) / (kThreads * 4), e->max_grid));
+  switch (e->model) {
+  case DIC_FM_U: rc = launch_eval_model<DIC_FM_U>(e, id, level, d_params, grid); break;
+  case DIC_FM_UV: rc = launch_eval_model<DIC_FM_UV>(e, id, level, d_params, grid); break;
+  case DIC_FM_UVQ: rc = launch_eval_model<DIC_FM_UVQ>(e, id, level, d_params, grid); break;
+  case DIC_FM_UVUxUyVxVy: rc = launch_eval_model<DIC_FM_UVUxUyVxVy>(e, id, level, d_params, grid); break;
+  default: rc = launch_eval_model<DIC_FM_QUADRATIC>(e, id, level, d_params, grid); break;
+  }
+  if (rc) return rc;
+  sum_partials_kernel<<<1, 128, 0, e->stream>>>(e->d_partials, grid, nacc, d_out);
+  e->launches++;
+  float h[kAccStride];
+  CU_TRY(e, cudaMemcpyAsync(h, d_out, sizeof(float) * nacc, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  int k = 0;
+  for (int p1 = 0; p1 < np; ++p1)
+    for (int p2 = 0; p2 < np; ++p2) A[p1 * np + p2] = 0.f;
+  for (int p1 = 0; p1 < np; ++p1)
+    for (int p2 = p1; p2 < np; ++p2) A[p1 * np + p2] = h[k++];
+  for (int p = 0; p < np; ++p) b[p] = h[k++];
+  if (chi) *chi = h[k];
+  if (n_oob) *n_oob = (int)(h[k + 1] + 0.5f);
+  return DIC_OK;
+}
+
+int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float lambda, float scaling,
+                   float *dp) {
+  if (!e || !A_upper || !b || !dp) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  const int np = np_of(e);
+  float h[kAccStride];
+  int k = 0;
+  for (int p1 = 0; p1 < np; ++p1)
+    for (int p2 = p1; p2 < np; ++p2) h[k++] = A_upper[p1 * np + p2];
+  for (int p = 0; p < np; ++p) h[k++] = b[p];
+  float *d_tot = e->d_scratch, *d_dp = e->d_scratch + 256;
+  int *d_ok = reinterpret_cast<int *>(e->d_scratch + 300);
+  CU_TRY(e, cudaMemcpyAsync(d_tot, h, sizeof(float) * k, cudaMemcpyHostToDevice, e->stream));
+  switch (np) {
+  case 1: solve_step_kernel<1><<<1, 32, 0, e->stream>>>(d_tot, scaling, lambda, d_dp, d_ok); break;
+  case 2: solve_step_kernel<2><<<1, 32, 0, e->stream>>>(d_tot, scaling, lambda, d_dp, d_ok); break;
+  case 3: solve_step_kernel<3><<<1, 32, 0, e->stream>>>(d_tot, scaling, lambda, d_dp, d_ok); break;
+  case 6: solve_step_kernel<6><<<1, 32, 0, e->stream>>>(d_tot, scaling, lambda, d_dp, d_ok); break;
+  default: solve_step_kernel<12><<<1, 32, 0, e->stream>>>(d_tot, scaling, lambda, d_dp, d_ok); break;
+  }
+  e->launches++;
+  int ok = 0;
+  CU_TRY(e, cudaMemcpyAsync(dp, d_dp, sizeof(float) * np, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return ok ? DIC_OK : DIC_ERROR_SOLVER;
+}
+
+float dic_last_correlate_ms(dic_engine *e) { return e ? e->last_ms : 0.f; }
+int64_t dic_kernel_launches(const dic_engine *e) { return e ? (int64_t)e->launches.load() : 0; }
+void *dic_correlation_stream(dic_engine *e) { return e ? (void *)e->stream : nullptr; }
+int dic_synchronize(dic_engine *e) {
+  if (!e) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->img_stream));
+  return DIC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,600 @@
+// dic_kernels.cuh -- the CUDA kernels of the B200 DIC engine (sm_100a).
+//
+//   gn_solve_kernel     one launch per correlate(): every pyramid level, every LM iteration, the
+//                       reduction and the 6x6 / 12x12 solve stay on the device
+//                       (replaces kCorrelation + k_global_reduction + k_build_LS_problem_in_GPU0 +
+//                        cuSOLVER + kUpdateParameters + kScale and the per-iteration host sync of
+//                        cuda_class.cu:104-473; semantics of correlation_class.cpp:349-640)
+//   gn_eval_kernel      one evaluation only (parity tests: A, b, chi per evaluation)
+//   pyramid_level_kernel  pyramid_class.cpp:52-134, bit-exact
+//   list builders       manager_class.cpp:1596-1614 / :816-940, pyramid_class.cpp:289-323
+#pragma once
+#include <float.h>
+
+#include "dic_device.cuh"
+
+namespace dic {
+
+constexpr int kAccStride = 96; // floats per CTA partial record (>= Acc<12>::kN = 92)
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------ LM state machine
+
+// Executed by ONE full warp after every evaluation. tot = the evaluation's reduced sums.
+// Restates correlation_class.cpp:373-591 as "what to evaluate next"; parameter vectors are held
+// one element per lane.
+template <int MODEL>
+__device__ void lm_step(volatile LMState *s, const float *tot, const SolveSettings &cfg,
+                        const SectorDev *sec, dic_result *result, float *smem) {
+  constexpr int NP = model_nparams(MODEL);
+  using L = Acc<NP>;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < NP;
+  const int li = act ? lane : 0;
+  const float min_lambda = 1e-9f, max_lambda = 1e9f;
+
+  int level = s->level, level_old = s->level_old, phase = s->phase;
+  int iteration = s->iteration, use_saved = s->use_saved;
+  int error_code = s->error_code, reached = s->reached_iterations;
+  float lambda = s->lambda, last_good_chi = s->last_good_chi, scaling = s->scaling;
+  float e_p = s->p[li], e_mp = s->mp[li], e_lg = s->last_good[li];
+  float e_tent = s->tentative[li], e_saved = s->saved[li];
+  int evals = s->evals[level] + 1, iters = s->iters[level];
+  const int this_level = level;
+
+  const float chi = tot[L::kChi] * scaling;
+  const bool oob = tot[L::kOob] > 0.5f;
+  float *dp = smem + NP * (NP + 1);
+  bool end_level = false, finish = false, begin_iter = false;
+  __syncwarp();
+
+  if (phase == PH_INIT) {
+    // correlation_class.cpp:410-439
+    bool ok = !oob;
+    if (ok) {
+      last_good_chi = chi;
+      ok = warp_solve<NP>(tot, scaling, lambda, smem, dp);
+      if (!ok) error_code = DIC_ERROR_SOLVER;
+    } else {
+      error_code = DIC_ERROR_INTERPOLATION_OUT_OF_IMAGE;
+    }
+    if (!ok) { // :413-419: give up on the whole pyramid
+      e_mp = e_p;
+      level_old = level;
+      finish = true;
+    } else {
+      e_saved = e_p + dp[li];
+      e_mp = e_saved;
+      use_saved = 1;
+      iteration = 1;
+      begin_iter = true;
+    }
+  } else if (phase == PH_REDO) {
+    // :475-499, parameters evaluated were last_good
+    bool ok = !oob;
+    if (ok) {
+      ok = warp_solve<NP>(tot, scaling, lambda, smem, dp);
+      if (!ok) error_code = DIC_ERROR_SOLVER;
+    } else {
+      error_code = DIC_ERROR_INTERPOLATION_OUT_OF_IMAGE;
+    }
+    if (!ok) {
+      e_mp = e_lg;
+      end_level = true;
+    } else {
+      e_tent = e_lg + dp[li];
+      e_mp = e_tent;
+      e_p = e_tent;
+      phase = PH_TENT;
+    }
+  } else {
+    // :503-585, parameters evaluated were tentative
+    bool ok = !oob;
+    if (ok) {
+      ok = warp_solve<NP>(tot, scaling, fmaxf(lambda * 0.4f, min_lambda), smem, dp);
+      if (!ok) error_code = DIC_ERROR_SOLVER;
+    } else {
+      error_code = DIC_ERROR_INTERPOLATION_OUT_OF_IMAGE;
+    }
+    if (!ok) {
+      e_mp = e_tent;
+      end_level = true;
+    } else {
+      e_saved = e_tent + dp[li];
+      e_mp = e_saved;
+      float delta_chi = fabsf((last_good_chi - chi) / (fmaxf(last_good_chi, chi) + cfg.precision));
+      if (chi <= last_good_chi) {
+        last_good_chi = chi;
+        lambda = fmaxf(lambda * 0.4f, min_lambda);
+        e_lg = e_tent;
+        use_saved = 1;
+      } else {
+        lambda = fminf(lambda * 10.0f, max_lambda);
+        use_saved = 0;
+      }
+      if (delta_chi < cfg.precision) end_level = true;
+      else { ++iteration; begin_iter = true; }
+    }
+  }
+
+  if (begin_iter) { // :441-467
+    if (iteration > cfg.max_iters || lambda >= max_lambda) {
+      error_code = DIC_ERROR_MAX_ITERS_REACHED;
+      end_level = true;
+    } else {
+      reached = iteration;
+      iters = iteration;
+      if (use_saved) { e_tent = e_saved; e_p = e_tent; phase = PH_TENT; }
+      else { e_p = e_lg; phase = PH_REDO; }
+    }
+  }
+
+  int next_level = level;
+  if (end_level) { // :589 and the top of the level loop :373-407
+    level_old = level;
+    next_level = level - cfg.step;
+    if (next_level < cfg.start) {
+      finish = true;
+    } else {
+      e_mp = translate_param<MODEL>(e_mp, li, level_old, next_level);
+      error_code = DIC_OK;
+      lambda = 0.0001f;
+      last_good_chi = FLT_MAX;
+      e_lg = e_mp;
+      e_p = e_mp;
+      scaling = 1.f / (float)sec->n[next_level];
+      phase = PH_INIT;
+    }
+  }
+  if (finish) e_mp = translate_param<MODEL>(e_mp, li, level_old, 0); // :638 / :417
+
+  __syncwarp();
+  if (act) {
+    s->p[li] = e_p; s->mp[li] = e_mp; s->last_good[li] = e_lg;
+    s->tentative[li] = e_tent; s->saved[li] = e_saved;
+    if (finish) result->resultingParameters[li] = e_mp;
+  }
+  if (lane == 0) {
+    s->evals[this_level] = evals;
+    s->iters[this_level] = iters;
+    s->level = finish ? level : next_level;
+    s->level_old = level_old;
+    s->phase = phase; s->iteration = iteration; s->use_saved = use_saved;
+    s->error_code = error_code; s->reached_iterations = reached;
+    s->lambda = lambda; s->last_good_chi = last_good_chi; s->scaling = scaling;
+    s->done = finish ? 1 : 0;
+    if (finish) {
+      for (int i = NP; i < kMaxParams; ++i) result->resultingParameters[i] = 0.f;
+      result->chi = last_good_chi;
+      result->numberOfPoints = sec->n[0];
+      result->iterations = reached;
+      result->errorCode = error_code;
+      result->undCenterX = sec->cx;
+      result->undCenterY = sec->cy;
+      for (int l = 0; l < kMaxLevels; ++l) {
+        result->iterationsPerLevel[l] = l == this_level ? iters : s->iters[l];
+        result->evaluationsPerLevel[l] = l == this_level ? evals : s->evals[l];
+        result->pointsPerLevel[l] = (l >= cfg.start && l <= cfg.stop && (l - cfg.start) % cfg.step == 0)
+                                        ? sec->n[l] : 0;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Initial LM state (top of correlation_class.cpp:349-407 for the coarsest level).
+template <int MODEL>
+__device__ void lm_init(volatile LMState *s, const SolveSettings &cfg, const SectorDev *sec,
+                        const float *guess) {
+  constexpr int NP = model_nparams(MODEL);
+  const int lane = threadIdx.x & 31;
+  if (lane < NP) {
+    float v = translate_param<MODEL>(guess[lane], lane, 0, cfg.stop);
+    s->p[lane] = v; s->mp[lane] = v; s->last_good[lane] = v; s->tentative[lane] = v;
+    s->saved[lane] = v;
+  }
+  if (lane == 0) {
+    s->lambda = 0.0001f; s->last_good_chi = FLT_MAX;
+    s->scaling = 1.f / (float)sec->n[cfg.stop];
+    s->level = cfg.stop; s->level_old = 0; s->iteration = 0; s->use_saved = 1;
+    s->phase = PH_INIT; s->done = 0; s->error_code = DIC_OK; s->reached_iterations = 0;
+    for (int l = 0; l < kMaxLevels; ++l) { s->evals[l] = 0; s->iters[l] = 0; }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ one evaluation pass
+
+template <int MODEL, int INTERP, int MODE>
+__device__ __forceinline__ void evaluate_list(const SolveSettings &cfg, const SectorDev *sec,
+                                              int level, const float *p, long first, long stride,
+                                              float *acc) {
+  const LevelImage und = cfg.und[level];
+  const LevelImage def = cfg.def[level];
+  const float2 *__restrict__ xy = sec->xy[level];
+  const long n = sec->n[level];
+  const float inv = 1.f / (float)(1 << level); // pyramid_class.cpp:357-361
+  const float cx = sec->cx * inv, cy = sec->cy * inv;
+  for (long i = first; i < n; i += stride) {
+    float2 q = __ldg(xy + i);
+    accumulate_pixel<MODEL, INTERP, MODE>(und, def, p, cx, cy, q.x, q.y, acc);
+  }
+}
+
+// GRID = true : every CTA of a cooperative launch works on ONE sector; per evaluation the CTA
+//               partial sums go to `partials`, the last CTA to arrive adds them in a fixed order
+//               (deterministic), runs the LM step + solve in one warp and releases the others.
+// GRID = false: each CTA owns whole sectors (BASELINE config 4: thousands of small subsets);
+//               the LM state lives in shared memory and only __syncthreads is needed.
+template <int MODEL, int INTERP, int MODE, bool GRID>
+__global__ void __launch_bounds__(kThreads)
+gn_solve_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
+                const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
+                int n_sectors, GridWork *work, float *partials) {
+  constexpr int NP = model_nparams(MODEL);
+  using L = Acc<NP>;
+  constexpr int NACC = L::kN;
+  __shared__ float s_red[(kThreads / 32) * NACC];
+  __shared__ float s_tot[NACC];
+  __shared__ float s_solve[NP * (NP + 1) + NP + 4];
+  __shared__ float s_p[kMaxParams];
+  __shared__ int s_ctl[4];
+  __shared__ LMState s_state;
+  __shared__ double s_dred[GRID ? (kThreads / 32) * NACC : 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
+    const SectorDev *sec = sectors + first_sector + si;
+    const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
+    dic_result *result = results + first_sector + si;
+    volatile LMState *st = GRID ? &work->state : &s_state;
+    unsigned int my_gen = 0;
+    if (GRID) {
+      if (tid == 0) s_ctl[2] = (int)ld_acquire_u32(&work->generation);
+      if (blockIdx.x == 0 && warp == 0) { lm_init<MODEL>(st, cfg, sec, guess); __threadfence(); }
+    } else {
+      if (warp == 0) lm_init<MODEL>(st, cfg, sec, guess);
+    }
+    if (tid < NP) s_p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
+    if (tid == 0) { s_ctl[0] = cfg.stop; s_ctl[1] = 0; }
+    __syncthreads();
+    if (GRID) my_gen = (unsigned int)s_ctl[2];
+
+    while (true) {
+      const int level = s_ctl[0];
+      float p[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) p[i] = s_p[i];
+      float acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+      if (GRID)
+        evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, (long)blockIdx.x * kThreads + tid,
+                                           (long)gridDim.x * kThreads, acc);
+      else
+        evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, tid, kThreads, acc);
+      block_reduce<NACC>(acc, s_red, s_tot);
+
+      if (GRID) {
+        if (tid < NACC) __stcg(&partials[(size_t)blockIdx.x * kAccStride + tid], s_tot[tid]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          unsigned int ticket = atomicAdd(&work->arrive, 1u);
+          s_ctl[3] = (ticket == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_ctl[3]) {
+          __threadfence();
+          // fixed-order sum over CTAs, in double: warp w takes CTAs w, w+8, ...
+          for (int k = lane; k < NACC; k += 32) {
+            double s = 0.0;
+            for (unsigned int c = warp; c < gridDim.x; c += kThreads / 32)
+              s += (double)__ldcg(&partials[(size_t)c * kAccStride + k]);
+            s_dred[warp * NACC + k] = s;
+          }
+          __syncthreads();
+          for (int k = tid; k < NACC; k += kThreads) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) s += s_dred[w * NACC + k];
+            s_tot[k] = (float)s;
+          }
+          __syncthreads();
+          if (warp == 0) {
+            lm_step<MODEL>(st, s_tot, cfg, sec, result, s_solve);
+            __threadfence();
+            if (lane == 0) {
+              work->arrive = 0;
+              __threadfence();
+              st_release_u32(&work->generation, my_gen + 1);
+            }
+          }
+        }
+        if (tid == 0) {
+          while (ld_acquire_u32(&work->generation) == my_gen) { __nanosleep(32); }
+        }
+        ++my_gen;
+        __syncthreads();
+        if (tid < NP) s_p[tid] = st->p[tid];
+        if (tid == 0) { s_ctl[0] = st->level; s_ctl[1] = st->done; }
+      } else {
+        if (warp == 0) lm_step<MODEL>(st, s_tot, cfg, sec, result, s_solve);
+        __syncthreads();
+        if (tid < NP) s_p[tid] = st->p[tid];
+        if (tid == 0) { s_ctl[0] = st->level; s_ctl[1] = st->done; }
+      }
+      __syncthreads();
+      if (s_ctl[1]) break;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ single evaluation (tests)
+
+template <int MODEL, int INTERP, int MODE>
+__global__ void __launch_bounds__(kThreads)
+gn_eval_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec, int level,
+               const float *__restrict__ params, float *partials) {
+  constexpr int NP = model_nparams(MODEL);
+  constexpr int NACC = Acc<NP>::kN;
+  __shared__ float s_red[(kThreads / 32) * NACC];
+  __shared__ float s_tot[NACC];
+  float p[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = params[i];
+  float acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+  evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, (long)blockIdx.x * kThreads + threadIdx.x,
+                                     (long)gridDim.x * kThreads, acc);
+  block_reduce<NACC>(acc, s_red, s_tot);
+  if (threadIdx.x < NACC) partials[(size_t)blockIdx.x * kAccStride + threadIdx.x] = s_tot[threadIdx.x];
+}
+
+// out[k] = sum over CTAs of partials[c][k], fixed order, double accumulation
+__global__ void sum_partials_kernel(const float *partials, int n_cta, int nacc, float *out) {
+  int k = threadIdx.x;
+  if (k >= nacc) return;
+  double s = 0.0;
+  for (int c = 0; c < n_cta; ++c) s += (double)partials[(size_t)c * kAccStride + k];
+  out[k] = (float)s;
+}
+
+template <int NP>
+__global__ void solve_step_kernel(const float *tot, float scaling, float lambda, float *dp_out,
+                                  int *ok_out) {
+  __shared__ float smem[NP * (NP + 1) + NP + 4];
+  __shared__ float s_tot[NP * (NP + 1) / 2 + NP];
+  for (int i = threadIdx.x; i < NP * (NP + 1) / 2 + NP; i += 32) s_tot[i] = tot[i];
+  __syncwarp();
+  float *dp = smem + NP * (NP + 1);
+  bool ok = warp_solve<NP>(s_tot, scaling, lambda, smem, dp);
+  if (threadIdx.x < NP) dp_out[threadIdx.x] = ok ? dp[threadIdx.x] : 0.f;
+  if (threadIdx.x == 0) *ok_out = ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ pyramid
+
+// pyramid_class.cpp:52-134. One CTA = 32 x 8 target pixels; the (68 x 20) u8 source footprint is
+// staged in shared memory once, then every target pixel runs the reference's 25 sequential
+// fp32 mul + add (dj outer, di inner, no FMA contraction) and truncates to u8. Target border
+// rows / columns are written as 0 (the reference leaves a zero-initialised border, :98-102).
+constexpr int kPyrTX = 32, kPyrTY = 8;
+struct PyrWeights { float w[25]; };
+
+__global__ void __launch_bounds__(kPyrTX *kPyrTY)
+pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int dcols, int dpitch,
+                     PyrWeights kw) {
+  constexpr int SW = 2 * kPyrTX + 4, SH = 2 * kPyrTY + 3;
+  __shared__ uint8_t tile[SH][SW];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ox = blockIdx.x * kPyrTX, oy = blockIdx.y * kPyrTY; // target origin
+  const int sx0 = 2 * ox - 2, sy0 = 2 * oy - 2;                 // source origin of the tile
+  for (int idx = ty * kPyrTX + tx; idx < SH * SW; idx += kPyrTX * kPyrTY) {
+    int r = idx / SW, c = idx % SW;
+    int sx = sx0 + c, sy = sy0 + r;
+    uint8_t v = 0;
+    if (sx >= 0 && sy >= 0 && sx < src.cols && sy < src.rows) v = __ldg(src.ptr + (size_t)sy * src.pitch + sx);
+    tile[r][c] = v;
+  }
+  __syncthreads();
+  const int ti = ox + tx, tj = oy + ty;
+  if (ti >= dcols || tj >= drows) return;
+  uint8_t out = 0;
+  if (ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1) {
+    float addition = 0.f;
+#pragma unroll
+    for (int dj = 0; dj < 5; ++dj)
+#pragma unroll
+      for (int di = 0; di < 5; ++di) {
+        float s = (float)tile[2 * ty + dj][2 * tx + di];
+        addition = __fadd_rn(addition, __fmul_rn(s, kw.w[dj * 5 + di]));
+      }
+    out = (uint8_t)__float2uint_rz(addition);
+  }
+  dst[(size_t)tj * dpitch + ti] = out;
+}
+
+// level-0 upload helper: tightly packed (or pitched) u8 rows -> engine pitch
+__global__ void copy_rows_kernel(const uint8_t *__restrict__ src, int spitch, uint8_t *__restrict__ dst,
+                                 int dpitch, int rows, int cols) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x < cols && y < rows) dst[(size_t)y * dpitch + x] = src[(size_t)y * spitch + x];
+}
+
+// ------------------------------------------------------------------ pixel lists
+
+// Rectangle, level list in row-major order. Keeps level-0 pixels whose coordinates are multiples
+// of `mag` (pyramid_class.cpp:306-316) and scales them by 1/mag.
+__global__ void rect_fill_kernel(float2 *__restrict__ out, long n, int xs, int ys, int nx, int mag) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int row = (int)(i / nx), col = (int)(i % nx);
+  float inv = 1.f / (float)mag;
+  out[i] = make_float2((float)(xs + col * mag) * inv, (float)(ys + row * mag) * inv);
+}
+
+// Annulus / annular sector membership, manager_class.cpp:897-919, evaluated in fp32 with the
+// reference's operation order (no contraction). Candidates are the box pixels whose coordinates
+// are multiples of `mag`, enumerated row-major.
+struct AnnulusPred {
+  int xs, ys, nxc, mag, as;
+  float cx, cy, ri2, ro2;
+  float c00x, c01x, c10x, c11x, c00y, c01y, c10y, c11y;
+  __device__ __forceinline__ bool operator()(long idx, float2 &out) const {
+    int row = (int)(idx / nxc), col = (int)(idx % nxc);
+    float i = (float)(xs + col * mag);
+    float j = (float)(ys + row * mag);
+    float ax = __fsub_rn(i, cx), ay = __fsub_rn(j, cy);
+    float r2 = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));
+    if (!(r2 > ri2 && r2 < ro2)) return false;
+    if (as != 1) {
+      float cross1 = __fsub_rn(__fmul_rn(__fsub_rn(c11x, i), __fsub_rn(c01y, c11y)),
+                               __fmul_rn(__fsub_rn(c11y, j), __fsub_rn(c01x, c11x)));
+      float cross2 = __fsub_rn(__fmul_rn(__fsub_rn(c00x, i), __fsub_rn(c10y, c00y)),
+                               __fmul_rn(__fsub_rn(c00y, j), __fsub_rn(c10x, c00x)));
+      if (!(__fmul_rn(cross1, cross2) > 0.f)) return false;
+    }
+    float inv = 1.f / (float)mag;
+    out = make_float2(i * inv, j * inv);
+    return true;
+  }
+};
+
+// Generic list decimation, pyramid_class.cpp:306-316.
+struct DecimatePred {
+  const float2 *src;
+  int mag;
+  __device__ __forceinline__ bool operator()(long idx, float2 &out) const {
+    float2 q = src[idx];
+    int ix = (int)(q.x + 0.5f), iy = (int)(q.y + 0.5f);
+    if (ix % mag != 0 || iy % mag != 0) return false;
+    float inv = 1.f / (float)mag;
+    out = make_float2(q.x * inv, q.y * inv);
+    return true;
+  }
+};
+
+// Order-preserving stream compaction: count pass, scan of CTA counts, emit pass.
+constexpr int kCompactThreads = 256, kCompactItems = 8;
+constexpr int kCompactChunk = kCompactThreads * kCompactItems;
+
+template <class Pred, bool EMIT>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_kernel(Pred pred, long ncand, unsigned int *block_counts,
+               const unsigned long long *block_offsets, float2 *__restrict__ out) {
+  __shared__ unsigned int warp_tot[kCompactThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long base = (long)blockIdx.x * kCompactChunk;
+  unsigned long long running = EMIT ? block_offsets[blockIdx.x] : 0ull;
+  unsigned int total = 0;
+  for (int it = 0; it < kCompactItems; ++it) {
+    long idx = base + (long)it * kCompactThreads + tid;
+    float2 q;
+    bool keep = idx < ncand && pred(idx, q);
+    unsigned int bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactThreads / 32; ++w) {
+      unsigned int t = warp_tot[w];
+      if (w < warp) before += t;
+      all += t;
+    }
+    if (EMIT && keep) out[running + before + __popc(bal & ((1u << lane) - 1u))] = q;
+    running += all;
+    total += all;
+    __syncthreads();
+  }
+  if (!EMIT && tid == 0) block_counts[blockIdx.x] = total;
+}
+
+// exclusive scan of CTA counts (single CTA), total written to offsets[n]
+__global__ void scan_counts_kernel(const unsigned int *counts, int n, unsigned long long *offsets) {
+  __shared__ unsigned long long buf[1024];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned long long v = i < n ? counts[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      unsigned long long t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) offsets[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+// Blob: row spans (y, x_begin, x_end) produced on the host from the ear-clipped triangles
+// (polygon_class.cpp:339-403) are expanded to pixels in the reference's emission order.
+struct Span { int y, xb, xe; long offset; };
+__global__ void expand_spans_kernel(const Span *__restrict__ spans, int n_spans, long n_pixels,
+                                    float2 *__restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pixels) return;
+  int lo = 0, hi = n_spans - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (spans[mid].offset <= i) lo = mid; else hi = mid - 1;
+  }
+  Span s = spans[lo];
+  out[i] = make_float2((float)(s.xb + (int)(i - s.offset)), (float)s.y);
+}
+
+// kModel_inPlace (correlationKernel.cu:56-110): def positions of a list under `params`.
+template <int MODEL>
+__global__ void warp_list_kernel(const float2 *__restrict__ src, long n, const float *params,
+                                 float cx, float cy, float2 *__restrict__ dst) {
+  constexpr int NP = model_nparams(MODEL);
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) p[k] = params[k];
+  float2 q = src[i];
+  float xd, yd, dx, dy;
+  warp_point<MODEL, DIC_MODE_PARITY>(p, q.x, q.y, cx, cy, xd, yd, dx, dy);
+  dst[i] = make_float2(xd, yd);
+}
+
+// exact integer sums of a list of integer-valued points (DIC_CENTER_EXACT)
+__global__ void sum_xy_kernel(const float2 *__restrict__ xy, long n, unsigned long long *sums) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long sx = 0, sy = 0;
+  for (; i < n; i += (long)gridDim.x * blockDim.x) {
+    float2 q = xy[i];
+    sx += (long long)llrintf(q.x * 1024.f);
+    sy += (long long)llrintf(q.y * 1024.f);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[0], (unsigned long long)sx);
+    atomicAdd(&sums[1], (unsigned long long)sy);
+  }
+}
+
+} // namespace dic

@@ -1,0 +1,194 @@
+/* include/dic_b200.h -- C-ABI of libdic_b200.so, the B200-native DIC engine.
+ *
+ * Drop-in boundary: one `extern "C"` entry point per public method of
+ * the reference's GPU facade `CudaClass` (cuda_class.cuh:46-79), which is the only thing the
+ * reference's orchestrator (`managerClass`, manager_class.h:84-86) talks to on its GPU path.
+ * Same verbs, same argument meaning, same error enum -- but raw buffers instead of file
+ * paths / cv::Mat / v_points, and RESULT SEMANTICS OF THE REFERENCE CPU ENGINE
+ * (chi = sum V^2 / N, look-ahead step damped with max(0.4 lambda, 1e-9), `iterations` = index
+ * inside the last level, error 2 on out-of-image).
+ *
+ * Plain pointers and sizes only; no CUDA, torch or C++ types in any signature. All functions
+ * return a dic_error (0 = ok) unless stated. The engine owns all device memory. Calls on one
+ * engine are not re-entrant, except dic_reset_next_pyramid which may run on a second host
+ * thread concurrently with dic_correlate (manager_class.cpp:1438-1447).
+ */
+#ifndef DIC_B200_H
+#define DIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIC_MAX_PARAMS 12
+#define DIC_MAX_LEVELS 8
+
+/* enums.hpp:25-35 errorEnum, same numeric values */
+typedef enum {
+  DIC_OK = 0,
+  DIC_ERROR_MODEL_OUT_OF_IMAGE = 1,
+  DIC_ERROR_INTERPOLATION_OUT_OF_IMAGE = 2,
+  DIC_ERROR_MAX_ITERS_REACHED = 3,
+  DIC_ERROR_BAD_DOMAIN = 4,
+  DIC_ERROR_SOLVER = 5, /* enums.hpp: error_cuSolver -- here: non-SPD normal equations */
+  DIC_ERROR_CUDA = 6,
+  DIC_ERROR_MULTITHREAD = 7,
+  DIC_ERROR_BAD_ARGUMENT = 8 /* extension: API misuse (null pointer, unknown sector, ...) */
+} dic_error;
+
+/* enums.hpp:17-23 fittingModelEnum (+ the 12-parameter extension of BASELINE.json) */
+typedef enum {
+  DIC_FM_U = 0,
+  DIC_FM_UV = 1,
+  DIC_FM_UVQ = 2,
+  DIC_FM_UVUxUyVxVy = 3,
+  DIC_FM_QUADRATIC = 4 /* p = u v ux uy vx vy uxx uxy uyy vxx vxy vyy (extension) */
+} dic_fitting_model;
+
+/* enums.hpp:10-15 interpolationModelEnum */
+typedef enum { DIC_IM_NEAREST = 0, DIC_IM_BILINEAR = 1, DIC_IM_BICUBIC = 2 } dic_interpolation_model;
+
+/* enums.hpp:83-88 deformationDescriptionEnum */
+typedef enum { DIC_DEF_STRICT_LAGRANGIAN = 0, DIC_DEF_LAGRANGIAN = 1, DIC_DEF_EULERIAN = 2 } dic_deformation_description;
+
+/* Arithmetic form of the per-pixel evaluation (extension):
+ *  PARITY: the reference's fp32 operation order (monomial bicubic in 1+t, unfused mul/add),
+ *          bit-identical w, dw/dx, dw/dy per pixel to interpolation_class.cpp:79-138.
+ *  FAST:   the same interpolant (Catmull-Rom) in weight form with FMAs; more accurate than
+ *          the reference's own rounding noise, ~3x fewer instructions. */
+typedef enum { DIC_MODE_PARITY = 0, DIC_MODE_FAST = 1 } dic_arith_mode;
+
+/* How the domain centre is derived when the caller does not give one (annulus, blob):
+ *  REFERENCE: sequential fp32 mean over the pixel list in the reference's list order
+ *             (pyramid_class.cpp:325-347) -- reproduces the CPU engine's centre bit for bit.
+ *  EXACT:     the true mean (integer sums on the device). */
+typedef enum { DIC_CENTER_REFERENCE = 0, DIC_CENTER_EXACT = 1 } dic_center_mode;
+
+/* domains.hpp:110-118 CorrelationResult, widened to 12 parameters plus work accounting. */
+typedef struct {
+  float resultingParameters[DIC_MAX_PARAMS];
+  float chi;          /* last_good_chi of the finest level, = sum V^2 / N (CPU semantics) */
+  int numberOfPoints; /* level-0 pixel count */
+  int iterations;     /* iteration index reached inside the LAST level (correlation_class.cpp:870) */
+  int errorCode;      /* dic_error */
+  float undCenterX;
+  float undCenterY;
+  /* extension: per-level accounting (index = pyramid level) */
+  int iterationsPerLevel[DIC_MAX_LEVELS];
+  int evaluationsPerLevel[DIC_MAX_LEVELS]; /* passes over the level's pixels */
+  int pointsPerLevel[DIC_MAX_LEVELS];
+} dic_result;
+
+typedef struct dic_engine dic_engine;
+
+/* ---- CudaClass::initialize (cuda_class.cu:40-93): number of usable devices (0 => caller
+ *      disables GPU mode, mainapp.cpp:99). */
+int dic_device_count(void);
+
+/* ---- CudaClass ctor/dtor. `device` is the CUDA ordinal (reference hard-codes 0,
+ *      cuda_class.cu:333-338). Returns NULL on failure. */
+dic_engine *dic_create(int device);
+void dic_destroy(dic_engine *e);
+/* last CUDA / engine error text for this engine (never NULL) */
+const char *dic_last_error(const dic_engine *e);
+
+/* ---- setters: CudaClass::set_max_iters / set_precision / set_fitting_model /
+ *      set_interpolation_model (cuda_class.cu:95-101, 475-496) */
+int dic_set_max_iters(dic_engine *e, int maximum_iterations);
+int dic_set_precision(dic_engine *e, float required_precision);
+int dic_set_fitting_model(dic_engine *e, int fitting_model);
+int dic_set_interpolation_model(dic_engine *e, int interpolation_model);
+/* extensions */
+int dic_set_arith_mode(dic_engine *e, int arith_mode);
+int dic_set_center_mode(dic_engine *e, int center_mode);
+
+/* ---- CudaClass::resetImagePyramids(undPath, defPath, nxtPath, color, start, step, stop)
+ *      (cuda_class.cu:512-572): host u8 images (row-major, `channels` interleaved; only
+ *      channels == 1 is implemented), builds all three pyramids. nxt may be NULL. */
+int dic_reset_image_pyramids(dic_engine *e, const uint8_t *und, const uint8_t *def,
+                             const uint8_t *nxt, int rows, int cols, int channels,
+                             int pyramid_start, int pyramid_step, int pyramid_stop);
+/* same, but the level-0 images already live in device memory (pitch in bytes) */
+int dic_reset_image_pyramids_device(dic_engine *e, const void *und_dev, const void *def_dev,
+                                    const void *nxt_dev, int rows, int cols, int pitch,
+                                    int pyramid_start, int pyramid_step, int pyramid_stop);
+/* ---- CudaClass::resetNextPyramid(nxtPath) (cuda_class.cu:498-510) */
+int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols);
+int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt_dev, int rows, int cols, int pitch);
+/* replace only the deformed image (host convenience for frame loops without a nxt slot) */
+int dic_reset_def_pyramid(dic_engine *e, const uint8_t *def, int rows, int cols);
+int dic_reset_def_pyramid_device(dic_engine *e, const void *def_dev, int rows, int cols, int pitch);
+/* ---- CudaClass::makeUndPyramidFromDef / makeDefPyramidFromNxt (cuda_class.cu:607-613):
+ *      pointer rotation, no copy */
+int dic_make_und_pyramid_from_def(dic_engine *e);
+int dic_make_def_pyramid_from_nxt(dic_engine *e);
+
+/* ---- CudaClass::resetPolygon x3 (cuda_class.cu:574-605).
+ *      Membership follows the CPU engine's builders, not the reference GPU functors:
+ *      rect     manager_class.cpp:1596-1614  all integer (x,y), x0<=x<=x1, y0<=y<=y1;
+ *               centre = ((x0+x1)/2, (y0+y1)/2), the value the manager passes (:438-441)
+ *      annular  manager_class.cpp:816-940    strict ri^2 < r^2 < ro^2, half-open box, wedge test
+ *      blob     polygon_class.cpp            ear-clipped triangles, half-open scanline fill
+ *      Returns DIC_ERROR_BAD_DOMAIN for a self-intersecting contour or an empty level. */
+int dic_reset_polygon_rect(dic_engine *e, int iSector, int x0, int y0, int x1, int y1);
+int dic_reset_polygon_annular(dic_engine *e, int iSector, float r, float dr, float a, float da,
+                              float cx, float cy, int as);
+int dic_reset_polygon_blob(dic_engine *e, int iSector, const float *contour_xy, int n_vertices);
+/* extension: an arbitrary point list (what CorrelationClass::Newton_Raphson(guess, N, xy) takes,
+ * correlation_class.cpp:326-343). use_center: 0 = derive per the centre mode. */
+int dic_reset_polygon_points(dic_engine *e, int iSector, const float *xy, int64_t n,
+                             int use_center, float cx, float cy);
+/* extension: override the centre of an existing sector */
+int dic_set_polygon_center(dic_engine *e, int iSector, float cx, float cy);
+
+/* ---- CudaClass::updatePolygon(iSector, deformationDescription) (cuda_class.cu:596-605,
+ *      cuda_polygon.cu:268-415): Lagrangian = translate the list by the rounded centre shift of
+ *      the last result; strict Lagrangian = und points := last deformed points; Eulerian = no-op */
+int dic_update_polygon(dic_engine *e, int iSector, int deformation_description);
+
+/* ---- CudaClass::correlate(iSector, guess, results) (cuda_class.cu:104-293).
+ *      guess: level-0 units, n parameters; read, then overwritten with the result (as the
+ *      reference does, cuda_class.cu:289-290). out may be NULL. Returns out->errorCode. */
+int dic_correlate(dic_engine *e, int iSector, float *guess_inout, dic_result *out);
+/* extension (BASELINE config 4): n_sectors consecutive sector ids, one CTA per sector, one
+ * launch. guesses: n_sectors x n_params (row-major), overwritten; results: n_sectors entries. */
+int dic_correlate_batch(dic_engine *e, int first_sector, int n_sectors, float *guesses_inout,
+                        dic_result *results);
+/* extension: enqueue only (no host sync); dic_correlate_wait collects. Lets a caller overlap
+ * the next upload with the solve, and lets bench.py time the device alone. */
+int dic_correlate_async(dic_engine *e, int iSector, const float *guess);
+int dic_correlate_wait(dic_engine *e, int iSector, float *guess_out, dic_result *out);
+
+/* ---- CudaClass::getUndXY0ToCPU / getDefXY0ToCPU (cuda_class.cu, cuda_polygon.cu:417-428):
+ *      level-0 list in the reference CPU order. Writes min(cap, n) points (interleaved x,y);
+ *      *n_needed receives n. */
+int dic_get_und_xy0(dic_engine *e, int iSector, float *xy, int64_t cap, int64_t *n_needed);
+int dic_get_def_xy0(dic_engine *e, int iSector, float *xy, int64_t cap, int64_t *n_needed);
+
+/* ---- introspection used by the parity tests and bench (extensions) */
+/* which: 0 und, 1 def, 2 nxt. out may be NULL to query the size. */
+int dic_get_pyramid_level(dic_engine *e, int which, int level, uint8_t *out, int *rows, int *cols);
+int dic_get_level_points(dic_engine *e, int iSector, int level, float *xy, int64_t cap,
+                         int64_t *n_needed);
+int dic_get_level_center(dic_engine *e, int iSector, int level, float *cx, float *cy);
+/* one evaluation at `params` (LEVEL units): raw upper-triangular A (n x n row-major), b, chi
+ * (sum V^2, unscaled), number of out-of-image pixels. */
+int dic_evaluate(dic_engine *e, int iSector, int level, const float *params, float *A, float *b,
+                 float *chi, int *n_out_of_image);
+/* the damped solve of correlation_class.cpp:642-688 on caller data (device Cholesky) */
+int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float lambda,
+                   float scaling, float *dp);
+/* device-side time of the last correlate / correlate_batch launch in milliseconds (CUDA events
+ * on the correlation stream) and how many kernels this engine has launched so far */
+float dic_last_correlate_ms(dic_engine *e);
+int64_t dic_kernel_launches(const dic_engine *e);
+/* the CUDA stream handle (cudaStream_t as void*) the GN kernels run on, for event timing */
+void *dic_correlation_stream(dic_engine *e);
+int dic_synchronize(dic_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIC_B200_H */

@@ -1,0 +1,335 @@
+"""GPU suite (B200): the CUDA path through the C-ABI against the oracle and the golden vectors.
+
+Tolerances are BASELINE.json's: displacement 1e-4 px, gradient terms 1e-6, chi 1e-5 relative,
+iterations +-1. chi is compared with the double-accumulator oracle (the reference's own float
+accumulation moves chi by up to 2e-4 relative with its thread count) and must also sit
+inside the spread of the float oracle.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from correlation_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_UV, TOL_GRAD, TOL_CHI = 1e-4, 1e-6, 1e-5
+
+
+def make_oracle(und, dfm, **kw):
+    o = oracle.OracleEngine(**kw)
+    o.set_image("und", und)
+    o.set_image("def", dfm)
+    return o
+
+
+def check_result(got, want, n_grad_from=2, tol_uv=TOL_UV, tol_grad=TOL_GRAD, tol_chi=TOL_CHI):
+    assert got["error_code"] == want["error_code"], (got, want)
+    d = np.abs(got["params"].astype(np.float64) - want["params"])
+    assert d[:n_grad_from].max() < tol_uv, (got["params"], want["params"])
+    if d.size > n_grad_from:
+        assert d[n_grad_from:6].max() < tol_grad, (got["params"], want["params"])
+    assert abs(got["chi"] - want["chi"]) <= tol_chi * abs(want["chi"]), (got["chi"], want["chi"])
+    assert abs(got["iterations"] - want["iterations"]) <= 1
+    assert got["number_of_points"] == want["number_of_points"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.CudaEngine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def pair_a(golden):
+    return golden["A/und"], golden["A/def"]
+
+
+# ---------------------------------------------------------------- pyramid (bit-exact)
+
+def test_pyramid_bit_exact_vs_golden(eng, golden):
+    eng.resetImagePyramids(golden["A/und"], golden["A/def"], pyramid=(0, 1, 2))
+    for lv in (1, 2):
+        assert np.array_equal(eng.pyramid_level(0, lv), golden[f"A/pyr_und{lv}"])
+        assert np.array_equal(eng.pyramid_level(1, lv), golden[f"A/pyr_def{lv}"])
+    assert np.array_equal(eng.pyramid_level(0, 0), golden["A/und"])
+
+
+@pytest.mark.parametrize("shape", [(257, 301), (64, 64), (1000, 777)])
+def test_pyramid_bit_exact_odd_sizes(eng, shape):
+    rng = np.random.default_rng(shape[0])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    flat = np.full(shape, 128, np.uint8)  # the 128 -> 127 truncation case of SURVEY H2
+    for im in (img, flat):
+        eng.resetImagePyramids(im, im, pyramid=(0, 1, 3))
+        o = make_oracle(im, im, pyramid=(0, 1, 3))
+        for lv in (1, 2, 3):
+            assert np.array_equal(eng.pyramid_level(0, lv), o.pyramid_level(0, lv)), (shape, lv)
+
+
+# ---------------------------------------------------------------- pixel lists (bit-exact)
+
+def test_rect_lists_vs_golden(eng, golden):
+    eng.resetImagePyramids(golden["A/und"], golden["A/def"], pyramid=(0, 1, 2))
+    x0, y0, x1, y1 = (int(v) for v in golden["A/rect"])
+    assert eng.resetPolygon(0, x0, y0, x1, y1) == 0
+    for lv in (0, 1, 2):
+        assert np.array_equal(eng.level_points(0, lv), golden[f"A/points{lv}"])
+    assert eng.level_center(0, 0) == (95.0, 95.0)
+
+
+@pytest.mark.parametrize("geom", [(20.0, 40.0, 0.0, 2 * np.pi, 96.3, 95.1, 1),
+                                  (30.0, 35.0, 0.4, 1.1, 96.0, 96.0, 4),
+                                  (10.0, 70.0, 2.0, 2 * np.pi / 3, 90.5, 100.25, 3)])
+def test_annulus_lists_and_center_vs_oracle(eng, golden, geom):
+    eng.resetImagePyramids(golden["A/und"], golden["A/def"], pyramid=(0, 1, 2))
+    r, dr, a, da, cx, cy, n_as = geom
+    assert eng.resetPolygon(1, r, dr, a, da, cx, cy, n_as) == 0
+    want = oracle.annulus_points(r, dr, a, da, cx, cy, n_as)
+    assert np.array_equal(eng.getUndXY0ToCPU(1), want)
+    o = make_oracle(golden["A/und"], golden["A/def"], pyramid=(0, 1, 2))
+    o.set_points(want)
+    for lv in (1, 2):
+        assert np.array_equal(eng.level_points(1, lv), o.level_points(lv))
+    assert eng.level_center(1, 0) == o.level_center(0)  # sequential fp32 centre, bit for bit
+
+
+def test_blob_list_and_center_vs_golden(eng, golden):
+    eng.resetImagePyramids(golden["A/und"], golden["A/def"], pyramid=(0, 1, 2))
+    assert eng.resetPolygon(2, golden["C/contour"]) == 0
+    assert np.array_equal(eng.getUndXY0ToCPU(2), golden["C/points"])
+    assert np.array_equal(np.array(eng.level_center(2, 0)), golden["C/center"])
+    bow = np.array([[10, 10], [100, 100], [100, 10], [10, 100]], np.float32)
+    assert eng.resetPolygon(3, bow) == 4  # error_bad_domain
+
+
+# ---------------------------------------------------------------- one evaluation: A, b, chi
+
+@pytest.mark.parametrize("mode", [engine.MODE_PARITY, engine.MODE_FAST])
+def test_single_evaluation_vs_oracle(eng, golden, mode):
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_interpolation_model(engine.IM_BICUBIC)
+    eng.set_arith_mode(mode)
+    eng.resetImagePyramids(golden["A/und"], golden["A/def"], pyramid=(0, 1, 2))
+    x0, y0, x1, y1 = (int(v) for v in golden["A/rect"])
+    eng.resetPolygon(0, x0, y0, x1, y1)
+    o = make_oracle(golden["A/und"], golden["A/def"], n_threads=1, pyramid=(0, 1, 2), accum_double=True)
+    o.set_points(oracle.rect_points(x0, y0, x1, y1), center=(95.0, 95.0))
+    p = np.array([1.7, -0.6, 0.004, -0.003, 0.002, 0.005], np.float32)
+    for lv in (0, 1, 2):
+        q = p.copy()
+        q[:2] /= (1 << lv)
+        A, b, chi, oob = eng.evaluate(0, lv, q)
+        Ao, bo, chio, _ = o.evaluate(lv, q)
+        # parity mode: per-pixel values are bit-identical, only the summation order differs
+        rtol = 2e-6 if mode == engine.MODE_PARITY else 2e-4
+        assert oob == 0
+        assert np.allclose(np.triu(A), np.triu(Ao), rtol=rtol, atol=rtol * np.abs(Ao).max()), lv
+        assert np.allclose(b, bo, rtol=rtol, atol=rtol * np.abs(bo).max()), lv
+        assert abs(chi - chio) <= rtol * chio, (lv, chi, chio)
+    eng.set_arith_mode(engine.MODE_PARITY)
+
+
+def test_solve_step_vs_oracle(eng):
+    rng = np.random.default_rng(1)
+    J = rng.normal(size=(500, 6)) * np.array([1, 1, 40, 40, 40, 40])
+    A = (J.T @ J).astype(np.float32)
+    b = (J.T @ rng.normal(size=500)).astype(np.float32)
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    o = oracle.OracleEngine(n_threads=1)
+    for lam in (1e-4, 4e-5, 1e-2):
+        got = eng.solve_step(np.triu(A), b, lam, 1 / 500)
+        want = o.solve_step(np.triu(A), b, lam, 1 / 500)
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-8)
+
+
+# ---------------------------------------------------------------- full correlate()
+
+def test_correlate_rect_affine_vs_golden_and_oracle(eng, golden):
+    g = golden
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_interpolation_model(engine.IM_BICUBIC)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 2))
+    x0, y0, x1, y1 = (int(v) for v in g["A/rect"])
+    eng.resetPolygon(0, x0, y0, x1, y1)
+    got = eng.correlate(0, np.zeros(6))
+    od = make_oracle(g["A/und"], g["A/def"], n_threads=20, pyramid=(0, 1, 2), accum_double=True)
+    want = od.correlate(np.zeros(6), oracle.rect_points(x0, y0, x1, y1), center=(95.0, 95.0))
+    check_result(got, want)
+    # and against the unmodified reference's golden output (its own float accumulation: chi
+    # carries the thread-count bias of SURVEY H1, so 1e-4 there)
+    for T in (1, 20):
+        d = np.abs(got["params"] - g[f"A/T{T}/params"])
+        assert d[:2].max() < TOL_UV and d[2:].max() < TOL_GRAD
+        assert abs(got["chi"] - g[f"A/T{T}/chi"]) < 1e-4 * g[f"A/T{T}/chi"]
+        assert abs(got["iterations"] - int(g[f"A/T{T}/iterations"])) <= 1
+    assert got["evaluations"][:3] == want["evaluations"][:3]
+    assert got["points_per_level"][:3] == want["points_per_level"][:3]
+
+
+def test_correlate_fast_mode_stays_close(eng, golden):
+    g = golden
+    eng.set_arith_mode(engine.MODE_FAST)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 2))
+    x0, y0, x1, y1 = (int(v) for v in g["A/rect"])
+    eng.resetPolygon(0, x0, y0, x1, y1)
+    got = eng.correlate(0, np.zeros(6))
+    eng.set_arith_mode(engine.MODE_PARITY)
+    d = np.abs(got["params"] - g["A/T20/params"])
+    # the reference's own monomial-form rounding noise bounds this, not our kernel
+    assert d[:2].max() < 2e-4 and d[2:].max() < 4e-6
+    assert abs(got["chi"] - g["A/T20/chi"]) < 3e-4 * g["A/T20/chi"]
+
+
+@pytest.mark.parametrize("mname,model", [("U", engine.FM_U), ("UV", engine.FM_UV), ("UVQ", engine.FM_UVQ)])
+@pytest.mark.parametrize("iname,interp", [("nearest", engine.IM_NEAREST), ("bilinear", engine.IM_BILINEAR),
+                                          ("bicubic", engine.IM_BICUBIC)])
+def test_correlate_other_models_vs_golden(eng, golden, mname, model, iname, interp):
+    g = golden
+    eng.set_fitting_model(model)
+    eng.set_interpolation_model(interp)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 1))
+    x0, y0, x1, y1 = (int(v) for v in g["A/rect"])
+    eng.resetPolygon(0, x0, y0, x1, y1)
+    got = eng.correlate(0, np.zeros(eng.n_params))
+    tag = f"B/{mname}_{iname}"
+    assert got["error_code"] == int(g[tag + "/error_code"])
+    d = np.abs(got["params"] - g[tag + "/params"])
+    # nearest-neighbour "interpolation" is piecewise constant: its LM path is chaotic at 1e-4,
+    # so only the smooth interpolants get the tight bound
+    tol = (5e-2, 5e-4) if iname == "nearest" else (TOL_UV, TOL_GRAD)
+    assert d[:min(2, d.size)].max() < tol[0], (got["params"], g[tag + "/params"])
+    if d.size > 2:
+        assert d[2:].max() < tol[1]
+    if iname != "nearest":
+        assert abs(got["chi"] - g[tag + "/chi"]) < 1e-4 * g[tag + "/chi"]
+        assert abs(got["iterations"] - int(g[tag + "/iterations"])) <= 1
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_interpolation_model(engine.IM_BICUBIC)
+
+
+def test_correlate_blob_vs_golden(eng, golden):
+    g = golden
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 2))
+    eng.resetPolygon(2, g["C/contour"])
+    got = eng.correlate(2, np.zeros(6))
+    d = np.abs(got["params"] - g["C/blob/params"])
+    assert d[:2].max() < TOL_UV and d[2:].max() < TOL_GRAD
+    assert abs(got["chi"] - g["C/blob/chi"]) < 1e-4 * g["C/blob/chi"]
+    assert got["iterations"] == int(g["C/blob/iterations"])
+    assert got["number_of_points"] == int(g["C/blob/number_of_points"])
+
+
+def test_correlate_annulus_vs_oracle(eng):
+    truth = (0.8, -1.1, 0.002, 0.003, -0.002, 0.001)
+    und, dfm = synth.make_pair(400, 420, 31, truth, center=(210, 200))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    geom = (60.0, 110.0, 0.0, 2 * np.pi, 210.0, 200.0, 1)
+    assert eng.resetPolygon(0, *geom) == 0
+    got = eng.correlate(0, np.zeros(6))
+    o = make_oracle(und, dfm, n_threads=20, pyramid=(0, 1, 2), accum_double=True)
+    want = o.correlate(np.zeros(6), oracle.annulus_points(*geom))
+    check_result(got, want)
+
+
+def test_correlate_quadratic_vs_oracle_extension(eng):
+    """12-parameter model: extension, parity unpinned by the reference -- GPU vs our oracle."""
+    truth = np.array([1.2, -0.8, .003, -.002, .001, .004, 2e-5, -1e-5, 1.5e-5, -2e-5, 1e-5, 5e-6])
+    und, dfm = synth.make_pair(320, 320, 21, truth, center=(160, 160))
+    eng.set_fitting_model(engine.FM_QUADRATIC)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    eng.resetPolygon(0, 40, 40, 280, 280)
+    got = eng.correlate(0, np.zeros(12))
+    o = make_oracle(und, dfm, model=oracle.FM_QUAD, n_threads=20, pyramid=(0, 1, 2), accum_double=True)
+    want = o.correlate(np.zeros(12), oracle.rect_points(40, 40, 280, 280), center=(160.0, 160.0))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    check_result(got, want)
+    assert np.abs(got["params"][6:] - want["params"][6:]).max() < 1e-7
+    assert np.abs(got["params"][6:] - truth[6:]).max() < 1.5e-5
+
+
+def test_error_paths(eng, golden):
+    g = golden
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 1))
+    eng.resetPolygon(0, 2, 2, 60, 60)
+    got = eng.correlate(0, np.array([-8, -8, 0, 0, 0, 0], np.float32))
+    assert got["error_code"] == int(g["D/oob/error_code"]) == 2
+    assert np.array_equal(got["params"], g["D/oob/params"])
+    assert got["chi"] == g["D/oob/chi"]
+    eng.set_max_iters(1)
+    eng.set_precision(1e-9)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 0))
+    x0, y0, x1, y1 = (int(v) for v in g["A/rect"])
+    eng.resetPolygon(0, x0, y0, x1, y1)
+    got = eng.correlate(0, np.zeros(6))
+    eng.set_max_iters(50)
+    eng.set_precision(1e-3)
+    assert got["error_code"] == int(g["E/maxit/error_code"]) == 3
+    assert got["iterations"] == int(g["E/maxit/iterations"])
+    assert np.abs(got["params"] - g["E/maxit/params"]).max() < 1e-4
+
+
+def test_frame_rotation_and_next_pyramid(eng):
+    frames = [synth.make_image(200, 200, 9, p, (100, 100)) for p in
+              (None, (0.5, 0.2, 0, 0, 0, 0), (1.0, 0.4, 0.001, 0, 0, 0.001))]
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(frames[0], frames[1], frames[2], pyramid=(0, 1, 1))
+    eng.resetPolygon(0, 50, 50, 150, 150)
+    o = make_oracle(frames[0], frames[1], n_threads=20, pyramid=(0, 1, 1), accum_double=True)
+    o.set_image("nxt", frames[2])
+    xy = oracle.rect_points(50, 50, 150, 150)
+    check_result(eng.correlate(0, np.zeros(6)), o.correlate(np.zeros(6), xy, center=(100., 100.)))
+    eng.makeUndPyramidFromDef()
+    eng.makeDefPyramidFromNxt()
+    o.und_from_def()
+    o.def_from_nxt()
+    check_result(eng.correlate(0, np.zeros(6)), o.correlate(np.zeros(6), xy, center=(100., 100.)))
+
+
+# ---------------------------------------------------------------- batch of subsets (config 4 shape)
+
+def test_batch_of_subsets_equals_one_by_one_and_oracle(eng):
+    truth = (1.1, 0.6, 0.002, -0.001, 0.001, 0.002)
+    und, dfm = synth.make_pair(384, 384, 41, truth, center=(192, 192))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    boxes = []
+    for i in range(4):
+        for j in range(4):
+            cx, cy = 64 + 32 + 64 * i, 64 + 32 + 64 * j
+            boxes.append((cx - 31, cy - 31, cx + 31, cy + 31))
+    for k, bx in enumerate(boxes):
+        assert eng.resetPolygon(k, *bx) == 0
+    batch = eng.correlate_batch(0, np.zeros((16, 6), np.float32))
+    o = make_oracle(und, dfm, n_threads=1, pyramid=(0, 1, 2), accum_double=True)
+    for k, bx in enumerate(boxes):
+        single = eng.correlate(k, np.zeros(6))
+        assert np.abs(batch[k]["params"] - single["params"]).max() < 2e-6
+        want = o.correlate(np.zeros(6), oracle.rect_points(*bx), center=((bx[0] + bx[2]) / 2, (bx[1] + bx[3]) / 2))
+        check_result(batch[k], want)
+
+
+# ---------------------------------------------------------------- full-size property tests
+
+def test_full_size_c1_recovers_truth_and_matches_oracle(eng):
+    """BASELINE config 1 at full size: 1024^2 pair, 511^2 rectangle, affine, 3 levels."""
+    truth = np.array((1.75, -0.6, .004, -.003, .002, .005))
+    und, dfm = synth.make_pair(1024, 1024, 1, truth, center=(512, 512))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    eng.resetPolygon(0, 257, 257, 767, 767)
+    got = eng.correlate(0, np.zeros(6))
+    assert np.abs(got["params"][:2] - truth[:2]).max() < 2e-3
+    assert np.abs(got["params"][2:] - truth[2:]).max() < 2e-5
+    o = make_oracle(und, dfm, n_threads=20, pyramid=(0, 1, 2), accum_double=True)
+    want = o.correlate(np.zeros(6), oracle.rect_points(257, 257, 767, 767), center=(512., 512.))
+    check_result(got, want)
+    # idempotence: restarting from the answer stays there
+    again = eng.correlate(0, got["params"])
+    assert np.abs(again["params"][:2] - got["params"][:2]).max() < 1e-3
