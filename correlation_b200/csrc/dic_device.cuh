@@ -17,6 +17,7 @@ namespace dic {
 constexpr int kMaxLevels = DIC_MAX_LEVELS;
 constexpr int kMaxParams = DIC_MAX_PARAMS;
 constexpr int kThreads = 256; // threads per CTA of the GN kernels
+constexpr int kMaxMarks = 128;
 
 // ------------------------------------------------------------------ descriptors
 
@@ -47,11 +48,18 @@ struct LMState {
   int evals[kMaxLevels], iters[kMaxLevels];
 };
 
-// Grid-wide reduction / barrier scratch (grid mode).
+// Grid-wide reduction / barrier scratch (grid mode). CTA 0 is the master: it owns the LM state in
+// its shared memory and publishes only the next command (parameters, level, done).
 struct GridWork {
-  unsigned int arrive;     // tickets of the current evaluation
-  unsigned int generation; // bumped by the last CTA after the LM step
-  LMState state;
+  unsigned int arrive;     // worker CTAs that have delivered their partial sums
+  unsigned int generation; // bumped by the master after every LM step
+  float pub_p[kMaxParams];
+  int pub_level, pub_done;
+  double acc[96]; // grid-wide sums of the current evaluation (fp64 atomics), zeroed by the master
+  // master-side timeline of the last launch (ns, %globaltimer): per evaluation
+  // [0] pass started, [1] own pass done, [2] all workers arrived, [3] LM step published
+  int n_marks;
+  unsigned long long marks[kMaxMarks][4];
 };
 
 struct SolveSettings {
@@ -365,70 +373,71 @@ __device__ __forceinline__ void block_reduce(float *acc, float *red, float *out)
 // ------------------------------------------------------------------ solve (one warp)
 
 // Damped normal equations of correlation_class.cpp:642-688: A, b scaled by 1/N, diagonal times
-// (1 + lambda). Solved by a Jacobi-equilibrated Cholesky factorisation run by one warp in shared
-// memory (replaces the reference's cuSOLVER potrf/potrs, cuda_solver.cu:119-149, and the CPU's
-// Eigen QR). tot: packed upper A, then b. Returns false when a pivot is not positive.
+// (1 + lambda). Solved by a Jacobi-equilibrated Cholesky factorisation held in registers, one
+// matrix row per lane, columns exchanged by warp shuffles (replaces the reference's cuSOLVER
+// potrf/potrs, cuda_solver.cu:119-149, and the CPU's Eigen QR). tot: packed upper A, then b
+// (shared memory). smem: NP*NP floats of scratch for the transposed back-substitution.
+// Returns false (warp-uniform) when a pivot is not positive.
 template <int NP>
-__device__ bool warp_solve(const float *tot, float scaling, float lambda, float *M /*NP*(NP+1)*/,
-                           float *dp /*NP*/) {
+__device__ bool warp_solve(const float *tot, float scaling, float lambda, float *smem, float *dp) {
   const int lane = threadIdx.x & 31;
-  float *S = M + NP * NP; // NP scale factors
-  // unpack, scale, damp
-  for (int idx = lane; idx < NP * NP; idx += 32) {
-    int i = idx / NP, j = idx % NP;
+  const int i = lane < NP ? lane : NP - 1;
+  const unsigned full = 0xffffffffu;
+  float a[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
     int r = i < j ? i : j, c = i < j ? j : i;
-    int k = r * NP - r * (r - 1) / 2 + (c - r);
-    float v = tot[k] * scaling;
-    if (i == j) v *= (1.f + lambda);
-    M[idx] = v;
+    float v = tot[r * NP - r * (r - 1) / 2 + (c - r)] * scaling;
+    a[j] = (i == j) ? v * (1.f + lambda) : v;
   }
-  __syncwarp();
-  if (lane < NP) {
-    float d = M[lane * NP + lane];
-    S[lane] = d > 0.f ? rsqrtf(d) : 0.f;
-  }
-  __syncwarp();
-  bool ok = true;
-  for (int i = 0; i < NP; ++i) ok = ok && (S[i] > 0.f);
-  if (!ok) return false;
-  for (int idx = lane; idx < NP * NP; idx += 32) {
-    int i = idx / NP, j = idx % NP;
-    M[idx] *= S[i] * S[j];
-  }
-  __syncwarp();
-  // right-looking Cholesky, lower triangle in place
+  float rhs = tot[NP * (NP + 1) / 2 + i] * scaling;
+  float dii = 0.f;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) dii = (j == i) ? a[j] : dii;
+  if (__any_sync(full, lane < NP && !(dii > 0.f))) return false;
+  const float sc = 1.0f / sqrtf(dii);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) a[j] *= sc * __shfl_sync(full, sc, j);
+  rhs *= sc;
+  // right-looking Cholesky: after step k, a[k] of lane i >= k holds L[i][k]
+#pragma unroll
   for (int k = 0; k < NP; ++k) {
-    float d = M[k * NP + k];
-    if (!(d > 1e-12f)) return false;
-    float inv = rsqrtf(d);
-    __syncwarp();
-    if (lane >= k && lane < NP) M[lane * NP + k] *= inv; // column k (diag becomes sqrt(d))
-    __syncwarp();
-    for (int idx = lane; idx < NP * NP; idx += 32) {
-      int i = idx / NP, j = idx % NP;
-      if (j > k && i >= j) M[idx] -= M[i * NP + k] * M[j * NP + k];
+    const float dk = __shfl_sync(full, a[k], k);
+    if (!(dk > 1e-12f)) return false;
+    const float inv = 1.0f / sqrtf(dk);
+    const float lik = a[k] * inv;
+    a[k] = lik;
+#pragma unroll
+    for (int j = k + 1; j < NP; ++j) {
+      const float ljk = __shfl_sync(full, lik, j);
+      a[j] = (i >= j) ? fmaf(-lik, ljk, a[j]) : a[j];
     }
-    __syncwarp();
   }
-  // forward / backward substitution by lane 0 (n <= 12: ~150 dependent FMAs)
-  if (lane == 0) {
-    const float *bvec = tot + NP * (NP + 1) / 2;
-    float yv[NP];
+  float lii = 1.f;
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      float s = bvec[i] * scaling * S[i];
-      for (int j = 0; j < i; ++j) s -= M[i * NP + j] * yv[j];
-      yv[i] = s / M[i * NP + i];
-    }
+  for (int j = 0; j < NP; ++j) lii = (j == i) ? a[j] : lii;
+  const float rinv = 1.0f / lii;
+  // forward substitution L y = rhs (column oriented)
+  float y = rhs;
 #pragma unroll
-    for (int i = NP - 1; i >= 0; --i) {
-      float s = yv[i];
-      for (int j = i + 1; j < NP; ++j) s -= M[j * NP + i] * yv[j];
-      yv[i] = s / M[i * NP + i];
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) dp[i] = yv[i] * S[i];
+  for (int k = 0; k < NP; ++k) {
+    const float yk = __shfl_sync(full, y * rinv, k);
+    y = (i == k) ? yk : ((i > k) ? fmaf(-a[k], yk, y) : y);
   }
+  // backward substitution L^T x = y needs column access: rows go through shared memory once
+  if (lane < NP) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) smem[lane * NP + j] = a[j];
+  }
+  __syncwarp();
+  float x = y;
+#pragma unroll
+  for (int k = NP - 1; k >= 0; --k) {
+    const float xk = __shfl_sync(full, x * rinv, k);
+    const float lki = smem[k * NP + i]; // L[k][i], used by lanes i < k
+    x = (i == k) ? xk : ((i < k) ? fmaf(-lki, xk, x) : x);
+  }
+  if (lane < NP) dp[lane] = x * sc;
   __syncwarp();
   return true;
 }

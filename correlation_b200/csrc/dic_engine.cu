@@ -18,6 +18,7 @@
 
 #include "dic_kernels.cuh"
 #include "dic_polygon.hpp"
+#include "dic_tiles.cuh"
 
 using namespace dic;
 
@@ -36,6 +37,13 @@ struct Sector {
   // geometry kept for reference-order regeneration
   int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
   bool pending = false; // an async correlate is in flight
+  // structured form (dic_tiles.cuh): column-major 32x16 tiles per level (+ duplicate pixels)
+  Tile *tbuf = nullptr;
+  size_t tcap = 0;
+  float2 *ebuf = nullptr;
+  size_t ecap = 0;
+  TileLevel tl[kMaxLevels] = {};
+  bool has_tiles = false;
 };
 
 struct PyramidSlot {
@@ -62,6 +70,10 @@ struct dic_engine {
   int center_mode = DIC_CENTER_REFERENCE;
   std::vector<Sector> sectors;
   SectorDev *d_sectors = nullptr;
+  SectorTiles *d_sector_tiles = nullptr;
+  uint32_t *d_masks = nullptr;
+  size_t cap_masks = 0;
+  int kernel_variant = 0; // 0 auto, 1 pixel-list kernel, 2 tile kernel
   float *d_guess = nullptr;
   dic_result *d_results = nullptr;
   dic_result *h_results = nullptr; // pinned
@@ -182,10 +194,12 @@ int set_image(dic_engine *e, int role, const void *src, int rows, int cols, int 
 int ensure_sector_capacity(dic_engine *e, int n) {
   if (n <= e->cap_sectors) return DIC_OK;
   int cap = std::max(n, std::max(16, e->cap_sectors * 2));
-  SectorDev *ds = nullptr; float *dg = nullptr; dic_result *dr = nullptr;
+  SectorDev *ds = nullptr; float *dg = nullptr; dic_result *dr = nullptr; SectorTiles *dt = nullptr;
   dic_result *hr = nullptr; float *hg = nullptr;
   CU_TRY(e, cudaMalloc(&ds, sizeof(SectorDev) * cap));
   CU_TRY(e, cudaMalloc(&dg, sizeof(float) * kMaxParams * cap));
+  CU_TRY(e, cudaMalloc(&dt, sizeof(SectorTiles) * cap));
+  CU_TRY(e, cudaMemset(dt, 0, sizeof(SectorTiles) * cap));
   CU_TRY(e, cudaMalloc(&dr, sizeof(dic_result) * cap));
   CU_TRY(e, cudaMallocHost(&hr, sizeof(dic_result) * cap));
   CU_TRY(e, cudaMallocHost(&hg, sizeof(float) * kMaxParams * cap));
@@ -198,12 +212,14 @@ int ensure_sector_capacity(dic_engine *e, int n) {
     CU_TRY(e, cudaStreamSynchronize(e->stream));
     CU_TRY(e, cudaMemcpy(ds, e->d_sectors, sizeof(SectorDev) * e->cap_sectors, cudaMemcpyDeviceToDevice));
     CU_TRY(e, cudaMemcpy(dg, e->d_guess, sizeof(float) * kMaxParams * e->cap_sectors, cudaMemcpyDeviceToDevice));
+    CU_TRY(e, cudaMemcpy(dt, e->d_sector_tiles, sizeof(SectorTiles) * e->cap_sectors, cudaMemcpyDeviceToDevice));
     CU_TRY(e, cudaMemcpy(dr, e->d_results, sizeof(dic_result) * e->cap_sectors, cudaMemcpyDeviceToDevice));
     memcpy(hr, e->h_results, sizeof(dic_result) * e->cap_sectors);
     memcpy(hg, e->h_guess, sizeof(float) * kMaxParams * e->cap_sectors);
-    cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results);
+    cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results); cudaFree(e->d_sector_tiles);
     cudaFreeHost(e->h_results); cudaFreeHost(e->h_guess);
   }
+  e->d_sector_tiles = dt;
   e->d_sectors = ds; e->d_guess = dg; e->d_results = dr; e->h_results = hr; e->h_guess = hg;
   e->cap_sectors = cap;
   e->sectors.resize(cap);
@@ -244,8 +260,13 @@ int push_sector(dic_engine *e, int id) {
   memset(&d, 0, sizeof(d));
   for (int l = 0; l < kMaxLevels; ++l) { d.xy[l] = s.xy[l]; d.n[l] = (int)s.n[l]; }
   d.cx = s.cx; d.cy = s.cy;
+  SectorTiles t;
+  memset(&t, 0, sizeof(t));
+  if (s.has_tiles)
+    for (int l = 0; l < kMaxLevels; ++l) t.lev[l] = s.tl[l];
   CU_TRY(e, cudaMemcpyAsync(e->d_sectors + id, &d, sizeof(SectorDev), cudaMemcpyHostToDevice, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream)); // `d` lives on this stack frame
+  CU_TRY(e, cudaMemcpyAsync(e->d_sector_tiles + id, &t, sizeof(SectorTiles), cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream)); // `d`, `t` live on this stack frame
   return DIC_OK;
 }
 
@@ -347,6 +368,91 @@ int exact_center(dic_engine *e, Sector &s) {
   return DIC_OK;
 }
 
+
+// Builds the structured form of an integer-grid sector from its per-level pixel lists.
+int build_tiles(dic_engine *e, Sector &s, bool may_have_duplicates) {
+  s.has_tiles = false;
+  for (int l = 0; l < kMaxLevels; ++l) s.tl[l] = TileLevel{};
+  struct Grid { int l, gx0, gy0, ntx, nty; size_t slots; } g[kMaxLevels];
+  int ng = 0;
+  size_t total_slots = 0, max_slots = 0;
+  int *d_box = reinterpret_cast<int *>(e->d_scratch + 768);
+  for (int l = 0; l <= e->stop; ++l) {
+    if (!level_used(e, l) || s.n[l] <= 0) continue;
+    int box[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+    CU_TRY(e, cudaMemcpyAsync(d_box, box, sizeof(box), cudaMemcpyHostToDevice, e->stream));
+    int grid = (int)std::max<long>(1, std::min<long>((s.n[l] + 255) / 256, e->num_sms * 8));
+    bbox_kernel<<<grid, 256, 0, e->stream>>>(s.xy[l], s.n[l], d_box);
+    e->launches++;
+    CU_TRY(e, cudaMemcpyAsync(box, d_box, sizeof(box), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    if (box[0] < 0 || box[1] < 0) return DIC_OK; // negative coordinates: keep the list kernel
+    Grid q;
+    q.l = l;
+    q.gx0 = box[0] / kTileW * kTileW; q.gy0 = box[1] / kTileH * kTileH;
+    q.ntx = (box[2] - q.gx0) / kTileW + 1; q.nty = (box[3] - q.gy0) / kTileH + 1;
+    q.slots = (size_t)q.ntx * q.nty;
+    total_slots += q.slots;
+    max_slots = std::max(max_slots, q.slots);
+    g[ng++] = q;
+  }
+  if (ng == 0) return DIC_OK;
+  if (total_slots > s.tcap) {
+    if (s.tbuf) cudaFree(s.tbuf);
+    s.tbuf = nullptr; s.tcap = 0;
+    CU_TRY(e, cudaMalloc(&s.tbuf, sizeof(Tile) * total_slots));
+    s.tcap = total_slots;
+  }
+  size_t need_masks = max_slots * kTileH;
+  if (need_masks > e->cap_masks) {
+    if (e->d_masks) cudaFree(e->d_masks);
+    e->d_masks = nullptr; e->cap_masks = 0;
+    CU_TRY(e, cudaMalloc(&e->d_masks, sizeof(uint32_t) * need_masks * 2));
+    e->cap_masks = need_masks * 2;
+  }
+  const int extra_cap_per_level = may_have_duplicates ? 4096 : 0;
+  if (may_have_duplicates && s.ecap < (size_t)extra_cap_per_level * kMaxLevels) {
+    if (s.ebuf) cudaFree(s.ebuf);
+    CU_TRY(e, cudaMalloc(&s.ebuf, sizeof(float2) * extra_cap_per_level * kMaxLevels));
+    s.ecap = (size_t)extra_cap_per_level * kMaxLevels;
+  }
+  int *d_nextra = reinterpret_cast<int *>(e->d_scratch + 800);
+  size_t used = 0;
+  for (int k = 0; k < ng; ++k) {
+    const Grid &q = g[k];
+    CU_TRY(e, cudaMemsetAsync(e->d_masks, 0, sizeof(uint32_t) * q.slots * kTileH, e->stream));
+    CU_TRY(e, cudaMemsetAsync(d_nextra, 0, sizeof(int), e->stream));
+    float2 *extra = may_have_duplicates ? s.ebuf + (size_t)q.l * extra_cap_per_level : nullptr;
+    tiles_scatter_kernel<<<(unsigned)((s.n[q.l] + 255) / 256), 256, 0, e->stream>>>(
+        s.xy[q.l], s.n[q.l], q.gx0, q.gy0, q.nty, e->d_masks, extra, extra_cap_per_level, d_nextra);
+    TilePred pred{e->d_masks, q.gx0, q.gy0, q.nty};
+    size_t nblocks = (q.slots + kCompactChunk - 1) / kCompactChunk;
+    int rc = ensure_counts(e, nblocks);
+    if (rc) return rc;
+    compact_any_kernel<TilePred, Tile, false><<<(unsigned)nblocks, kCompactThreads, 0, e->stream>>>(
+        pred, (long)q.slots, e->d_counts, nullptr, nullptr);
+    scan_counts_kernel<<<1, 1024, 0, e->stream>>>(e->d_counts, (int)nblocks, e->d_offsets);
+    Tile *dst = s.tbuf + used;
+    compact_any_kernel<TilePred, Tile, true><<<(unsigned)nblocks, kCompactThreads, 0, e->stream>>>(
+        pred, (long)q.slots, nullptr, e->d_offsets, dst);
+    e->launches += 4;
+    unsigned long long ntiles = 0;
+    int nextra = 0;
+    CU_TRY(e, cudaMemcpyAsync(&ntiles, e->d_offsets + nblocks, sizeof(ntiles), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(&nextra, d_nextra, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    if (nextra > extra_cap_per_level) return DIC_OK; // too many duplicates: keep the list kernel
+    s.tl[q.l].tiles = dst;
+    s.tl[q.l].n_tiles = (int)ntiles;
+    s.tl[q.l].extra = extra;
+    s.tl[q.l].n_extra = nextra;
+    used += (size_t)ntiles;
+  }
+  CU_TRY(e, cudaGetLastError());
+  s.has_tiles = true;
+  return DIC_OK;
+}
+
 template <int MODEL, int INTERP, int MODE>
 int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
   SolveSettings cfg;
@@ -382,6 +488,66 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
   }
   e->launches++;
   return DIC_OK;
+}
+
+
+template <int MODEL, int MODE>
+int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
+  SolveSettings cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
+  for (int l = 0; l < kMaxLevels; ++l) { cfg.und[l] = u.lev[l]; cfg.def[l] = d.lev[l]; }
+  cfg.start = e->start; cfg.step = e->step; cfg.stop = e->stop;
+  cfg.max_iters = e->max_iters; cfg.precision = e->precision;
+  const SectorDev *sectors = e->d_sectors;
+  const SectorTiles *stiles = e->d_sector_tiles;
+  const float *guesses = e->d_guess;
+  dic_result *results = e->d_results;
+  GridWork *work = e->d_work;
+  float *partials = e->d_partials;
+  constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
+  const size_t smem = tiles_dyn_smem(NACC);
+  if (grid_mode) {
+    auto kern = gn_solve_tiles_kernel<MODEL, MODE, true>;
+    CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) { set_error(e, "gn_solve_tiles_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }
+    // one warp per ~2 finest-level tiles at most, never more CTAs than are co-resident
+    long nt = e->sectors[first].tl[e->start].n_tiles;
+    int want = (int)std::min<long>((nt + kWarpsPerCta - 1) / kWarpsPerCta, (long)per_sm * e->num_sms);
+    int grid = std::max(1, std::min(want, e->max_grid));
+    int one = 1;
+    void *args[] = {&cfg, &sectors, &stiles, &guesses, &results, &first, &one, &work, &partials};
+    CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, smem, e->stream));
+  } else {
+    auto kern = gn_solve_tiles_kernel<MODEL, MODE, false>;
+    CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
+    kern<<<grid, kThreads, smem, e->stream>>>(cfg, sectors, stiles, guesses, results, first, count, work, partials);
+    CU_TRY(e, cudaGetLastError());
+  }
+  e->launches++;
+  return DIC_OK;
+}
+
+bool tiles_applicable(const dic_engine *e, int first, int count) {
+  if (e->kernel_variant == 1) return false;
+  if (e->interp != DIC_IM_BICUBIC) return false;
+  if (e->model != DIC_FM_UVUxUyVxVy && e->model != DIC_FM_QUADRATIC) return false;
+  for (int i = 0; i < count; ++i)
+    if (!e->sectors[first + i].has_tiles) return false;
+  return true;
+}
+
+int launch_solve_tiles_any(dic_engine *e, bool grid_mode, int first, int count) {
+  if (e->model == DIC_FM_UVUxUyVxVy)
+    return e->mode == DIC_MODE_FAST ? launch_solve_tiles<DIC_FM_UVUxUyVxVy, DIC_MODE_FAST>(e, grid_mode, first, count)
+                                    : launch_solve_tiles<DIC_FM_UVUxUyVxVy, DIC_MODE_PARITY>(e, grid_mode, first, count);
+  return e->mode == DIC_MODE_FAST ? launch_solve_tiles<DIC_FM_QUADRATIC, DIC_MODE_FAST>(e, grid_mode, first, count)
+                                  : launch_solve_tiles<DIC_FM_QUADRATIC, DIC_MODE_PARITY>(e, grid_mode, first, count);
 }
 
 template <int MODEL, int INTERP>
@@ -477,7 +643,8 @@ void dic_destroy(dic_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->img_stream) cudaStreamSynchronize(e->img_stream);
-  for (auto &s : e->sectors) if (s.buf) cudaFree(s.buf);
+  for (auto &s : e->sectors) { if (s.buf) cudaFree(s.buf); if (s.tbuf) cudaFree(s.tbuf); if (s.ebuf) cudaFree(s.ebuf); }
+  cudaFree(e->d_sector_tiles); cudaFree(e->d_masks);
   for (auto &p : e->pyr) if (p.base) cudaFree(p.base);
   cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results);
   if (e->h_results) cudaFreeHost(e->h_results);
@@ -507,6 +674,10 @@ int dic_set_interpolation_model(dic_engine *e, int m) {
 int dic_set_arith_mode(dic_engine *e, int m) {
   if (!e || (m != DIC_MODE_PARITY && m != DIC_MODE_FAST)) return DIC_ERROR_BAD_ARGUMENT;
   e->mode = m; return DIC_OK;
+}
+int dic_set_kernel_variant(dic_engine *e, int v) {
+  if (!e || v < 0 || v > 2) return DIC_ERROR_BAD_ARGUMENT;
+  e->kernel_variant = v; return DIC_OK;
 }
 int dic_set_center_mode(dic_engine *e, int m) {
   if (!e || (m != DIC_CENTER_REFERENCE && m != DIC_CENTER_EXACT)) return DIC_ERROR_BAD_ARGUMENT;
@@ -612,6 +783,7 @@ static int begin_sector(dic_engine *e, int id, Sector **out) {
   Sector &s = e->sectors[id];
   s.kind = SK_NONE;
   s.pending = false;
+  s.has_tiles = false;
   clear_levels(s);
   *out = &s;
   return DIC_OK;
@@ -658,6 +830,7 @@ int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1
   s.integer_grid = true;
   if ((rc = check_levels_nonempty(e, s))) return rc;
   s.kind = SK_RECT;
+  if ((rc = build_tiles(e, s, false))) return rc;
   return push_sector(e, id);
 }
 
@@ -782,6 +955,7 @@ int dic_reset_polygon_annular(dic_engine *e, int id, float r, float dr, float a,
     return rc;
   }
   s.kind = SK_ANNULAR;
+  if ((rc = build_tiles(e, s, false))) return rc;
   return push_sector(e, id);
 }
 
@@ -805,6 +979,7 @@ static int finish_list_sector(dic_engine *e, int id, Sector &s, SectorKind kind,
     return rc;
   }
   s.kind = kind;
+  if (s.integer_grid && (rc = build_tiles(e, s, true))) return rc;
   return push_sector(e, id);
 }
 
@@ -897,7 +1072,8 @@ static int enqueue_correlate(dic_engine *e, int first, int count, const float *g
   CU_TRY(e, cudaMemcpyAsync(e->d_guess + (size_t)first * kMaxParams, e->h_guess + (size_t)first * kMaxParams,
                             sizeof(float) * kMaxParams * count, cudaMemcpyHostToDevice, e->stream));
   CU_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  rc = launch_solve_any(e, grid_mode, first, count);
+  rc = tiles_applicable(e, first, count) ? launch_solve_tiles_any(e, grid_mode, first, count)
+                                         : launch_solve_any(e, grid_mode, first, count);
   if (rc) return rc;
   CU_TRY(e, cudaEventRecord(e->ev1, e->stream));
   e->timing_pending = true;
@@ -1115,6 +1291,15 @@ int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float la
   return ok ? DIC_OK : DIC_ERROR_SOLVER;
 }
 
+int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap) {
+  if (!e || !marks) return 0;
+  cudaSetDevice(e->device);
+  GridWork h;
+  if (cudaMemcpy(&h, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  int n = std::min(std::min(h.n_marks, cap), kMaxMarks);
+  memcpy(marks, h.marks, sizeof(unsigned long long) * 4 * n);
+  return n;
+}
 float dic_last_correlate_ms(dic_engine *e) { return e ? e->last_ms : 0.f; }
 int64_t dic_kernel_launches(const dic_engine *e) { return e ? (int64_t)e->launches.load() : 0; }
 void *dic_correlation_stream(dic_engine *e) { return e ? (void *)e->stream : nullptr; }

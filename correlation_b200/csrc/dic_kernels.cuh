@@ -22,6 +22,11 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -32,7 +37,7 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
 // Restates correlation_class.cpp:373-591 as "what to evaluate next"; parameter vectors are held
 // one element per lane.
 template <int MODEL>
-__device__ void lm_step(volatile LMState *s, const float *tot, const SolveSettings &cfg,
+__device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
                         const SectorDev *sec, dic_result *result, float *smem) {
   constexpr int NP = model_nparams(MODEL);
   using L = Acc<NP>;
@@ -192,7 +197,7 @@ __device__ void lm_step(volatile LMState *s, const float *tot, const SolveSettin
 
 // Initial LM state (top of correlation_class.cpp:349-407 for the coarsest level).
 template <int MODEL>
-__device__ void lm_init(volatile LMState *s, const SolveSettings &cfg, const SectorDev *sec,
+__device__ void lm_init(LMState *s, const SolveSettings &cfg, const SectorDev *sec,
                         const float *guess) {
   constexpr int NP = model_nparams(MODEL);
   const int lane = threadIdx.x & 31;
@@ -229,111 +234,151 @@ __device__ __forceinline__ void evaluate_list(const SolveSettings &cfg, const Se
   }
 }
 
-// GRID = true : every CTA of a cooperative launch works on ONE sector; per evaluation the CTA
-//               partial sums go to `partials`, the last CTA to arrive adds them in a fixed order
-//               (deterministic), runs the LM step + solve in one warp and releases the others.
-// GRID = false: each CTA owns whole sectors (BASELINE config 4: thousands of small subsets);
-//               the LM state lives in shared memory and only __syncthreads is needed.
+// Shared-memory block common to both solve kernels.
+template <int NP> struct SolveShared {
+  static constexpr int NACC = Acc<NP>::kN;
+  float tot[NACC];
+  float solve[NP * NP + NP + 4];
+  float p[kMaxParams];
+  int level, done;
+  LMState state;
+  double dred[(kThreads / 32) * NACC];
+};
+
+// After one evaluation pass: sh.tot holds this CTA's sums. Produces the next command in
+// sh.p / sh.level / sh.done for every CTA.
+//   GRID: CTA 0 is the master. Workers that took part (`active`) store their sums to `partials`,
+//   fence, and bump `arrive`; the master waits for n_active - 1 arrivals, adds the rows in a
+//   fixed order (double accumulation, deterministic), runs the LM step + solve in its warp 0
+//   with the state in ITS shared memory, publishes the command and releases `generation`.
+//   Batch: the CTA owns the sector; only __syncthreads is needed.
+template <int MODEL, bool GRID>
+__device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)> &sh, bool active,
+                                                int n_active, const SolveSettings &cfg,
+                                                const SectorDev *sec, dic_result *result,
+                                                GridWork *work, float *partials, unsigned int &my_gen) {
+  constexpr int NP = model_nparams(MODEL);
+  constexpr int NACC = Acc<NP>::kN;
+  constexpr int kW = kThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (GRID) {
+    if (blockIdx.x != 0) {
+      if (active) {
+        if (tid < NACC) atomicAdd(&work->acc[tid], (double)sh.tot[tid]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(&work->arrive, 1u);
+      }
+      if (tid == 0) {
+        while (ld_acquire_u32(&work->generation) == my_gen) { __nanosleep(64); }
+      }
+      __syncthreads();
+      if (tid < NP) sh.p[tid] = __ldcg(&work->pub_p[tid]);
+      if (tid == 0) { sh.level = __ldcg(&work->pub_level); sh.done = __ldcg(&work->pub_done); }
+    } else {
+      if (tid == 0) {
+        int m = work->n_marks;
+        if (m < kMaxMarks) work->marks[m][1] = global_ns();
+        while (ld_acquire_u32(&work->arrive) < (unsigned int)(n_active - 1)) {}
+        if (m < kMaxMarks) work->marks[m][2] = global_ns();
+      }
+      __syncthreads();
+      if (tid < NACC) {
+        // workers' sums arrive through fp64 atomics (order-independent to well below fp32 ulp)
+        double s = (double)sh.tot[tid] + __ldcg(&work->acc[tid]);
+        __stcg(&work->acc[tid], 0.0);
+        sh.tot[tid] = (float)s;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
+        if (lane < NP) { float v = sh.state.p[lane]; sh.p[lane] = v; __stcg(&work->pub_p[lane], v); }
+        if (lane == 0) {
+          sh.level = sh.state.level; sh.done = sh.state.done;
+          __stcg(&work->pub_level, sh.state.level); __stcg(&work->pub_done, sh.state.done);
+          __stcg(&work->arrive, 0u);
+          int m = work->n_marks;
+          if (m < kMaxMarks) { work->marks[m][3] = global_ns(); work->n_marks = m + 1; }
+          if (m + 1 < kMaxMarks) work->marks[m + 1][0] = work->marks[m][3];
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(&work->generation, my_gen + 1);
+      }
+    }
+    ++my_gen;
+    __syncthreads();
+  } else {
+    if (warp == 0) {
+      lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
+      if (lane < NP) sh.p[lane] = sh.state.p[lane];
+      if (lane == 0) { sh.level = sh.state.level; sh.done = sh.state.done; }
+    }
+    __syncthreads();
+  }
+}
+
+// Start of a sector: every CTA derives the first command locally; the owner of the LM state
+// (master CTA in grid mode, the CTA itself in batch mode) initialises it.
+template <int MODEL, bool GRID>
+__device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &sh, const SolveSettings &cfg,
+                                             const SectorDev *sec, const float *guess, GridWork *work,
+                                             unsigned int &my_gen) {
+  constexpr int NP = model_nparams(MODEL);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ unsigned int s_gen;
+  if (GRID && tid == 0) s_gen = ld_acquire_u32(&work->generation);
+  if ((!GRID || blockIdx.x == 0) && warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, guess);
+  if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->marks[0][0] = global_ns(); }
+  if (tid < NP) sh.p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
+  if (tid == 0) { sh.level = cfg.stop; sh.done = 0; }
+  __syncthreads();
+  my_gen = GRID ? s_gen : 0u;
+}
+
+// GRID = true : every CTA of a cooperative launch works on ONE sector (large domains).
+// GRID = false: each CTA owns whole sectors (BASELINE config 4: thousands of small subsets).
 template <int MODEL, int INTERP, int MODE, bool GRID>
 __global__ void __launch_bounds__(kThreads)
 gn_solve_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
                 const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
                 int n_sectors, GridWork *work, float *partials) {
   constexpr int NP = model_nparams(MODEL);
-  using L = Acc<NP>;
-  constexpr int NACC = L::kN;
+  constexpr int NACC = Acc<NP>::kN;
   __shared__ float s_red[(kThreads / 32) * NACC];
-  __shared__ float s_tot[NACC];
-  __shared__ float s_solve[NP * (NP + 1) + NP + 4];
-  __shared__ float s_p[kMaxParams];
-  __shared__ int s_ctl[4];
-  __shared__ LMState s_state;
-  __shared__ double s_dred[GRID ? (kThreads / 32) * NACC : 1];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ SolveShared<NP> sh;
+  const int tid = threadIdx.x;
 
   for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
     const SectorDev *sec = sectors + first_sector + si;
     const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
     dic_result *result = results + first_sector + si;
-    volatile LMState *st = GRID ? &work->state : &s_state;
-    unsigned int my_gen = 0;
-    if (GRID) {
-      if (tid == 0) s_ctl[2] = (int)ld_acquire_u32(&work->generation);
-      if (blockIdx.x == 0 && warp == 0) { lm_init<MODEL>(st, cfg, sec, guess); __threadfence(); }
-    } else {
-      if (warp == 0) lm_init<MODEL>(st, cfg, sec, guess);
-    }
-    if (tid < NP) s_p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
-    if (tid == 0) { s_ctl[0] = cfg.stop; s_ctl[1] = 0; }
-    __syncthreads();
-    if (GRID) my_gen = (unsigned int)s_ctl[2];
-
+    unsigned int my_gen;
+    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, work, my_gen);
     while (true) {
-      const int level = s_ctl[0];
+      const int level = sh.level;
       float p[NP];
 #pragma unroll
-      for (int i = 0; i < NP; ++i) p[i] = s_p[i];
+      for (int i = 0; i < NP; ++i) p[i] = sh.p[i];
       float acc[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-      if (GRID)
-        evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, (long)blockIdx.x * kThreads + tid,
-                                           (long)gridDim.x * kThreads, acc);
-      else
-        evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, tid, kThreads, acc);
-      block_reduce<NACC>(acc, s_red, s_tot);
-
+      int n_active = 1;
+      bool active = true;
       if (GRID) {
-        if (tid < NACC) __stcg(&partials[(size_t)blockIdx.x * kAccStride + tid], s_tot[tid]);
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-          unsigned int ticket = atomicAdd(&work->arrive, 1u);
-          s_ctl[3] = (ticket == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (s_ctl[3]) {
-          __threadfence();
-          // fixed-order sum over CTAs, in double: warp w takes CTAs w, w+8, ...
-          for (int k = lane; k < NACC; k += 32) {
-            double s = 0.0;
-            for (unsigned int c = warp; c < gridDim.x; c += kThreads / 32)
-              s += (double)__ldcg(&partials[(size_t)c * kAccStride + k]);
-            s_dred[warp * NACC + k] = s;
-          }
-          __syncthreads();
-          for (int k = tid; k < NACC; k += kThreads) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) s += s_dred[w * NACC + k];
-            s_tot[k] = (float)s;
-          }
-          __syncthreads();
-          if (warp == 0) {
-            lm_step<MODEL>(st, s_tot, cfg, sec, result, s_solve);
-            __threadfence();
-            if (lane == 0) {
-              work->arrive = 0;
-              __threadfence();
-              st_release_u32(&work->generation, my_gen + 1);
-            }
-          }
-        }
-        if (tid == 0) {
-          while (ld_acquire_u32(&work->generation) == my_gen) { __nanosleep(32); }
-        }
-        ++my_gen;
-        __syncthreads();
-        if (tid < NP) s_p[tid] = st->p[tid];
-        if (tid == 0) { s_ctl[0] = st->level; s_ctl[1] = st->done; }
+        long need = ((long)sec->n[level] + kThreads * 4 - 1) / (kThreads * 4);
+        n_active = (int)max(1l, min(need, (long)gridDim.x));
+        active = (int)blockIdx.x < n_active;
+        if (active)
+          evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, (long)blockIdx.x * kThreads + tid,
+                                             (long)n_active * kThreads, acc);
       } else {
-        if (warp == 0) lm_step<MODEL>(st, s_tot, cfg, sec, result, s_solve);
-        __syncthreads();
-        if (tid < NP) s_p[tid] = st->p[tid];
-        if (tid == 0) { s_ctl[0] = st->level; s_ctl[1] = st->done; }
+        evaluate_list<MODEL, INTERP, MODE>(cfg, sec, level, p, tid, kThreads, acc);
       }
       __syncthreads();
-      if (s_ctl[1]) break;
+      block_reduce<NACC>(acc, s_red, sh.tot);
+      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, partials, my_gen);
+      if (sh.done) break;
     }
     __syncthreads();
   }
@@ -374,7 +419,7 @@ template <int NP>
 __global__ void solve_step_kernel(const float *tot, float scaling, float lambda, float *dp_out,
                                   int *ok_out) {
   __shared__ float smem[NP * (NP + 1) + NP + 4];
-  __shared__ float s_tot[NP * (NP + 1) / 2 + NP];
+  __shared__ float s_tot[NP * (NP + 1) / 2 + NP + 2];
   for (int i = threadIdx.x; i < NP * (NP + 1) / 2 + NP; i += 32) s_tot[i] = tot[i];
   __syncwarp();
   float *dp = smem + NP * (NP + 1);

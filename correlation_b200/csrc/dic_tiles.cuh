@@ -1,0 +1,508 @@
+// dic_tiles.cuh -- the structured (tile) form of the fused Gauss-Newton evaluation.
+//
+// Integer-grid domains (rectangles, annuli, blobs: everything the reference's builders produce,
+// manager_class.cpp:1596-1614 / :816-940, polygon_class.cpp) are stored per pyramid level as
+// 32 x 16 pixel tiles with one 32-bit membership mask per row, ordered COLUMN-major so that a warp
+// walks down one 32-pixel-wide strip: lane <-> x, loop <-> y. That layout buys three things the
+// pixel-list kernel cannot have:
+//   1. coalesced u8 traffic: a warp-row of the reference image is one 32-byte sector, and the
+//      deformed-image footprint of a whole tile (about 40 x 24 pixels) is staged ONCE into shared
+//      memory as fp32 (u8 -> float conversion per deformed pixel, not 16x per domain pixel);
+//   2. dx = x - cx is a per-lane constant, so J^T J / J^T r are accumulated as moments in dy only
+//      (sum g g' dy^b, sum V g dy^b): 15 + 6 + 2 registers for the 12-parameter model instead of
+//      92, 9 + 4 + 2 instead of 29 for the affine one, and 3-4x fewer FMAs per pixel;
+//   3. the in-image test (interpolation_class.cpp:82-83) is hoisted to one test per tile; tiles
+//      whose warped footprint leaves the image or the staging buffer take the per-pixel path.
+// The moments are expanded to the full upper-triangular A, b with the lane's dx powers only when
+// the warp changes strip or the evaluation ends.
+#pragma once
+#include "dic_kernels.cuh"
+
+namespace dic {
+
+constexpr int kTileW = 32, kTileH = 16;
+constexpr int kPatchW = 48, kPatchH = 24; // fp32 staging of the deformed footprint, per warp
+constexpr int kWarpsPerCta = kThreads / 32;
+
+struct Tile {
+  int x0, y0;             // level coordinates of the tile's first pixel
+  uint32_t rows[kTileH];  // bit l of rows[r] <=> pixel (x0 + l, y0 + r) belongs to the domain
+};
+
+struct TileLevel {
+  const Tile *tiles;
+  int n_tiles;
+  const float2 *extra; // pixels that occur more than once in the reference list (blob edges)
+  int n_extra;
+};
+
+struct SectorTiles {
+  TileLevel lev[kMaxLevels];
+};
+
+// ---- monomial bookkeeping: parameter k <-> (gradient component g, X^a Y^b, coefficient)
+// affine:    u v ux uy vx vy                     (model_class.cpp:150-202)
+// quadratic: ... uxx uxy uyy vxx vxy vyy         (extension; 1/2 on the pure second-order terms)
+template <int NP> struct Mono {
+  static __host__ __device__ constexpr int g(int k) { return k < 2 ? k : (k < 6 ? (k - 2) / 2 : (k - 6) / 3); }
+  static __host__ __device__ constexpr int a(int k) {
+    return k < 2 ? 0 : k < 6 ? ((k - 2) % 2 == 0 ? 1 : 0) : ((k - 6) % 3 == 0 ? 2 : (k - 6) % 3 == 1 ? 1 : 0);
+  }
+  static __host__ __device__ constexpr int b(int k) {
+    return k < 2 ? 0 : k < 6 ? ((k - 2) % 2 == 1 ? 1 : 0) : ((k - 6) % 3 == 2 ? 2 : (k - 6) % 3 == 1 ? 1 : 0);
+  }
+  static __host__ __device__ constexpr float c(int k) { return (k >= 6 && (k - 6) % 3 != 1) ? 0.5f : 1.f; }
+};
+
+template <int NP> struct Mom {
+  static constexpr int kDeg = NP == 12 ? 2 : 1;    // degree of the warp in Y
+  static constexpr int kNB = 2 * kDeg + 1;          // Y powers in A: 0 .. 2 deg
+  static constexpr int kNBV = kDeg + 1;             // Y powers in b
+  static constexpr int kGG = 0;                     // [3][kNB]  xx, xy, yy
+  static constexpr int kVG = 3 * kNB;               // [2][kNBV]
+  static constexpr int kChi = kVG + 2 * kNBV;
+  static constexpr int kOob = kChi + 1;
+  static constexpr int kN = kOob + 1;
+};
+
+// One pixel into the lane's moment accumulators.
+template <int NP>
+__device__ __forceinline__ void accumulate_moments(float *mom, float V, float wx, float wy, float Y) {
+  using M = Mom<NP>;
+  float gxx = wx * wx, gxy = wx * wy, gyy = wy * wy, vx = V * wx, vy = V * wy;
+  mom[M::kChi] = fmaf(V, V, mom[M::kChi]);
+  float yp = 1.f;
+#pragma unroll
+  for (int b = 0; b < M::kNB; ++b) {
+    if (b == 0) {
+      mom[M::kGG + 0] += gxx; mom[M::kGG + M::kNB] += gxy; mom[M::kGG + 2 * M::kNB] += gyy;
+      mom[M::kVG + 0] += vx; mom[M::kVG + M::kNBV] += vy;
+    } else {
+      yp = b == 1 ? Y : yp * Y;
+      mom[M::kGG + b] = fmaf(gxx, yp, mom[M::kGG + b]);
+      mom[M::kGG + M::kNB + b] = fmaf(gxy, yp, mom[M::kGG + M::kNB + b]);
+      mom[M::kGG + 2 * M::kNB + b] = fmaf(gyy, yp, mom[M::kGG + 2 * M::kNB + b]);
+      if (b < M::kNBV) {
+        mom[M::kVG + b] = fmaf(vx, yp, mom[M::kVG + b]);
+        mom[M::kVG + M::kNBV + b] = fmaf(vy, yp, mom[M::kVG + M::kNBV + b]);
+      }
+    }
+  }
+}
+
+// Expand the lane's moments with its X = dx into the packed upper-triangular A, b, chi, oob,
+// warp-reduce, and add into the warp's shared accumulator row. Clears the moments.
+template <int NP>
+__device__ __forceinline__ void flush_moments(float *mom, float X, float *warp_acc) {
+  using M = Mom<NP>;
+  using L = Acc<NP>;
+  using MO = Mono<NP>;
+  const int lane = threadIdx.x & 31;
+  float xp[5];
+  xp[0] = 1.f; xp[1] = X; xp[2] = X * X; xp[3] = xp[2] * X; xp[4] = xp[2] * xp[2];
+  int k = 0;
+#pragma unroll
+  for (int p1 = 0; p1 < NP; ++p1) {
+#pragma unroll
+    for (int p2 = p1; p2 < NP; ++p2) {
+      const int gg = MO::g(p1) + MO::g(p2); // 0 xx, 1 xy, 2 yy
+      const int a = MO::a(p1) + MO::a(p2), b = MO::b(p1) + MO::b(p2);
+      float v = MO::c(p1) * MO::c(p2) * xp[a] * mom[M::kGG + gg * M::kNB + b];
+      v = warp_sum(v);
+      if (lane == 0) warp_acc[k] += v;
+      ++k;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float v = MO::c(p) * xp[MO::a(p)] * mom[M::kVG + MO::g(p) * M::kNBV + MO::b(p)];
+    v = warp_sum(v);
+    if (lane == 0) warp_acc[L::kB + p] += v;
+  }
+  {
+    float v = warp_sum(mom[M::kChi]);
+    float o = warp_sum(mom[M::kOob]);
+    if (lane == 0) { warp_acc[L::kChi] += v; warp_acc[L::kOob] += o; }
+  }
+#pragma unroll
+  for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
+}
+
+// ---- staging: u8 rows -> fp32 shared memory, 4 pixels per lane per step (one 32-bit load, four
+// PRMT + FADD conversions, one 128-bit shared store). Pixels outside the image are stored as 0;
+// they are never used by an in-bounds sample.
+__device__ __forceinline__ void stage_rows(const LevelImage &img, int px0 /*multiple of 4*/, int py0,
+                                           int width4 /*float4 per row, <= 16*/, int height, float *dst,
+                                           int dst_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int c4 = lane & 15, half = lane >> 4; // 16 lanes per row, two rows per step
+  const int x = px0 + 4 * c4;
+  const bool col_ok = c4 < width4 && x >= 0 && x < img.pitch - 3;
+  for (int r = half; r < height; r += 2) {
+    const int y = py0 + r;
+    if (c4 < width4) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && y >= 0 && y < img.rows) {
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img.ptr + (size_t)y * img.pitch + x));
+        f = make_float4(u8_to_float(v, 0), u8_to_float(v, 1), u8_to_float(v, 2), u8_to_float(v, 3));
+      }
+      *reinterpret_cast<float4 *>(dst + r * dst_pitch + 4 * c4) = f;
+    }
+  }
+}
+
+__device__ __forceinline__ float floor_magic(float x, int &i) {
+  // floor for 0 <= x < 2^22 without the conversion pipe: round-down add of 2^23
+  float m = __fadd_rd(x, 8388608.0f);
+  i = __float_as_int(m) & 0x7fffff;
+  return m - 8388608.0f;
+}
+
+// Deformed position of pixel (X = x - cx, Y = y - cy): per-lane constants in X, polynomial in Y.
+// Parity mode evaluates the reference's left-to-right fp32 expression instead (warp_point).
+template <int NP> struct LaneWarp {
+  float cx0, cx1, cx2, cy0, cy1, cy2;
+  __device__ __forceinline__ void set(const float *p, float x, float X) {
+    // x' = x + u + ux X + uy Y (+ 1/2 uxx X^2 + uxy X Y + 1/2 uyy Y^2)
+    cx0 = x + p[0] + p[2] * X; cx1 = p[3]; cx2 = 0.f;
+    cy0 = p[1] + p[4] * X; cy1 = p[5]; cy2 = 0.f;       // y' = y + v + vx X + vy Y (+ ...)
+    if (NP == 12) {
+      cx0 += 0.5f * p[6] * X * X; cx1 += p[7] * X; cx2 = 0.5f * p[8];
+      cy0 += 0.5f * p[9] * X * X; cy1 += p[10] * X; cy2 = 0.5f * p[11];
+    }
+  }
+};
+
+// One staged pixel: deformed position from the lane constants, 4x4 fp32 gather from the staged
+// patch, bicubic, residual, moments. `mf` is 1 for member pixels and 0 otherwise (FULL: no mask).
+template <int MODEL, int MODE, bool FULL>
+__device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<model_nparams(MODEL)> &lw,
+                                             float xf, float yf, float ccx, float ccy, const float *patch,
+                                             int px0, int py0, float und_w, float mf, float *mom) {
+  constexpr int NP = model_nparams(MODEL);
+  const float Y = __fsub_rn(yf, ccy);
+  float xd, yd;
+  if (MODE == DIC_MODE_PARITY) {
+    float dxx, dyy;
+    warp_point<MODEL, MODE>(pw, xf, yf, ccx, ccy, xd, yd, dxx, dyy);
+  } else {
+    xd = fmaf(fmaf(lw.cx2, Y, lw.cx1), Y, lw.cx0);
+    yd = fmaf(fmaf(lw.cy2, Y, lw.cy1), Y, lw.cy0) + yf;
+  }
+  int ix, iy;
+  const float fx = floor_magic(xd, ix), fy = floor_magic(yd, iy);
+  const float *q = patch + (iy - 1 - py0) * kPatchW + (ix - 1 - px0);
+  float pp[4][4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) pp[rr][cc] = q[rr * kPatchW + cc];
+  float w, wx, wy;
+  if (MODE == DIC_MODE_PARITY) bicubic_parity(pp, xd, yd, ix, iy, w, wx, wy);
+  else bicubic_fast(pp, xd - fx, yd - fy, w, wx, wy);
+  float V = und_w - w;
+  if (!FULL) { V *= mf; wx *= mf; wy *= mf; }
+  accumulate_moments<NP>(mom, V, wx, wy, Y);
+}
+
+// ---- one evaluation over a range of work units of one level. A unit is `rpu` consecutive rows
+// of one tile (rpu = 16 >> split_log2): coarse levels and small subsets split their tiles so
+// that every resident warp has work; units keep the column-major strip order.
+template <int MODEL, int MODE>
+__device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const SectorDev *sec,
+                                               const TileLevel tl, int level, const float *p,
+                                               int unit_begin, int unit_end, int split_log2, float *patch,
+                                               float *und_tile, float *warp_acc) {
+  constexpr int NP = model_nparams(MODEL);
+  using M = Mom<NP>;
+  const int lane = threadIdx.x & 31;
+  const LevelImage und = cfg.und[level];
+  const LevelImage def = cfg.def[level];
+  const float inv = 1.f / (float)(1 << level);
+  const float ccx = sec->cx * inv, ccy = sec->cy * inv;
+  const int rpu = kTileH >> split_log2;
+  float mom[M::kN];
+#pragma unroll
+  for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
+  // parity mode replays the reference's warp expression per pixel: keep the parameters in
+  // registers there; fast mode only needs them at unit set-up (shared memory is fine)
+  float preg[MODE == DIC_MODE_PARITY ? NP : 1];
+  if (MODE == DIC_MODE_PARITY) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) preg[i] = p[i];
+  }
+  const float *pw = MODE == DIC_MODE_PARITY ? preg : p;
+
+  int cur_x0 = INT_MIN;
+  float X = 0.f, xf = 0.f;
+  LaneWarp<NP> lw;
+  lw.set(p, 0.f, 0.f);
+
+  for (int u = unit_begin; u < unit_end; ++u) {
+    const Tile *tp = tl.tiles + (u >> split_log2);
+    const int r0 = (u & ((1 << split_log2) - 1)) * rpu;
+    const int x0 = __ldg(&tp->x0), y0 = __ldg(&tp->y0) + r0;
+    // this lane's column of the membership mask: bit r <=> pixel (x0 + lane, y0 + r)
+    uint32_t colmask = 0, all_rows = 0xffffffffu;
+    for (int r = 0; r < rpu; ++r) {
+      const uint32_t m = __ldg(&tp->rows[r0 + r]);
+      colmask |= ((m >> lane) & 1u) << r;
+      all_rows &= m;
+    }
+    if (__all_sync(0xffffffffu, colmask == 0)) continue; // empty row chunk of a partial tile
+    if (x0 != cur_x0) {
+      if (cur_x0 != INT_MIN) flush_moments<NP>(mom, X, warp_acc);
+      cur_x0 = x0;
+      xf = (float)(x0 + lane);
+      X = __fsub_rn(xf, ccx);
+      lw.set(p, xf, X);
+    }
+    // footprint of the unit under the current parameters (corners, widened for curvature)
+    float bx0, bx1, by0, by1;
+    {
+      const float Xa = (float)x0 - ccx, Xb = (float)(x0 + kTileW - 1) - ccx;
+      const float Ya = (float)y0 - ccy, Yb = (float)(y0 + rpu - 1) - ccy;
+      bx0 = by0 = 3.0e38f; bx1 = by1 = -3.0e38f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float Xc = (c & 1) ? Xb : Xa, Yc = (c & 2) ? Yb : Ya;
+        float xd = Xc + ccx + p[0] + p[2] * Xc + p[3] * Yc;
+        float yd = Yc + ccy + p[1] + p[4] * Xc + p[5] * Yc;
+        if (NP == 12) {
+          xd += 0.5f * p[6] * Xc * Xc + p[7] * Xc * Yc + 0.5f * p[8] * Yc * Yc;
+          yd += 0.5f * p[9] * Xc * Xc + p[10] * Xc * Yc + 0.5f * p[11] * Yc * Yc;
+        }
+        bx0 = fminf(bx0, xd); bx1 = fmaxf(bx1, xd); by0 = fminf(by0, yd); by1 = fmaxf(by1, yd);
+      }
+      float slack = 0.01f;
+      if (NP == 12)
+        slack += 128.f * (fabsf(p[6]) + fabsf(p[9])) + 32.f * (fabsf(p[8]) + fabsf(p[11]));
+      bx0 -= slack; by0 -= slack; bx1 += slack; by1 += slack;
+    }
+    // staged window: columns [px0, px0 + 4*w4), rows [py0, py0 + h)
+    const int px0 = ((int)floorf(bx0) - 1) & ~3, py0 = (int)floorf(by0) - 1;
+    const int pxe = (int)floorf(bx1) + 3, pye = (int)floorf(by1) + 3; // exclusive
+    const int w4 = (pxe - px0 + 3) >> 2, h = pye - py0;
+    const bool inside = bx0 > 1.f && by0 > 1.f && bx1 < (float)def.cols - 2.f && by1 < (float)def.rows - 2.f;
+    const bool staged = inside && w4 * 4 <= kPatchW && h <= kPatchH && w4 > 0 && h > 0;
+    __syncwarp();
+    stage_rows(und, x0 & ~3, y0, (x0 & 3) ? 9 : 8, rpu, und_tile, kTileW + 8);
+    if (staged) stage_rows(def, px0, py0, w4, h, patch, kPatchW);
+    __syncwarp();
+    const float *ucol = und_tile + (x0 & 3) + lane;
+
+    if (staged) {
+      if (all_rows == 0xffffffffu) {
+#pragma unroll 2
+        for (int r = 0; r < rpu; ++r)
+          staged_pixel<MODEL, MODE, true>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
+                                          ucol[r * (kTileW + 8)], 1.f, mom);
+      } else {
+#pragma unroll 2
+        for (int r = 0; r < rpu; ++r)
+          staged_pixel<MODEL, MODE, false>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
+                                           ucol[r * (kTileW + 8)], (float)((colmask >> r) & 1u), mom);
+      }
+    } else {
+      // footprint leaves the image or the staging buffer: per-pixel path with the reference's
+      // own bounds test (error 2 + zero contribution, interpolation_class.cpp:129-137)
+#pragma unroll 1
+      for (int r = 0; r < rpu; ++r) {
+        if (!((colmask >> r) & 1u)) continue;
+        const float yf = (float)(y0 + r);
+        float xd, yd, dxx, dyy, w, wx, wy;
+        warp_point<MODEL, MODE>(p, xf, yf, ccx, ccy, xd, yd, dxx, dyy);
+        if (!sample_def<DIC_IM_BICUBIC, MODE>(def, xd, yd, w, wx, wy)) mom[M::kOob] += 1.f;
+        accumulate_moments<NP>(mom, ucol[r * (kTileW + 8)] - w, wx, wy, dyy);
+      }
+    }
+  }
+  if (cur_x0 != INT_MIN) flush_moments<NP>(mom, X, warp_acc);
+}
+
+// Duplicate pixels of a blob list (beyond their first occurrence), handled by one warp.
+template <int MODEL, int MODE>
+__device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, const SectorDev *sec,
+                                                const TileLevel tl, int level, const float *p,
+                                                float *warp_acc) {
+  constexpr int NP = model_nparams(MODEL);
+  using M = Mom<NP>;
+  const int lane = threadIdx.x & 31;
+  const LevelImage und = cfg.und[level];
+  const LevelImage def = cfg.def[level];
+  const float inv = 1.f / (float)(1 << level);
+  const float ccx = sec->cx * inv, ccy = sec->cy * inv;
+  float mom[M::kN];
+#pragma unroll
+  for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
+  for (int base = 0; base < tl.n_extra; base += 32) {
+    const int i = base + lane;
+    float Xe = 0.f;
+    if (i < tl.n_extra) {
+      float2 q = __ldg(tl.extra + i);
+      float xd, yd, dxx, dyy, w, wx, wy;
+      warp_point<MODEL, MODE>(p, q.x, q.y, ccx, ccy, xd, yd, dxx, dyy);
+      if (!sample_def<DIC_IM_BICUBIC, MODE>(def, xd, yd, w, wx, wy)) mom[M::kOob] += 1.f;
+      int uix = (int)(q.x + 0.5f), uiy = (int)(q.y + 0.5f);
+      float V = (float)__ldg(und.ptr + (size_t)uiy * und.pitch + uix) - w;
+      accumulate_moments<NP>(mom, V, wx, wy, dyy);
+      Xe = dxx;
+    }
+    flush_moments<NP>(mom, Xe, warp_acc);
+  }
+}
+
+// ---- the solve kernel on tiles (same LM / barrier / solve machinery as gn_solve_kernel)
+template <int MODEL, int MODE, bool GRID>
+__global__ void __launch_bounds__(kThreads, 2)
+gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
+                      const SectorTiles *__restrict__ sector_tiles, const float *__restrict__ guesses,
+                      dic_result *__restrict__ results, int first_sector, int n_sectors, GridWork *work,
+                      float *partials) {
+  constexpr int NP = model_nparams(MODEL);
+  constexpr int NACC = Acc<NP>::kN;
+  extern __shared__ __align__(16) float dyn_smem[];
+  float *s_patch = dyn_smem;                                          // [warps][kPatchH*kPatchW]
+  float *s_und = s_patch + kWarpsPerCta * kPatchH * kPatchW;          // [warps][kTileH*(kTileW+8)]
+  float *s_wacc = s_und + kWarpsPerCta * kTileH * (kTileW + 8);       // [warps][NACC]
+  __shared__ SolveShared<NP> sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float *patch = s_patch + warp * kPatchH * kPatchW;
+  float *und_tile = s_und + warp * kTileH * (kTileW + 8);
+  float *warp_acc = s_wacc + warp * NACC;
+
+  for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
+    const SectorDev *sec = sectors + first_sector + si;
+    const SectorTiles *stl = sector_tiles + first_sector + si;
+    const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
+    dic_result *result = results + first_sector + si;
+    unsigned int my_gen;
+    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, work, my_gen);
+    while (true) {
+      const int level = sh.level;
+      for (int k = lane; k < NACC; k += 32) warp_acc[k] = 0.f;
+      __syncwarp();
+      TileLevel tl;
+      tl.tiles = stl->lev[level].tiles; tl.n_tiles = stl->lev[level].n_tiles;
+      tl.extra = stl->lev[level].extra; tl.n_extra = stl->lev[level].n_extra;
+      // split tiles into row chunks until every warp that can take part has a unit (rpu >= 4)
+      const int warps_avail = GRID ? (int)gridDim.x * kWarpsPerCta : kWarpsPerCta;
+      int split_log2 = 0;
+      while (split_log2 < 2 && (tl.n_tiles << split_log2) < warps_avail) ++split_log2;
+      const int n_units = tl.n_tiles << split_log2;
+      int n_active = 1;
+      bool active = true;
+      if (GRID) {
+        n_active = max(1, min((n_units + kWarpsPerCta - 1) / kWarpsPerCta, (int)gridDim.x));
+        active = (int)blockIdx.x < n_active;
+      }
+      if (active) {
+        const int nw = n_active * kWarpsPerCta;
+        const int wg = GRID ? blockIdx.x * kWarpsPerCta + warp : warp;
+        const int per = (n_units + nw - 1) / nw;
+        const int ub = min(n_units, wg * per), ue = min(n_units, ub + per);
+        evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, und_tile, warp_acc);
+        if (tl.n_extra > 0 && wg == 0) evaluate_extras<MODEL, MODE>(cfg, sec, tl, level, sh.p, warp_acc);
+      }
+      __syncthreads();
+      for (int k = tid; k < NACC; k += kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) s += s_wacc[w * NACC + k];
+        sh.tot[k] = s;
+      }
+      __syncthreads();
+      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, partials, my_gen);
+      if (sh.done) break;
+    }
+    __syncthreads();
+  }
+}
+
+constexpr size_t tiles_dyn_smem(int nacc) {
+  return sizeof(float) * (size_t)kWarpsPerCta * (kPatchH * kPatchW + kTileH * (kTileW + 8) + nacc);
+}
+
+// ------------------------------------------------------------------ tile construction
+
+// Scatter a level's pixel list into the mask grid (column-major slots). A pixel whose bit is
+// already set is a duplicate of the reference list and goes to `extra`.
+__global__ void tiles_scatter_kernel(const float2 *__restrict__ xy, long n, int gx0, int gy0, int nty,
+                                     uint32_t *masks, float2 *extra, int extra_cap, int *n_extra) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 q = xy[i];
+  int x = (int)(q.x + 0.5f) - gx0, y = (int)(q.y + 0.5f) - gy0;
+  int tx = x / kTileW, ty = y / kTileH;
+  uint32_t bit = 1u << (x - tx * kTileW);
+  uint32_t old = atomicOr(&masks[((size_t)tx * nty + ty) * kTileH + (y - ty * kTileH)], bit);
+  if (old & bit) {
+    int k = atomicAdd(n_extra, 1);
+    if (k < extra_cap) extra[k] = q;
+  }
+}
+
+struct TilePred {
+  const uint32_t *masks;
+  int gx0, gy0, nty;
+  __device__ __forceinline__ bool operator()(long idx, Tile &out) const {
+    const uint32_t *m = masks + (size_t)idx * kTileH;
+    uint32_t any = 0;
+#pragma unroll
+    for (int r = 0; r < kTileH; ++r) { out.rows[r] = m[r]; any |= m[r]; }
+    int tx = (int)(idx / nty), ty = (int)(idx % nty);
+    out.x0 = gx0 + tx * kTileW; out.y0 = gy0 + ty * kTileH;
+    return any != 0;
+  }
+};
+
+template <class Pred, class Out, bool EMIT>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_any_kernel(Pred pred, long ncand, unsigned int *block_counts,
+                   const unsigned long long *block_offsets, Out *__restrict__ out) {
+  __shared__ unsigned int warp_tot[kCompactThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long base = (long)blockIdx.x * kCompactChunk;
+  unsigned long long running = EMIT ? block_offsets[blockIdx.x] : 0ull;
+  unsigned int total = 0;
+  for (int it = 0; it < kCompactItems; ++it) {
+    long idx = base + (long)it * kCompactThreads + tid;
+    Out q;
+    bool keep = idx < ncand && pred(idx, q);
+    unsigned int bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactThreads / 32; ++w) {
+      unsigned int t = warp_tot[w];
+      if (w < warp) before += t;
+      all += t;
+    }
+    if (EMIT && keep) out[running + before + __popc(bal & ((1u << lane) - 1u))] = q;
+    running += all;
+    total += all;
+    __syncthreads();
+  }
+  if (!EMIT && tid == 0) block_counts[blockIdx.x] = total;
+}
+
+// integer bounding box of a list (for blob / point-list sectors)
+__global__ void bbox_kernel(const float2 *__restrict__ xy, long n, int *box /*minx miny maxx maxy*/) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+  for (; i < n; i += (long)gridDim.x * blockDim.x) {
+    float2 q = xy[i];
+    int x = (int)(q.x + 0.5f), y = (int)(q.y + 0.5f);
+    mnx = min(mnx, x); mny = min(mny, y); mxx = max(mxx, x); mxy = max(mxy, y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&box[0], mnx); atomicMin(&box[1], mny); atomicMax(&box[2], mxx); atomicMax(&box[3], mxy);
+  }
+}
+
+} // namespace dic

@@ -55,7 +55,7 @@ _lib = None
 EXPORTS = [
     "dic_device_count", "dic_create", "dic_destroy", "dic_last_error", "dic_set_max_iters",
     "dic_set_precision", "dic_set_fitting_model", "dic_set_interpolation_model",
-    "dic_set_arith_mode", "dic_set_center_mode", "dic_reset_image_pyramids",
+    "dic_set_arith_mode", "dic_set_center_mode", "dic_set_kernel_variant", "dic_reset_image_pyramids",
     "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_device",
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
@@ -63,7 +63,7 @@ EXPORTS = [
     "dic_update_polygon", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
-    "dic_last_correlate_ms", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
+    "dic_last_correlate_ms", "dic_get_timeline", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library():
         "dic_set_interpolation_model": (I, [P, I]),
         "dic_set_arith_mode": (I, [P, I]),
         "dic_set_center_mode": (I, [P, I]),
+        "dic_set_kernel_variant": (I, [P, I]),
         "dic_reset_image_pyramids": (I, [P, P, P, P, I, I, I, I, I, I]),
         "dic_reset_image_pyramids_device": (I, [P, P, P, P, I, I, I, I, I, I]),
         "dic_reset_next_pyramid": (I, [P, P, I, I]),
@@ -115,6 +116,7 @@ def load_library():
         "dic_evaluate": (I, [P, I, I, P, P, P, fp, C.POINTER(I)]),
         "dic_solve_step": (I, [P, P, P, F, F, P]),
         "dic_last_correlate_ms": (F, [P]),
+        "dic_get_timeline": (I, [P, P, I]),
         "dic_kernel_launches": (I64, [P]),
         "dic_correlation_stream": (P, [P]),
         "dic_synchronize": (I, [P]),
@@ -191,6 +193,9 @@ class CudaEngine:
 
     def set_center_mode(self, m):
         self._ck(self.lib.dic_set_center_mode(self.h, int(m)))
+
+    def set_kernel_variant(self, v):
+        self._ck(self.lib.dic_set_kernel_variant(self.h, int(v)))
 
     # -- images
     @staticmethod
@@ -334,6 +339,11 @@ class CudaEngine:
 
     def last_correlate_ms(self):
         return float(self.lib.dic_last_correlate_ms(self.h))
+
+    def timeline(self):
+        m = np.zeros((128, 4), np.uint64)
+        n = self.lib.dic_get_timeline(self.h, _ptr(m), 128)
+        return m[:n].astype(np.int64)
 
     def kernel_launches(self):
         return int(self.lib.dic_kernel_launches(self.h))

@@ -103,6 +103,9 @@ int dic_set_interpolation_model(dic_engine *e, int interpolation_model);
 /* extensions */
 int dic_set_arith_mode(dic_engine *e, int arith_mode);
 int dic_set_center_mode(dic_engine *e, int center_mode);
+/* 0 = automatic (tile kernel for integer-grid domains with the affine / quadratic model and
+ * bicubic interpolation, pixel-list kernel otherwise), 1 = force the pixel-list kernel */
+int dic_set_kernel_variant(dic_engine *e, int variant);
 
 /* ---- CudaClass::resetImagePyramids(undPath, defPath, nxtPath, color, start, step, stop)
  *      (cuda_class.cu:512-572): host u8 images (row-major, `channels` interleaved; only
@@ -183,6 +186,9 @@ int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float la
 /* device-side time of the last correlate / correlate_batch launch in milliseconds (CUDA events
  * on the correlation stream) and how many kernels this engine has launched so far */
 float dic_last_correlate_ms(dic_engine *e);
+/* master-CTA timeline of the last single-sector correlate: per evaluation 4 device timestamps (ns):
+ * pass start, own pass done, all CTAs arrived, LM step published. Returns the evaluation count. */
+int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap);
 int64_t dic_kernel_launches(const dic_engine *e);
 /* the CUDA stream handle (cudaStream_t as void*) the GN kernels run on, for event timing */
 void *dic_correlation_stream(dic_engine *e);

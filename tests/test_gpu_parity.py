@@ -333,3 +333,41 @@ def test_full_size_c1_recovers_truth_and_matches_oracle(eng):
     # idempotence: restarting from the answer stays there
     again = eng.correlate(0, got["params"])
     assert np.abs(again["params"][:2] - got["params"][:2]).max() < 1e-3
+
+
+# ---------------------------------------------------------------- tile kernel == pixel-list kernel
+
+@pytest.mark.parametrize("model", [engine.FM_UVUxUyVxVy, engine.FM_QUADRATIC])
+@pytest.mark.parametrize("mode", [engine.MODE_PARITY, engine.MODE_FAST])
+@pytest.mark.parametrize("domain", ["rect", "annulus", "blob", "rect_edge"])
+def test_tile_kernel_equals_list_kernel(eng, model, mode, domain):
+    truth = (1.3, -0.9, 0.003, 0.002, -0.002, 0.004)
+    und, dfm = synth.make_pair(420, 400, 51, truth, center=(200, 210))
+    eng.set_fitting_model(model)
+    eng.set_arith_mode(mode)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    if domain == "rect":
+        assert eng.resetPolygon(0, 37, 41, 361, 377) == 0
+    elif domain == "rect_edge":  # tiles whose footprint touches the image border: per-pixel path
+        assert eng.resetPolygon(0, 6, 6, 390, 410) == 0
+    elif domain == "annulus":
+        assert eng.resetPolygon(0, 50.0, 120.0, 0.3, 2.2, 200.0, 210.0, 2) == 0
+    else:
+        assert eng.resetPolygon(0, synth.star_polygon(200.0, 210.0, 130.0, n_vertices=32, seed=8)) == 0
+    n = eng.n_params
+    res = {}
+    for variant in (1, 0):
+        eng.set_kernel_variant(variant)
+        res[variant] = eng.correlate(0, np.zeros(n))
+    eng.set_kernel_variant(0)
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    a, b = res[1], res[0]
+    assert a["error_code"] == b["error_code"] == 0
+    assert a["number_of_points"] == b["number_of_points"]
+    assert a["evaluations"] == b["evaluations"]
+    d = np.abs(a["params"] - b["params"])
+    # same per-pixel arithmetic in parity mode; only the summation tree differs
+    tol = (2e-5, 2e-7) if mode == engine.MODE_PARITY else (1e-4, 1e-6)
+    assert d[:2].max() < tol[0] and d[2:6].max() < tol[1], (a["params"], b["params"])
+    assert abs(a["chi"] - b["chi"]) < (2e-5 if mode == engine.MODE_PARITY else 1e-4) * b["chi"]
