@@ -389,7 +389,7 @@ int build_tiles(dic_engine *e, Sector &s, bool may_have_duplicates) {
     if (box[0] < 0 || box[1] < 0) return DIC_OK; // negative coordinates: keep the list kernel
     Grid q;
     q.l = l;
-    q.gx0 = box[0] / kTileW * kTileW; q.gy0 = box[1] / kTileH * kTileH;
+    q.gx0 = box[0]; q.gy0 = box[1]; // tiles start at the domain's own corner: no partial first row / column
     q.ntx = (box[2] - q.gx0) / kTileW + 1; q.nty = (box[3] - q.gy0) / kTileH + 1;
     q.slots = (size_t)q.ntx * q.nty;
     total_slots += q.slots;

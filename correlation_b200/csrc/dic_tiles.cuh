@@ -21,7 +21,7 @@
 namespace dic {
 
 constexpr int kTileW = 32, kTileH = 16;
-constexpr int kPatchW = 48, kPatchH = 24; // fp32 staging of the deformed footprint, per warp
+constexpr int kPatchW = 48, kPatchH = 24; // 48 = 32 + halo 3 + strain margin + 8-byte alignment // fp32 staging of the deformed footprint, per warp
 constexpr int kWarpsPerCta = kThreads / 32;
 
 struct Tile {
@@ -90,6 +90,40 @@ __device__ __forceinline__ void accumulate_moments(float *mom, float V, float wx
   }
 }
 
+// Warp transpose-reduction of N per-lane values (N padded to a multiple of 32): five butterfly
+// stages, each halving the values a lane still carries, N - N/32 shuffles in total instead of 5 N.
+// On return lane l holds in v[j] (j < NPAD/32) the warp total of value index (j * 32 + perm(l)),
+// where perm(l) reverses nothing: index = j * 32 + l with the bit order produced below.
+template <int NPAD>
+__device__ __forceinline__ void warp_transpose_sum(float *v) {
+  const int lane = threadIdx.x & 31;
+  int cnt = NPAD;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int half = cnt >> 1;
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < NPAD / 2; ++i) {
+      if (i < half) {
+        const float keep = up ? v[i + half] : v[i];
+        const float give = up ? v[i] : v[i + half];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, give, o);
+      }
+    }
+    cnt = half;
+  }
+}
+// value index held by `lane` in slot j after warp_transpose_sum<NPAD>
+template <int NPAD>
+__device__ __forceinline__ int transpose_index(int lane, int j) {
+  // stage o keeps the upper half of the current range when (lane & o): the final index is
+  // sum over stages of (bit ? half_size_at_that_stage : 0) + j
+  int idx = 0, half = NPAD >> 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { idx += (lane & o) ? half : 0; half >>= 1; }
+  return idx + j;
+}
+
 // Expand the lane's moments with its X = dx into the packed upper-triangular A, b, chi, oob,
 // warp-reduce, and add into the warp's shared accumulator row. Clears the moments.
 template <int NP>
@@ -97,9 +131,11 @@ __device__ __forceinline__ void flush_moments(float *mom, float X, float *warp_a
   using M = Mom<NP>;
   using L = Acc<NP>;
   using MO = Mono<NP>;
+  constexpr int NPAD = (L::kN + 31) / 32 * 32;
   const int lane = threadIdx.x & 31;
   float xp[5];
   xp[0] = 1.f; xp[1] = X; xp[2] = X * X; xp[3] = xp[2] * X; xp[4] = xp[2] * xp[2];
+  float v[NPAD];
   int k = 0;
 #pragma unroll
   for (int p1 = 0; p1 < NP; ++p1) {
@@ -107,46 +143,50 @@ __device__ __forceinline__ void flush_moments(float *mom, float X, float *warp_a
     for (int p2 = p1; p2 < NP; ++p2) {
       const int gg = MO::g(p1) + MO::g(p2); // 0 xx, 1 xy, 2 yy
       const int a = MO::a(p1) + MO::a(p2), b = MO::b(p1) + MO::b(p2);
-      float v = MO::c(p1) * MO::c(p2) * xp[a] * mom[M::kGG + gg * M::kNB + b];
-      v = warp_sum(v);
-      if (lane == 0) warp_acc[k] += v;
+      v[k] = MO::c(p1) * MO::c(p2) * xp[a] * mom[M::kGG + gg * M::kNB + b];
       ++k;
     }
   }
 #pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    float v = MO::c(p) * xp[MO::a(p)] * mom[M::kVG + MO::g(p) * M::kNBV + MO::b(p)];
-    v = warp_sum(v);
-    if (lane == 0) warp_acc[L::kB + p] += v;
+  for (int p = 0; p < NP; ++p)
+    v[L::kB + p] = MO::c(p) * xp[MO::a(p)] * mom[M::kVG + MO::g(p) * M::kNBV + MO::b(p)];
+  v[L::kChi] = mom[M::kChi];
+  v[L::kOob] = mom[M::kOob];
+#pragma unroll
+  for (int i = L::kN; i < NPAD; ++i) v[i] = 0.f;
+  warp_transpose_sum<NPAD>(v);
+#pragma unroll
+  for (int j = 0; j < NPAD / 32; ++j) {
+    const int idx = transpose_index<NPAD>(lane, j);
+    if (idx < L::kN) warp_acc[idx] += v[j];
   }
-  {
-    float v = warp_sum(mom[M::kChi]);
-    float o = warp_sum(mom[M::kOob]);
-    if (lane == 0) { warp_acc[L::kChi] += v; warp_acc[L::kOob] += o; }
-  }
+  __syncwarp();
 #pragma unroll
   for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
 }
 
-// ---- staging: u8 rows -> fp32 shared memory, 4 pixels per lane per step (one 32-bit load, four
-// PRMT + FADD conversions, one 128-bit shared store). Pixels outside the image are stored as 0;
-// they are never used by an in-bounds sample.
-__device__ __forceinline__ void stage_rows(const LevelImage &img, int px0 /*multiple of 4*/, int py0,
-                                           int width4 /*float4 per row, <= 16*/, int height, float *dst,
-                                           int dst_pitch) {
+// ---- staging: u8 rows -> fp32 shared memory, 8 pixels per lane per step (one 64-bit load, eight
+// PRMT + FADD conversions, two 128-bit shared stores); 8 lanes per row, 4 rows per step. Pixels
+// outside the image are stored as 0; they are never used by an in-bounds sample.
+__device__ __forceinline__ void stage_rows(const LevelImage &img, int px0 /*multiple of 8*/, int py0,
+                                           int width8 /*8-pixel groups per row, <= 8*/, int height,
+                                           float *dst, int dst_pitch) {
   const int lane = threadIdx.x & 31;
-  const int c4 = lane & 15, half = lane >> 4; // 16 lanes per row, two rows per step
-  const int x = px0 + 4 * c4;
-  const bool col_ok = c4 < width4 && x >= 0 && x < img.pitch - 3;
-  for (int r = half; r < height; r += 2) {
+  const int c8 = lane & 7, sub = lane >> 3;
+  const int x = px0 + 8 * c8;
+  const bool col_ok = c8 < width8 && x >= 0 && x < img.pitch - 7;
+  for (int r = sub; r < height; r += 4) {
     const int y = py0 + r;
-    if (c4 < width4) {
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c8 < width8) {
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
       if (col_ok && y >= 0 && y < img.rows) {
-        uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img.ptr + (size_t)y * img.pitch + x));
-        f = make_float4(u8_to_float(v, 0), u8_to_float(v, 1), u8_to_float(v, 2), u8_to_float(v, 3));
+        uint2 v = __ldg(reinterpret_cast<const uint2 *>(img.ptr + (size_t)y * img.pitch + x));
+        f0 = make_float4(u8_to_float(v.x, 0), u8_to_float(v.x, 1), u8_to_float(v.x, 2), u8_to_float(v.x, 3));
+        f1 = make_float4(u8_to_float(v.y, 0), u8_to_float(v.y, 1), u8_to_float(v.y, 2), u8_to_float(v.y, 3));
       }
-      *reinterpret_cast<float4 *>(dst + r * dst_pitch + 4 * c4) = f;
+      float4 *d = reinterpret_cast<float4 *>(dst + r * dst_pitch + 8 * c8);
+      d[0] = f0;
+      d[1] = f1;
     }
   }
 }
@@ -178,7 +218,7 @@ template <int NP> struct LaneWarp {
 template <int MODEL, int MODE, bool FULL>
 __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<model_nparams(MODEL)> &lw,
                                              float xf, float yf, float ccx, float ccy, const float *patch,
-                                             int px0, int py0, float und_w, float mf, float *mom) {
+                                             int px0, int py0, float und_w, bool member, float *mom) {
   constexpr int NP = model_nparams(MODEL);
   const float Y = __fsub_rn(yf, ccy);
   float xd, yd;
@@ -201,7 +241,7 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
   if (MODE == DIC_MODE_PARITY) bicubic_parity(pp, xd, yd, ix, iy, w, wx, wy);
   else bicubic_fast(pp, xd - fx, yd - fy, w, wx, wy);
   float V = und_w - w;
-  if (!FULL) { V *= mf; wx *= mf; wy *= mf; }
+  if (!FULL) { V = member ? V : 0.f; wx = member ? wx : 0.f; wy = member ? wy : 0.f; }
   accumulate_moments<NP>(mom, V, wx, wy, Y);
 }
 
@@ -280,28 +320,29 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
       bx0 -= slack; by0 -= slack; bx1 += slack; by1 += slack;
     }
     // staged window: columns [px0, px0 + 4*w4), rows [py0, py0 + h)
-    const int px0 = ((int)floorf(bx0) - 1) & ~3, py0 = (int)floorf(by0) - 1;
+    const int px0 = ((int)floorf(bx0) - 1) & ~7, py0 = (int)floorf(by0) - 1;
     const int pxe = (int)floorf(bx1) + 3, pye = (int)floorf(by1) + 3; // exclusive
-    const int w4 = (pxe - px0 + 3) >> 2, h = pye - py0;
+    const int w8 = (pxe - px0 + 7) >> 3, h = pye - py0;
     const bool inside = bx0 > 1.f && by0 > 1.f && bx1 < (float)def.cols - 2.f && by1 < (float)def.rows - 2.f;
-    const bool staged = inside && w4 * 4 <= kPatchW && h <= kPatchH && w4 > 0 && h > 0;
+    const bool staged = inside && w8 * 8 <= kPatchW && h <= kPatchH && w8 > 0 && h > 0;
     __syncwarp();
-    stage_rows(und, x0 & ~3, y0, (x0 & 3) ? 9 : 8, rpu, und_tile, kTileW + 8);
-    if (staged) stage_rows(def, px0, py0, w4, h, patch, kPatchW);
+    if (staged) stage_rows(def, px0, py0, w8, h, patch, kPatchW);
     __syncwarp();
-    const float *ucol = und_tile + (x0 & 3) + lane;
+    // reference-image pixels of this lane's column: one coalesced byte per warp-row
+    const uint8_t *ucol = und.ptr + (size_t)y0 * und.pitch + x0 + lane;
 
     if (staged) {
       if (all_rows == 0xffffffffu) {
 #pragma unroll 2
         for (int r = 0; r < rpu; ++r)
           staged_pixel<MODEL, MODE, true>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
-                                          ucol[r * (kTileW + 8)], 1.f, mom);
+                                          (float)__ldg(ucol + (size_t)r * und.pitch), true, mom);
       } else {
 #pragma unroll 2
         for (int r = 0; r < rpu; ++r)
           staged_pixel<MODEL, MODE, false>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
-                                           ucol[r * (kTileW + 8)], (float)((colmask >> r) & 1u), mom);
+                                           (float)__ldg(ucol + (size_t)r * und.pitch),
+                                           ((colmask >> r) & 1u) != 0, mom);
       }
     } else {
       // footprint leaves the image or the staging buffer: per-pixel path with the reference's
@@ -313,7 +354,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
         float xd, yd, dxx, dyy, w, wx, wy;
         warp_point<MODEL, MODE>(p, xf, yf, ccx, ccy, xd, yd, dxx, dyy);
         if (!sample_def<DIC_IM_BICUBIC, MODE>(def, xd, yd, w, wx, wy)) mom[M::kOob] += 1.f;
-        accumulate_moments<NP>(mom, ucol[r * (kTileW + 8)] - w, wx, wy, dyy);
+        accumulate_moments<NP>(mom, (float)__ldg(ucol + (size_t)r * und.pitch) - w, wx, wy, dyy);
       }
     }
   }
@@ -363,12 +404,11 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
   constexpr int NACC = Acc<NP>::kN;
   extern __shared__ __align__(16) float dyn_smem[];
   float *s_patch = dyn_smem;                                          // [warps][kPatchH*kPatchW]
-  float *s_und = s_patch + kWarpsPerCta * kPatchH * kPatchW;          // [warps][kTileH*(kTileW+8)]
-  float *s_wacc = s_und + kWarpsPerCta * kTileH * (kTileW + 8);       // [warps][NACC]
+  float *s_wacc = s_patch + kWarpsPerCta * kPatchH * kPatchW;        // [warps][NACC]
   __shared__ SolveShared<NP> sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float *patch = s_patch + warp * kPatchH * kPatchW;
-  float *und_tile = s_und + warp * kTileH * (kTileW + 8);
+  float *und_tile = nullptr;
   float *warp_acc = s_wacc + warp * NACC;
 
   for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
@@ -420,7 +460,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
 }
 
 constexpr size_t tiles_dyn_smem(int nacc) {
-  return sizeof(float) * (size_t)kWarpsPerCta * (kPatchH * kPatchW + kTileH * (kTileW + 8) + nacc);
+  return sizeof(float) * (size_t)kWarpsPerCta * (kPatchH * kPatchW + nacc);
 }
 
 // ------------------------------------------------------------------ tile construction

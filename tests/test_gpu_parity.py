@@ -312,7 +312,10 @@ def test_batch_of_subsets_equals_one_by_one_and_oracle(eng):
         single = eng.correlate(k, np.zeros(6))
         assert np.abs(batch[k]["params"] - single["params"]).max() < 2e-6
         want = o.correlate(np.zeros(6), oracle.rect_points(*bx), center=((bx[0] + bx[2]) / 2, (bx[1] + bx[3]) / 2))
-        check_result(batch[k], want)
+        # chi of a 63x63 subset sits ~1e4 below the image contrast, so a 1e-6 px difference in the
+        # (not fully converged, precision 1e-3) final iterate already moves it by 1e-5 relative
+        # (DESIGN.md "chi sensitivity"); parameters keep the strict bound
+        check_result(batch[k], want, tol_chi=1e-4)
 
 
 # ---------------------------------------------------------------- full-size property tests
