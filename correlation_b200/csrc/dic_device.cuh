@@ -18,6 +18,7 @@ constexpr int kMaxLevels = DIC_MAX_LEVELS;
 constexpr int kMaxParams = DIC_MAX_PARAMS;
 constexpr int kThreads = 256; // threads per CTA of the GN kernels
 constexpr int kMaxMarks = 128;
+constexpr int kMaxRanks = 8;
 
 // ------------------------------------------------------------------ descriptors
 
@@ -29,7 +30,8 @@ struct LevelImage {
 // Per-sector device record (one per domain / subdivision subset).
 struct SectorDev {
   const float2 *xy[kMaxLevels]; // per-level pixel list (x, y) in level units
-  int n[kMaxLevels];
+  int n[kMaxLevels];       // pixels this GPU owns at each level
+  int n_total[kMaxLevels]; // pixels of the whole domain (== n unless the domain is row-split over GPUs)
   float cx, cy; // level-0 centre
 };
 
@@ -48,6 +50,12 @@ struct LMState {
   int evals[kMaxLevels], iters[kMaxLevels];
 };
 
+// One rank's mailbox: slot [parity][sender rank] holds the sender's sums of evaluation `seq`.
+struct Mailbox {
+  float sums[2][kMaxRanks][96];
+  unsigned int seq[2][kMaxRanks]; // written last (release): evaluation number + 1
+};
+
 // Grid-wide reduction / barrier scratch (grid mode). CTA 0 is the master: it owns the LM state in
 // its shared memory and publishes only the next command (parameters, level, done).
 struct GridWork {
@@ -56,6 +64,13 @@ struct GridWork {
   float pub_p[kMaxParams];
   int pub_level, pub_done;
   double acc[96]; // grid-wide sums of the current evaluation (fp64 atomics), zeroed by the master
+  // row-split of one domain over several GPUs: every rank's master adds its sums to
+  // every peer's mailbox over NVLink, then all ranks add the rows in rank order (bitwise identical)
+  int rs_rank, rs_world;
+  unsigned int rs_seq;             // evaluations exchanged so far (same on all ranks)
+  int rs_error;                    // set when a peer did not answer in time
+  struct Mailbox *rs_local;        // this rank's mailbox (peers write into it)
+  struct Mailbox *rs_peer[kMaxRanks]; // peer-mapped mailboxes, index = rank
   // master-side timeline of the last launch (ns, %globaltimer): per evaluation
   // [0] pass started, [1] own pass done, [2] all workers arrived, [3] LM step published
   int n_marks;

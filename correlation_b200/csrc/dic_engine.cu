@@ -32,6 +32,8 @@ struct Sector {
   size_t cap = 0;        // in float2
   float2 *xy[kMaxLevels] = {};
   long n[kMaxLevels] = {};
+  long n_total[kMaxLevels] = {}; // whole-domain counts when this GPU holds only a band of rows
+  bool banded = false;
   float cx = 0.f, cy = 0.f;
   bool integer_grid = true;
   // geometry kept for reference-order regeneration
@@ -40,6 +42,7 @@ struct Sector {
   // structured form (dic_tiles.cuh): column-major 32x16 tiles per level (+ duplicate pixels)
   Tile *tbuf = nullptr;
   size_t tcap = 0;
+  bool buf_owned = false, tbuf_owned = false; // false: lives in the engine arena
   float2 *ebuf = nullptr;
   size_t ecap = 0;
   TileLevel tl[kMaxLevels] = {};
@@ -73,7 +76,16 @@ struct dic_engine {
   SectorTiles *d_sector_tiles = nullptr;
   uint32_t *d_masks = nullptr;
   size_t cap_masks = 0;
+  SectorDev *h_sectors = nullptr;      // pinned mirrors: async upload of the sector records
+  SectorTiles *h_sector_tiles = nullptr;
+  // bump arena for small sector buffers (thousands of subsets: no cudaMalloc per sector)
+  std::vector<char *> arena_chunks;
+  char *arena_cur = nullptr;
+  size_t arena_left = 0;
   int kernel_variant = 0; // 0 auto, 1 pixel-list kernel, 2 tile kernel
+  Mailbox *d_mailbox = nullptr; // row-split: peers write their sums here
+  void *peer_mailbox[kMaxRanks] = {};
+  int rs_rank = 0, rs_world = 1;
   float *d_guess = nullptr;
   dic_result *d_results = nullptr;
   dic_result *h_results = nullptr; // pinned
@@ -191,11 +203,37 @@ int set_image(dic_engine *e, int role, const void *src, int rows, int cols, int 
   return build_levels(e, s, e->stop, st);
 }
 
+
+constexpr size_t kArenaChunk = 64u << 20, kArenaMaxAlloc = 4u << 20;
+
+// Device memory for a sector buffer: small requests come from the engine's bump arena (released
+// with the engine), large ones get their own allocation.
+int sector_alloc(dic_engine *e, size_t bytes, void **out, bool *owned) {
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes > kArenaMaxAlloc) {
+    CU_TRY(e, cudaMalloc(out, bytes));
+    *owned = true;
+    return DIC_OK;
+  }
+  if (bytes > e->arena_left) {
+    char *chunk = nullptr;
+    CU_TRY(e, cudaMalloc(&chunk, kArenaChunk));
+    e->arena_chunks.push_back(chunk);
+    e->arena_cur = chunk;
+    e->arena_left = kArenaChunk;
+  }
+  *out = e->arena_cur;
+  e->arena_cur += bytes;
+  e->arena_left -= bytes;
+  *owned = false;
+  return DIC_OK;
+}
+
 int ensure_sector_capacity(dic_engine *e, int n) {
   if (n <= e->cap_sectors) return DIC_OK;
   int cap = std::max(n, std::max(16, e->cap_sectors * 2));
   SectorDev *ds = nullptr; float *dg = nullptr; dic_result *dr = nullptr; SectorTiles *dt = nullptr;
-  dic_result *hr = nullptr; float *hg = nullptr;
+  dic_result *hr = nullptr; float *hg = nullptr; SectorDev *hs = nullptr; SectorTiles *ht = nullptr;
   CU_TRY(e, cudaMalloc(&ds, sizeof(SectorDev) * cap));
   CU_TRY(e, cudaMalloc(&dg, sizeof(float) * kMaxParams * cap));
   CU_TRY(e, cudaMalloc(&dt, sizeof(SectorTiles) * cap));
@@ -203,6 +241,10 @@ int ensure_sector_capacity(dic_engine *e, int n) {
   CU_TRY(e, cudaMalloc(&dr, sizeof(dic_result) * cap));
   CU_TRY(e, cudaMallocHost(&hr, sizeof(dic_result) * cap));
   CU_TRY(e, cudaMallocHost(&hg, sizeof(float) * kMaxParams * cap));
+  CU_TRY(e, cudaMallocHost(&hs, sizeof(SectorDev) * cap));
+  CU_TRY(e, cudaMallocHost(&ht, sizeof(SectorTiles) * cap));
+  memset(hs, 0, sizeof(SectorDev) * cap);
+  memset(ht, 0, sizeof(SectorTiles) * cap);
   CU_TRY(e, cudaMemset(ds, 0, sizeof(SectorDev) * cap));
   CU_TRY(e, cudaMemset(dg, 0, sizeof(float) * kMaxParams * cap));
   CU_TRY(e, cudaMemset(dr, 0, sizeof(dic_result) * cap));
@@ -216,9 +258,12 @@ int ensure_sector_capacity(dic_engine *e, int n) {
     CU_TRY(e, cudaMemcpy(dr, e->d_results, sizeof(dic_result) * e->cap_sectors, cudaMemcpyDeviceToDevice));
     memcpy(hr, e->h_results, sizeof(dic_result) * e->cap_sectors);
     memcpy(hg, e->h_guess, sizeof(float) * kMaxParams * e->cap_sectors);
+    memcpy(hs, e->h_sectors, sizeof(SectorDev) * e->cap_sectors);
+    memcpy(ht, e->h_sector_tiles, sizeof(SectorTiles) * e->cap_sectors);
     cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results); cudaFree(e->d_sector_tiles);
-    cudaFreeHost(e->h_results); cudaFreeHost(e->h_guess);
+    cudaFreeHost(e->h_results); cudaFreeHost(e->h_guess); cudaFreeHost(e->h_sectors); cudaFreeHost(e->h_sector_tiles);
   }
+  e->h_sectors = hs; e->h_sector_tiles = ht;
   e->d_sector_tiles = dt;
   e->d_sectors = ds; e->d_guess = dg; e->d_results = dr; e->h_results = hr; e->h_guess = hg;
   e->cap_sectors = cap;
@@ -246,27 +291,34 @@ bool level_used(const dic_engine *e, int l) {
 
 int sector_reserve(dic_engine *e, Sector &s, size_t total) {
   if (total > s.cap) {
-    if (s.buf) CU_TRY(e, cudaFree(s.buf));
+    if (s.buf && s.buf_owned) CU_TRY(e, cudaFree(s.buf));
     s.buf = nullptr; s.cap = 0;
-    CU_TRY(e, cudaMalloc(&s.buf, sizeof(float2) * std::max<size_t>(total, 1)));
-    s.cap = std::max<size_t>(total, 1);
+    size_t n = std::max<size_t>(total, 1);
+    void *p = nullptr;
+    int rc = sector_alloc(e, sizeof(float2) * n, &p, &s.buf_owned);
+    if (rc) return rc;
+    s.buf = static_cast<float2 *>(p);
+    s.cap = n;
   }
   return DIC_OK;
 }
 
 int push_sector(dic_engine *e, int id) {
   Sector &s = e->sectors[id];
-  SectorDev d;
+  SectorDev &d = e->h_sectors[id];
   memset(&d, 0, sizeof(d));
-  for (int l = 0; l < kMaxLevels; ++l) { d.xy[l] = s.xy[l]; d.n[l] = (int)s.n[l]; }
+  for (int l = 0; l < kMaxLevels; ++l) {
+    d.xy[l] = s.xy[l]; d.n[l] = (int)s.n[l];
+    d.n_total[l] = (int)(s.banded ? s.n_total[l] : s.n[l]);
+  }
   d.cx = s.cx; d.cy = s.cy;
-  SectorTiles t;
+  SectorTiles &t = e->h_sector_tiles[id];
   memset(&t, 0, sizeof(t));
   if (s.has_tiles)
     for (int l = 0; l < kMaxLevels; ++l) t.lev[l] = s.tl[l];
+  // the pinned mirrors stay valid until the sector is reset again, which first drains the stream
   CU_TRY(e, cudaMemcpyAsync(e->d_sectors + id, &d, sizeof(SectorDev), cudaMemcpyHostToDevice, e->stream));
   CU_TRY(e, cudaMemcpyAsync(e->d_sector_tiles + id, &t, sizeof(SectorTiles), cudaMemcpyHostToDevice, e->stream));
-  CU_TRY(e, cudaStreamSynchronize(e->stream)); // `d`, `t` live on this stack frame
   return DIC_OK;
 }
 
@@ -317,13 +369,17 @@ int decimate_levels(dic_engine *e, Sector &s) {
       // grow, preserving what is already there
       size_t ncap = used + (size_t)kept + (size_t)n0 / 2 + 16;
       float2 *nb = nullptr;
-      CU_TRY(e, cudaMalloc(&nb, sizeof(float2) * ncap));
+      bool nb_owned = false;
+      void *pv = nullptr;
+      int rc2 = sector_alloc(e, sizeof(float2) * ncap, &pv, &nb_owned);
+      if (rc2) return rc2;
+      nb = static_cast<float2 *>(pv);
       CU_TRY(e, cudaMemcpyAsync(nb, s.buf, sizeof(float2) * used, cudaMemcpyDeviceToDevice, e->stream));
       CU_TRY(e, cudaStreamSynchronize(e->stream));
       for (int k = 0; k < kMaxLevels; ++k)
         if (s.xy[k]) s.xy[k] = nb + (s.xy[k] - s.buf);
-      cudaFree(s.buf);
-      s.buf = nb; s.cap = ncap;
+      if (s.buf_owned) cudaFree(s.buf);
+      s.buf = nb; s.cap = ncap; s.buf_owned = nb_owned;
       pred.src = s.xy[prev];
     }
     s.xy[l] = s.buf + used;
@@ -337,12 +393,13 @@ int decimate_levels(dic_engine *e, Sector &s) {
 }
 
 void clear_levels(Sector &s) {
-  for (int l = 0; l < kMaxLevels; ++l) { s.xy[l] = nullptr; s.n[l] = 0; }
+  for (int l = 0; l < kMaxLevels; ++l) { s.xy[l] = nullptr; s.n[l] = 0; s.n_total[l] = 0; }
+  s.banded = false;
 }
 
 int check_levels_nonempty(dic_engine *e, const Sector &s) {
   for (int l = e->stop; l >= e->start; l -= e->step)
-    if (s.n[l] <= 0) return DIC_ERROR_BAD_DOMAIN;
+    if ((s.banded ? s.n_total[l] : s.n[l]) <= 0) return DIC_ERROR_BAD_DOMAIN;
   return DIC_OK;
 }
 
@@ -398,9 +455,12 @@ int build_tiles(dic_engine *e, Sector &s, bool may_have_duplicates) {
   }
   if (ng == 0) return DIC_OK;
   if (total_slots > s.tcap) {
-    if (s.tbuf) cudaFree(s.tbuf);
+    if (s.tbuf && s.tbuf_owned) cudaFree(s.tbuf);
     s.tbuf = nullptr; s.tcap = 0;
-    CU_TRY(e, cudaMalloc(&s.tbuf, sizeof(Tile) * total_slots));
+    void *pv = nullptr;
+    int rc0 = sector_alloc(e, sizeof(Tile) * total_slots, &pv, &s.tbuf_owned);
+    if (rc0) return rc0;
+    s.tbuf = static_cast<Tile *>(pv);
     s.tcap = total_slots;
   }
   size_t need_masks = max_slots * kTileH;
@@ -643,8 +703,15 @@ void dic_destroy(dic_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->img_stream) cudaStreamSynchronize(e->img_stream);
-  for (auto &s : e->sectors) { if (s.buf) cudaFree(s.buf); if (s.tbuf) cudaFree(s.tbuf); if (s.ebuf) cudaFree(s.ebuf); }
-  cudaFree(e->d_sector_tiles); cudaFree(e->d_masks);
+  for (auto &s : e->sectors) {
+    if (s.buf && s.buf_owned) cudaFree(s.buf);
+    if (s.tbuf && s.tbuf_owned) cudaFree(s.tbuf);
+    if (s.ebuf) cudaFree(s.ebuf);
+  }
+  for (char *c : e->arena_chunks) cudaFree(c);
+  if (e->h_sectors) cudaFreeHost(e->h_sectors);
+  if (e->h_sector_tiles) cudaFreeHost(e->h_sector_tiles);
+  cudaFree(e->d_sector_tiles); cudaFree(e->d_masks); cudaFree(e->d_mailbox);
   for (auto &p : e->pyr) if (p.base) cudaFree(p.base);
   cudaFree(e->d_sectors); cudaFree(e->d_guess); cudaFree(e->d_results);
   if (e->h_results) cudaFreeHost(e->h_results);
@@ -781,6 +848,7 @@ static int begin_sector(dic_engine *e, int id, Sector **out) {
   int rc = ensure_sector_capacity(e, id + 1);
   if (rc) return rc;
   Sector &s = e->sectors[id];
+  if (s.kind != SK_NONE) CU_TRY(e, cudaStreamSynchronize(e->stream)); // its pinned mirror may be in flight
   s.kind = SK_NONE;
   s.pending = false;
   s.has_tiles = false;
@@ -789,7 +857,7 @@ static int begin_sector(dic_engine *e, int id, Sector **out) {
   return DIC_OK;
 }
 
-int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1) {
+static int reset_rect_impl(dic_engine *e, int id, int x0, int y0, int x1, int y1, int band_y0, int band_y1) {
   Sector *sp;
   int rc = begin_sector(e, id, &sp);
   if (rc) return rc;
@@ -807,6 +875,10 @@ int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1
     auto last_mult = [mag](int a) { int q = a / mag; if (q * mag > a) --q; return q * mag; };
     int xs = first_mult(x0), xe = last_mult(x1), ys = first_mult(y0), ye = last_mult(y1);
     int nx = xe >= xs ? (xe - xs) / mag + 1 : 0, ny = ye >= ys ? (ye - ys) / mag + 1 : 0;
+    s.n_total[l] = (long)nx * ny;
+    // this GPU's band of rows [band_y0, band_y1] (the whole rectangle unless row-split)
+    ys = first_mult(std::max(y0, band_y0)); ye = last_mult(std::min(y1, band_y1));
+    ny = ye >= ys ? (ye - ys) / mag + 1 : 0;
     lv[nl++] = Lv{l, xs, ys, nx, ny, mag};
     total += (size_t)nx * ny;
   }
@@ -828,9 +900,38 @@ int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1
   s.cy = (float)(y0 + y1) * 0.5f;
   s.rx0 = x0; s.ry0 = y0; s.rx1 = x1; s.ry1 = y1;
   s.integer_grid = true;
+  s.banded = (band_y0 > y0 || band_y1 < y1);
   if ((rc = check_levels_nonempty(e, s))) return rc;
   s.kind = SK_RECT;
-  if ((rc = build_tiles(e, s, false))) return rc;
+  { // closed-form tiles: at level l the rectangle is [xs/mag, xe/mag] x [ys/mag, ye/mag]
+    size_t total_tiles = 0;
+    for (int k = 0; k < nl; ++k)
+      total_tiles += (size_t)((lv[k].nx + kTileW - 1) / kTileW) * ((lv[k].ny + kTileH - 1) / kTileH);
+    if (total_tiles > s.tcap) {
+      if (s.tbuf && s.tbuf_owned) cudaFree(s.tbuf);
+      s.tbuf = nullptr; s.tcap = 0;
+      void *pv = nullptr;
+      if ((rc = sector_alloc(e, sizeof(Tile) * total_tiles, &pv, &s.tbuf_owned))) return rc;
+      s.tbuf = static_cast<Tile *>(pv);
+      s.tcap = total_tiles;
+    }
+    for (int l = 0; l < kMaxLevels; ++l) s.tl[l] = TileLevel{};
+    size_t tused = 0;
+    for (int k = 0; k < nl; ++k) {
+      const int ntx = (lv[k].nx + kTileW - 1) / kTileW, nty = (lv[k].ny + kTileH - 1) / kTileH;
+      const int nt = ntx * nty;
+      if (nt <= 0) continue;
+      Tile *dst = s.tbuf + tused;
+      rect_tiles_kernel<<<(nt + 127) / 128, 128, 0, e->stream>>>(dst, ntx, nty, lv[k].xs / lv[k].mag,
+                                                                 lv[k].ys / lv[k].mag, lv[k].nx, lv[k].ny);
+      e->launches++;
+      s.tl[lv[k].l].tiles = dst;
+      s.tl[lv[k].l].n_tiles = nt;
+      tused += (size_t)nt;
+    }
+    CU_TRY(e, cudaGetLastError());
+    s.has_tiles = (x0 >= 0 && y0 >= 0);
+  }
   return push_sector(e, id);
 }
 
@@ -900,6 +1001,14 @@ static void annulus_reference_center(const AnnulusGeom &g, float cx, float cy, i
   count = n;
   ocx = n ? sx / (float)n : cx;
   ocy = n ? sy / (float)n : cy;
+}
+
+int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1) {
+  return reset_rect_impl(e, id, x0, y0, x1, y1, y0, y1);
+}
+int dic_reset_polygon_rect_band(dic_engine *e, int id, int x0, int y0, int x1, int y1, int band_y0, int band_y1) {
+  if (band_y1 < band_y0) return DIC_ERROR_BAD_ARGUMENT;
+  return reset_rect_impl(e, id, x0, y0, x1, y1, std::max(y0, band_y0), std::min(y1, band_y1));
 }
 
 int dic_reset_polygon_annular(dic_engine *e, int id, float r, float dr, float a, float da, float cx,
@@ -1055,6 +1164,65 @@ int dic_update_polygon(dic_engine *e, int id, int deformation_description) {
   if (deformation_description == DIC_DEF_EULERIAN) return DIC_OK; // cuda_polygon.cu:268-275
   set_error(e, "Lagrangian domain updates are not implemented yet (SURVEY 8f rank 1)");
   return DIC_ERROR_BAD_ARGUMENT;
+}
+
+
+// ------------------------------------------------------------------ row-split (one domain, several GPUs)
+
+int dic_rowsplit_mailbox_handle(dic_engine *e, void *handle_out, int handle_bytes) {
+  if (!e || !handle_out || handle_bytes < (int)sizeof(cudaIpcMemHandle_t)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  if (!e->d_mailbox) {
+    CU_TRY(e, cudaMalloc(&e->d_mailbox, sizeof(Mailbox)));
+    CU_TRY(e, cudaMemset(e->d_mailbox, 0, sizeof(Mailbox)));
+  }
+  cudaIpcMemHandle_t h;
+  CU_TRY(e, cudaIpcGetMemHandle(&h, e->d_mailbox));
+  memcpy(handle_out, &h, sizeof(h));
+  return DIC_OK;
+}
+
+int dic_rowsplit_connect(dic_engine *e, int rank, int world, const void *handles, int handle_bytes) {
+  if (!e || rank < 0 || world < 1 || world > kMaxRanks || rank >= world) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (!e->d_mailbox) {
+    CU_TRY(e, cudaMalloc(&e->d_mailbox, sizeof(Mailbox)));
+  }
+  CU_TRY(e, cudaMemset(e->d_mailbox, 0, sizeof(Mailbox)));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { e->peer_mailbox[r] = e->d_mailbox; continue; }
+    if (!handles || handle_bytes < (int)sizeof(cudaIpcMemHandle_t)) return DIC_ERROR_BAD_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char *>(handles) + (size_t)r * handle_bytes, sizeof(h));
+    void *p = nullptr;
+    CU_TRY(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_mailbox[r] = p;
+  }
+  e->rs_rank = rank; e->rs_world = world;
+  GridWork w;
+  CU_TRY(e, cudaMemcpy(&w, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost));
+  w.rs_rank = rank; w.rs_world = world; w.rs_seq = 0; w.rs_error = 0;
+  w.rs_local = e->d_mailbox;
+  for (int r = 0; r < kMaxRanks; ++r) w.rs_peer[r] = static_cast<Mailbox *>(r < world ? e->peer_mailbox[r] : nullptr);
+  CU_TRY(e, cudaMemcpy(e->d_work, &w, sizeof(GridWork), cudaMemcpyHostToDevice));
+  return DIC_OK;
+}
+
+int dic_rowsplit_disconnect(dic_engine *e) {
+  if (!e) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  for (int r = 0; r < e->rs_world; ++r)
+    if (r != e->rs_rank && e->peer_mailbox[r]) cudaIpcCloseMemHandle(e->peer_mailbox[r]);
+  for (auto &p : e->peer_mailbox) p = nullptr;
+  e->rs_rank = 0; e->rs_world = 1;
+  GridWork w;
+  CU_TRY(e, cudaMemcpy(&w, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost));
+  w.rs_rank = 0; w.rs_world = 1; w.rs_local = nullptr; w.rs_error = 0;
+  for (auto &p : w.rs_peer) p = nullptr;
+  CU_TRY(e, cudaMemcpy(e->d_work, &w, sizeof(GridWork), cudaMemcpyHostToDevice));
+  return DIC_OK;
 }
 
 // ------------------------------------------------------------------ correlate

@@ -155,7 +155,7 @@ __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
       last_good_chi = FLT_MAX;
       e_lg = e_mp;
       e_p = e_mp;
-      scaling = 1.f / (float)sec->n[next_level];
+      scaling = 1.f / (float)sec->n_total[next_level];
       phase = PH_INIT;
     }
   }
@@ -179,7 +179,7 @@ __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
     if (finish) {
       for (int i = NP; i < kMaxParams; ++i) result->resultingParameters[i] = 0.f;
       result->chi = last_good_chi;
-      result->numberOfPoints = sec->n[0];
+      result->numberOfPoints = sec->n_total[0];
       result->iterations = reached;
       result->errorCode = error_code;
       result->undCenterX = sec->cx;
@@ -188,7 +188,7 @@ __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
         result->iterationsPerLevel[l] = l == this_level ? iters : s->iters[l];
         result->evaluationsPerLevel[l] = l == this_level ? evals : s->evals[l];
         result->pointsPerLevel[l] = (l >= cfg.start && l <= cfg.stop && (l - cfg.start) % cfg.step == 0)
-                                        ? sec->n[l] : 0;
+                                        ? sec->n_total[l] : 0;
       }
     }
   }
@@ -208,7 +208,7 @@ __device__ void lm_init(LMState *s, const SolveSettings &cfg, const SectorDev *s
   }
   if (lane == 0) {
     s->lambda = 0.0001f; s->last_good_chi = FLT_MAX;
-    s->scaling = 1.f / (float)sec->n[cfg.stop];
+    s->scaling = 1.f / (float)sec->n_total[cfg.stop];
     s->level = cfg.stop; s->level_old = 0; s->iteration = 0; s->use_saved = 1;
     s->phase = PH_INIT; s->done = 0; s->error_code = DIC_OK; s->reached_iterations = 0;
     for (int l = 0; l < kMaxLevels; ++l) { s->evals[l] = 0; s->iters[l] = 0; }
@@ -232,6 +232,68 @@ __device__ __forceinline__ void evaluate_list(const SolveSettings &cfg, const Se
     float2 q = __ldg(xy + i);
     accumulate_pixel<MODEL, INTERP, MODE>(und, def, p, cx, cy, q.x, q.y, acc);
   }
+}
+
+// ------------------------------------------------------------------ row-split all-reduce
+//
+// One domain split by pixel rows over several GPUs: each evaluation ends with a sum of the
+// (n^2 + n)/2 + n + 2 normal-equation values over the ranks. Done here, inside the persistent
+// kernel, by the master CTA's warp 0: write this rank's sums into slot [parity][rank] of every
+// peer's mailbox (plain stores to peer-mapped memory: NVLink), system fence, release-store the
+// sequence number; then wait for every peer's slot of this evaluation in the local mailbox and add
+// the rows IN RANK ORDER, so that every rank gets bitwise the same totals and takes the same LM
+// decisions without a broadcast. Two parities: a rank cannot be more than one evaluation ahead of
+// a peer, because it needs that peer's sums of the current evaluation to get there.
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float *p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int NACC>
+__device__ void rowsplit_allreduce(GridWork *work, float *tot) {
+  const int lane = threadIdx.x & 31;
+  const int rank = work->rs_rank, world = work->rs_world;
+  const unsigned int seq = work->rs_seq;
+  const int par = seq & 1;
+  for (int r = 0; r < world; ++r) {
+    Mailbox *mb = work->rs_peer[r];
+    for (int k = lane; k < NACC; k += 32) mb->sums[par][rank][k] = tot[k];
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < world) st_release_sys_u32(&work->rs_peer[lane]->seq[par][rank], seq + 1);
+  // wait for all ranks (including our own loop-back write) -- bounded, never hang the GPU
+  bool ok = true;
+  if (lane < world) {
+    const unsigned int *flag = &work->rs_local->seq[par][lane];
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys_u32(flag) != seq + 1) {
+      if (global_ns() - t0 > 20000000000ull) { ok = false; break; } // 20 s
+      __nanosleep(100);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) {
+    if (lane == 0) work->rs_error = 1;
+  } else {
+    for (int k = lane; k < NACC; k += 32) {
+      double s = 0.0;
+      for (int r = 0; r < world; ++r) s += (double)ld_relaxed_sys_f32(&work->rs_local->sums[par][r][k]);
+      tot[k] = (float)s;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) work->rs_seq = seq + 1;
+  __syncwarp();
 }
 
 // Shared-memory block common to both solve kernels.
@@ -290,8 +352,15 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
         sh.tot[tid] = (float)s;
       }
       __syncthreads();
+      if (work->rs_local != nullptr) {
+        if (warp == 0) rowsplit_allreduce<NACC>(work, sh.tot);
+        __syncthreads();
+      }
       if (warp == 0) {
         lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
+        if (work->rs_local != nullptr && work->rs_error && lane == 0) {
+          sh.state.done = 1; result->errorCode = DIC_ERROR_MULTITHREAD; // a peer never answered
+        }
         if (lane < NP) { float v = sh.state.p[lane]; sh.p[lane] = v; __stcg(&work->pub_p[lane], v); }
         if (lane == 0) {
           sh.level = sh.state.level; sh.done = sh.state.done;

@@ -527,6 +527,21 @@ compact_any_kernel(Pred pred, long ncand, unsigned int *block_counts,
   if (!EMIT && tid == 0) block_counts[blockIdx.x] = total;
 }
 
+// Rectangle in level coordinates [gx0, gx0 + nx) x [gy0, gy0 + ny): tiles in closed form,
+// column-major (tile index = tx * nty + ty).
+__global__ void rect_tiles_kernel(Tile *__restrict__ out, int ntx, int nty, int gx0, int gy0, int nx, int ny) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntx * nty) return;
+  int tx = t / nty, ty = t - tx * nty;
+  Tile q;
+  q.x0 = gx0 + tx * kTileW; q.y0 = gy0 + ty * kTileH;
+  int wcols = min(kTileW, nx - tx * kTileW), hrows = min(kTileH, ny - ty * kTileH);
+  uint32_t m = wcols >= 32 ? 0xffffffffu : ((1u << wcols) - 1u);
+#pragma unroll
+  for (int r = 0; r < kTileH; ++r) q.rows[r] = r < hrows ? m : 0u;
+  out[t] = q;
+}
+
 // integer bounding box of a list (for blob / point-list sectors)
 __global__ void bbox_kernel(const float2 *__restrict__ xy, long n, int *box /*minx miny maxx maxy*/) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

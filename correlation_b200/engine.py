@@ -50,6 +50,14 @@ class DicResult(C.Structure):
                     pixel_evaluations=float(sum(e * p for e, p in zip(ev, pts))))
 
 
+RESULT_DTYPE = np.dtype([("resultingParameters", np.float32, (MAX_PARAMS,)), ("chi", np.float32),
+                         ("numberOfPoints", np.int32), ("iterations", np.int32), ("errorCode", np.int32),
+                         ("undCenterX", np.float32), ("undCenterY", np.float32),
+                         ("iterationsPerLevel", np.int32, (MAX_LEVELS,)),
+                         ("evaluationsPerLevel", np.int32, (MAX_LEVELS,)),
+                         ("pointsPerLevel", np.int32, (MAX_LEVELS,))])
+assert RESULT_DTYPE.itemsize == C.sizeof(DicResult)
+
 _lib = None
 
 EXPORTS = [
@@ -59,8 +67,8 @@ EXPORTS = [
     "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_device",
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
-    "dic_reset_polygon_blob", "dic_reset_polygon_points", "dic_set_polygon_center",
-    "dic_update_polygon", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
+    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_points", "dic_set_polygon_center",
+    "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
     "dic_last_correlate_ms", "dic_get_timeline", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
@@ -102,6 +110,10 @@ def load_library():
         "dic_reset_polygon_annular": (I, [P, I, F, F, F, F, F, F, I]),
         "dic_reset_polygon_blob": (I, [P, I, P, I]),
         "dic_reset_polygon_points": (I, [P, I, P, I64, I, F, F]),
+        "dic_reset_polygon_rect_band": (I, [P, I, I, I, I, I, I, I]),
+        "dic_rowsplit_mailbox_handle": (I, [P, P, I]),
+        "dic_rowsplit_connect": (I, [P, I, I, P, I]),
+        "dic_rowsplit_disconnect": (I, [P]),
         "dic_set_polygon_center": (I, [P, I, F, F]),
         "dic_update_polygon": (I, [P, I, I]),
         "dic_correlate": (I, [P, I, P, C.POINTER(DicResult)]),
@@ -243,6 +255,22 @@ class CudaEngine:
         return self._ck(self.lib.dic_reset_polygon_rect(self.h, iSector, int(x0), int(y0), int(x1), int(y1)),
                         soft=(4,))
 
+    def resetPolygonRectBand(self, iSector, x0, y0, x1, y1, band_y0, band_y1):
+        return self._ck(self.lib.dic_reset_polygon_rect_band(self.h, iSector, int(x0), int(y0), int(x1), int(y1),
+                                                             int(band_y0), int(band_y1)), soft=(4,))
+
+    def rowsplit_handle(self):
+        buf = np.zeros(64, np.uint8)
+        self._ck(self.lib.dic_rowsplit_mailbox_handle(self.h, _ptr(buf), 64))
+        return buf
+
+    def rowsplit_connect(self, rank, world, handles):
+        h = np.ascontiguousarray(handles, np.uint8).reshape(world, 64)
+        self._ck(self.lib.dic_rowsplit_connect(self.h, rank, world, _ptr(h), 64))
+
+    def rowsplit_disconnect(self):
+        self._ck(self.lib.dic_rowsplit_disconnect(self.h))
+
     def resetPolygonAnnular(self, iSector, r, dr, a, da, cx, cy, n_as):
         return self._ck(self.lib.dic_reset_polygon_annular(self.h, iSector, r, dr, a, da, cx, cy, int(n_as)),
                         soft=(4,))
@@ -282,13 +310,33 @@ class CudaEngine:
         self._ck(self.lib.dic_correlate_wait(self.h, iSector, _ptr(g), C.byref(r)), soft=(1, 2, 3, 5))
         return r.as_dict(self.n_params)
 
-    def correlate_batch(self, first_sector, guesses):
+    def correlate_batch_raw(self, first_sector, guesses, out=None):
+        """One launch for len(guesses) consecutive sectors. Returns (guesses_out, results) as numpy
+        arrays (results: structured RESULT_DTYPE); no per-sector Python objects."""
         g = np.ascontiguousarray(guesses, np.float32).reshape(-1, self.n_params).copy()
         n = g.shape[0]
-        res = (DicResult * n)()
-        self._ck(self.lib.dic_correlate_batch(self.h, first_sector, n, _ptr(g), C.cast(res, C.c_void_p)),
-                 soft=(1, 2, 3, 5))
-        return [res[i].as_dict(self.n_params) for i in range(n)]
+        res = out if out is not None else np.zeros(n, RESULT_DTYPE)
+        self._ck(self.lib.dic_correlate_batch(self.h, first_sector, n, _ptr(g), _ptr(res)), soft=(1, 2, 3, 5))
+        return g, res
+
+    def correlate_batch(self, first_sector, guesses):
+        _, res = self.correlate_batch_raw(first_sector, guesses)
+        out = []
+        for r in res:
+            ev, pts = r["evaluationsPerLevel"].tolist(), r["pointsPerLevel"].tolist()
+            out.append(dict(params=r["resultingParameters"][:self.n_params].copy(), chi=np.float32(r["chi"]),
+                            number_of_points=int(r["numberOfPoints"]), iterations=int(r["iterations"]),
+                            error_code=int(r["errorCode"]),
+                            und_center=(np.float32(r["undCenterX"]), np.float32(r["undCenterY"])),
+                            iterations_per_level=r["iterationsPerLevel"].tolist(), evaluations=ev,
+                            points_per_level=pts,
+                            pixel_evaluations=float(sum(e * p for e, p in zip(ev, pts)))))
+        return out
+
+    @staticmethod
+    def pixel_evaluations(res):
+        """sum over sectors and levels of points x evaluations for a RESULT_DTYPE array"""
+        return float((res["evaluationsPerLevel"].astype(np.float64) * res["pointsPerLevel"]).sum())
 
     # -- read-back
     def _points(self, fn, iSector, *lead):

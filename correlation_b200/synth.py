@@ -21,9 +21,14 @@ import numpy as np
 N_WAVES = 48
 
 
-def speckle_waves(seed: int, n_waves: int = N_WAVES):
+def speckle_waves(seed: int, n_waves: int = N_WAVES, spectrum=None):
+    """spectrum=None: wavelengths U(5, 20) px. spectrum=(lo, hi): log-uniform in [lo, hi]
+    px -- multi-scale speckle, so that coarse pyramid levels still carry signal (config 5)."""
     rng = np.random.default_rng(seed)
-    lam = rng.uniform(5.0, 20.0, n_waves)
+    if spectrum is None:
+        lam = rng.uniform(5.0, 20.0, n_waves)
+    else:
+        lam = np.exp(rng.uniform(math.log(spectrum[0]), math.log(spectrum[1]), n_waves))
     theta = rng.uniform(0.0, 2.0 * math.pi, n_waves)
     amp = rng.uniform(0.5, 1.0, n_waves)
     phase = rng.uniform(0.0, 2.0 * math.pi, n_waves)
@@ -70,12 +75,12 @@ def _field_block(xs, ys, waves, xp):
 
 
 def make_image(rows, cols, seed, params=None, center=None, contrast=45.0,
-               device=None, block_rows=512):
+               device=None, block_rows=512, spectrum=None, n_waves=N_WAVES):
     """u8 image (numpy uint8 [rows, cols], or a torch uint8 CUDA tensor if device is given).
 
     params=None -> the undeformed field; else the field sampled at W^-1 (the deformed image).
     """
-    waves = speckle_waves(seed)
+    waves = speckle_waves(seed, n_waves, spectrum)
     if device is None:
         xp = np
         out = np.empty((rows, cols), np.uint8)

@@ -139,6 +139,10 @@ int dic_reset_polygon_rect(dic_engine *e, int iSector, int x0, int y0, int x1, i
 int dic_reset_polygon_annular(dic_engine *e, int iSector, float r, float dr, float a, float da,
                               float cx, float cy, int as);
 int dic_reset_polygon_blob(dic_engine *e, int iSector, const float *contour_xy, int n_vertices);
+/* extension (BASELINE config 5): this GPU takes only image rows [band_y0, band_y1] of the rectangle;
+ * centre, point counts and chi scaling stay those of the whole rectangle. Use with dic_rowsplit_*. */
+int dic_reset_polygon_rect_band(dic_engine *e, int iSector, int x0, int y0, int x1, int y1, int band_y0,
+                                int band_y1);
 /* extension: an arbitrary point list (what CorrelationClass::Newton_Raphson(guess, N, xy) takes,
  * correlation_class.cpp:326-343). use_center: 0 = derive per the centre mode. */
 int dic_reset_polygon_points(dic_engine *e, int iSector, const float *xy, int64_t n,
@@ -163,6 +167,19 @@ int dic_correlate_batch(dic_engine *e, int first_sector, int n_sectors, float *g
  * the next upload with the solve, and lets bench.py time the device alone. */
 int dic_correlate_async(dic_engine *e, int iSector, const float *guess);
 int dic_correlate_wait(dic_engine *e, int iSector, float *guess_out, dic_result *out);
+
+/* ---- extension: one domain row-split over `world` GPUs of one node (one process per GPU).
+ *      Every evaluation ends with a sum of the normal equations over the ranks, done inside the
+ *      persistent kernel through peer-mapped mailboxes (CUDA IPC, NVLink): no NCCL call, no host
+ *      round trip, bitwise-identical totals on every rank. Protocol: each rank calls
+ *      dic_rowsplit_mailbox_handle (64-byte opaque handle), the host all-gathers the handles
+ *      (torch.distributed / MPI / anything), each rank calls dic_rowsplit_connect with all of them,
+ *      then dic_correlate is called collectively by all ranks on sectors built with
+ *      dic_reset_polygon_rect_band. A peer that does not answer within 20 s yields
+ *      DIC_ERROR_MULTITHREAD instead of a hang. */
+int dic_rowsplit_mailbox_handle(dic_engine *e, void *handle_out, int handle_bytes);
+int dic_rowsplit_connect(dic_engine *e, int rank, int world, const void *handles, int handle_bytes);
+int dic_rowsplit_disconnect(dic_engine *e);
 
 /* ---- CudaClass::getUndXY0ToCPU / getDefXY0ToCPU (cuda_class.cu, cuda_polygon.cu:417-428):
  *      level-0 list in the reference CPU order. Writes min(cap, n) points (interleaved x,y);

@@ -374,3 +374,29 @@ def test_tile_kernel_equals_list_kernel(eng, model, mode, domain):
     tol = (2e-5, 2e-7) if mode == engine.MODE_PARITY else (1e-4, 1e-6)
     assert d[:2].max() < tol[0] and d[2:6].max() < tol[1], (a["params"], b["params"])
     assert abs(a["chi"] - b["chi"]) < (2e-5 if mode == engine.MODE_PARITY else 1e-4) * b["chi"]
+
+
+# ---------------------------------------------------------------- row-split machinery (one GPU: loop-back)
+
+def test_rowsplit_loopback_and_band_bookkeeping(eng):
+    """world = 1 runs the whole mailbox all-reduce against the rank's own mailbox; a band sector keeps
+    the whole rectangle's centre / counts. (The 2-GPU run is tools/rowsplit_check.py under torchrun.)"""
+    from correlation_b200 import rowsplit
+    truth = (1.3, -0.9, 0.003, 0.002, -0.002, 0.004)
+    und, dfm = synth.make_pair(420, 400, 51, truth, center=(200, 210))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    eng.resetPolygon(0, 37, 41, 361, 377)
+    plain = eng.correlate(0, np.zeros(6))
+    rowsplit.connect(eng, None)
+    try:
+        looped = eng.correlate(0, np.zeros(6))
+        # a band holding the whole rectangle is the same problem
+        eng.resetPolygonRectBand(1, 37, 41, 361, 377, 0, 10000)
+        banded = eng.correlate(1, np.zeros(6))
+    finally:
+        eng.rowsplit_disconnect()
+    for r in (looped, banded):
+        assert r["error_code"] == 0 and r["evaluations"] == plain["evaluations"]
+        assert np.array_equal(r["params"], plain["params"]) and r["chi"] == plain["chi"]
+    assert rowsplit.equal_row_bands(41, 377, 3) == [(41, 152), (153, 264), (265, 377)]
