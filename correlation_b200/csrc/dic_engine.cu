@@ -842,6 +842,9 @@ int dic_make_def_pyramid_from_nxt(dic_engine *e) {
 
 // ------------------------------------------------------------------ domains
 
+static int download_list(dic_engine *e, const float2 *d, long n, std::vector<float2> &h);
+static void to_reference_order(const Sector &s, std::vector<float2> &h);
+
 static int begin_sector(dic_engine *e, int id, Sector **out) {
   if (!e || id < 0 || id > (1 << 24)) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
@@ -1159,13 +1162,60 @@ int dic_set_polygon_center(dic_engine *e, int id, float cx, float cy) {
   return push_sector(e, id);
 }
 
+// CudaClass::updatePolygon with the CPU path's semantics (manager_class.cpp:353-397, 616-676,
+// 1050-1110): Lagrangian = every point translated by the centre shift of the last result and
+// rounded to the grid (add_pair, :37-47); strict Lagrangian = und points := last deformed points.
 int dic_update_polygon(dic_engine *e, int id, int deformation_description) {
   if (!e || !sector_ok(e, id)) return DIC_ERROR_BAD_ARGUMENT;
   if (deformation_description == DIC_DEF_EULERIAN) return DIC_OK; // cuda_polygon.cu:268-275
-  set_error(e, "Lagrangian domain updates are not implemented yet (SURVEY 8f rank 1)");
-  return DIC_ERROR_BAD_ARGUMENT;
+  if (deformation_description != DIC_DEF_LAGRANGIAN && deformation_description != DIC_DEF_STRICT_LAGRANGIAN)
+    return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  Sector &s = e->sectors[id];
+  if (s.banded) { set_error(e, "domain updates of a row-split sector are not supported"); return DIC_ERROR_BAD_ARGUMENT; }
+  const dic_result &r = e->h_results[id];
+  const int np = np_of(e);
+  const float u = r.resultingParameters[0], v = np > 1 ? r.resultingParameters[1] : 0.f;
+  const long n0 = s.n[0];
+  const unsigned grid = (unsigned)((n0 + 255) / 256);
+  if (s.xy[0] != s.buf) return DIC_ERROR_BAD_ARGUMENT;
+  if (deformation_description == DIC_DEF_LAGRANGIAN) {
+    translate_round_kernel<<<grid, 256, 0, e->stream>>>(s.buf, n0, u, v);
+  } else {
+    float *d_params = e->d_scratch + 512;
+    CU_TRY(e, cudaMemcpyAsync(d_params, r.resultingParameters, sizeof(float) * np, cudaMemcpyHostToDevice, e->stream));
+    switch (e->model) {
+    case DIC_FM_U: warp_list_kernel<DIC_FM_U><<<grid, 256, 0, e->stream>>>(s.buf, n0, d_params, s.cx, s.cy, s.buf); break;
+    case DIC_FM_UV: warp_list_kernel<DIC_FM_UV><<<grid, 256, 0, e->stream>>>(s.buf, n0, d_params, s.cx, s.cy, s.buf); break;
+    case DIC_FM_UVQ: warp_list_kernel<DIC_FM_UVQ><<<grid, 256, 0, e->stream>>>(s.buf, n0, d_params, s.cx, s.cy, s.buf); break;
+    case DIC_FM_UVUxUyVxVy: warp_list_kernel<DIC_FM_UVUxUyVxVy><<<grid, 256, 0, e->stream>>>(s.buf, n0, d_params, s.cx, s.cy, s.buf); break;
+    default: warp_list_kernel<DIC_FM_QUADRATIC><<<grid, 256, 0, e->stream>>>(s.buf, n0, d_params, s.cx, s.cy, s.buf); break;
+    }
+    s.integer_grid = false;
+  }
+  e->launches++;
+  CU_TRY(e, cudaGetLastError());
+  for (int l = 1; l < kMaxLevels; ++l) { s.xy[l] = nullptr; s.n[l] = 0; }
+  s.has_tiles = false;
+  int rc = decimate_levels(e, s);
+  if (rc) return rc;
+  if ((rc = check_levels_nonempty(e, s))) return rc;
+  if (s.kind == SK_RECT) {
+    // the manager passes the rounded deformed centre of the previous frame (:2085-2086)
+    s.cx = (float)(int)(s.cx + u + 0.5f);
+    s.cy = (float)(int)(s.cy + v + 0.5f);
+  } else if (e->center_mode == DIC_CENTER_REFERENCE) {
+    std::vector<float2> h;
+    if ((rc = download_list(e, s.xy[0], n0, h))) return rc;
+    if (deformation_description == DIC_DEF_LAGRANGIAN) to_reference_order(s, h);
+    seq_mean(h, s.cx, s.cy);
+  } else if ((rc = exact_center(e, s))) {
+    return rc;
+  }
+  if (s.integer_grid && (rc = build_tiles(e, s, s.kind == SK_BLOB || s.kind == SK_POINTS))) return rc;
+  return push_sector(e, id);
 }
-
 
 // ------------------------------------------------------------------ row-split (one domain, several GPUs)
 

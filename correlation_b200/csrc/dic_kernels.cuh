@@ -692,6 +692,15 @@ __global__ void warp_list_kernel(const float2 *__restrict__ src, long n, const f
   dst[i] = make_float2(xd, yd);
 }
 
+// Lagrangian domain update of the CPU path: add_pair (manager_class.cpp:37-47) -- translate by the
+// centre shift and round to the pixel grid.
+__global__ void translate_round_kernel(float2 *xy, long n, float ox, float oy) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 q = xy[i];
+  xy[i] = make_float2((float)(int)(__fadd_rn(__fadd_rn(ox, q.x), 0.5f)), (float)(int)(__fadd_rn(__fadd_rn(oy, q.y), 0.5f)));
+}
+
 // exact integer sums of a list of integer-valued points (DIC_CENTER_EXACT)
 __global__ void sum_xy_kernel(const float2 *__restrict__ xy, long n, unsigned long long *sums) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,117 @@
+"""GPU suite: the headless C++ host (frame loop, constant-velocity guess, domain updates, CSV report)
+against the same sequence driven on the CPU oracle by a restatement of the manager's bookkeeping
+(manager_class.cpp:1297-1541, 2602-2707) kept in this test file."""
+import numpy as np
+import pytest
+
+import oracle
+from correlation_b200 import host, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_frames(n, rows, cols, seed, rate, center):
+    """frame k = field warped by k * rate (constant velocity)."""
+    return [synth.make_image(rows, cols, seed, None if k == 0 else tuple(k * np.array(rate)), center)
+            for k in range(n)]
+
+
+def oracle_sequence(frames, xy0, center, model=oracle.FM_AFFINE, pyramid=(0, 1, 2), reference_first=True,
+                    lagrangian=False, rect_center=None):
+    """The manager's CPU path for ONE sector whose centre equals the global centre (no sector offset)."""
+    n = oracle.N_PARAMS[model]
+    O = oracle.OracleEngine(model=model, n_threads=20, pyramid=pyramid, accum_double=True)
+    O.set_image("und", frames[0])
+    O.set_image("def", frames[1])
+    xy = np.array(xy0, np.float32)
+    p = np.zeros(n, np.float32)
+    p_prev = np.zeros(n, np.float32)
+    out = []
+    c = rect_center
+    for k in range(len(frames) - 1):
+        if k > 0:
+            if not reference_first:
+                O.und_from_def()
+            O.set_image("nxt", frames[k + 1])
+            O.def_from_nxt()
+        if k == 0:
+            guess = np.zeros(n, np.float32)
+            p_prev = guess.copy()
+        else:
+            if (not lagrangian) and reference_first:
+                guess = (p + (p - p_prev)).astype(np.float32)  # manager_class.cpp:2677-2686
+            else:
+                guess = p.copy()
+            p_prev = p.copy()
+            if lagrangian:  # add_pair, manager_class.cpp:37-47, offset = und_center - past_und_center = (u, v)
+                xy = np.stack([np.floor(np.float32(p[0]) + xy[:, 0] + np.float32(0.5)),
+                               np.floor(np.float32(p[1]) + xy[:, 1] + np.float32(0.5))], 1).astype(np.float32)
+                if c is not None:
+                    c = (float(int(c[0] + p[0] + 0.5)), float(int(c[1] + p[1] + 0.5)))
+        r = O.correlate(guess, xy, center=c)
+        p = r["params"].copy()
+        out.append(dict(r, guess=guess))
+    return out
+
+
+def test_blob_sequence_constant_velocity_vs_oracle():
+    rate = (0.8, -0.5, 0.0004, -0.0005, 0.0005, 0.0004)
+    frames = make_frames(6, 300, 320, 3, rate, (160, 150))
+    contour = synth.star_polygon(160.0, 150.0, 95.0, n_vertices=24, seed=3)
+    got = host.run_sequence(frames, contour=contour, pyramid=(0, 1, 2))
+    assert got["error"] == 0
+    hdr, rows = host.parse_report(got["csv"])
+    assert hdr[:3] == ["Frame#", "und_file_string", "def_file_string"] and hdr[-5:] == ["chi", "number_of_points", "iterations", "error_status", "error_code"]
+    assert len(rows) == 5
+    want = oracle_sequence(frames, oracle.blob_points(contour), None)
+    for k, (row, w) in enumerate(zip(rows, want)):
+        for p in range(6):
+            tol = 2e-4 if p < 2 else 2e-6  # CSV carries 6 significant digits
+            assert abs(row[f"parameter_{p}"] - w["params"][p]) < tol + 1e-5 * abs(w["params"][p]), (k, p)
+            assert abs(row[f"Initial_guess_{p}"] - w["guess"][p]) < tol + 1e-5 * abs(w["guess"][p]), (k, p)
+        assert int(row["number_of_points"]) == w["number_of_points"]
+        assert abs(int(row["iterations"]) - w["iterations"]) <= 1
+        assert int(row["error_code"]) == 0
+    # exact floats of the last frame
+    last = got["rows"][0]
+    d = np.abs(last["params"][:6] - want[-1]["params"])
+    assert d[:2].max() < 1e-4 and d[2:].max() < 1e-6
+    assert abs(last["chi"] - want[-1]["chi"]) < 1e-4 * want[-1]["chi"]
+    # constant velocity: from frame 2 on the extrapolated guess is already within a few 1e-3 px
+    assert abs(rows[3]["Initial_guess_0"] - rows[3]["parameter_0"]) < 2e-2
+
+
+def test_rect_lagrangian_previous_image_vs_oracle():
+    rate = (1.3, 0.7, 0.0, 0.0, 0.0, 0.0)
+    frames = make_frames(4, 256, 256, 9, rate, (128, 128))
+    rect = (64, 64, 193, 193)  # 129 wide: xdim = 64, centre 128
+    got = host.run_sequence(frames, rect=rect, pyramid=(0, 1, 1), deformation=1, reference=1)
+    assert got["error"] == 0
+    xy = oracle.rect_points(64, 64, 192, 192)
+    want = oracle_sequence(frames, xy, None, pyramid=(0, 1, 1), reference_first=False, lagrangian=True,
+                           rect_center=(128.0, 128.0))
+    hdr, rows = host.parse_report(got["csv"])
+    assert len(rows) == 3
+    for k, (row, w) in enumerate(zip(rows, want)):
+        assert abs(row["parameter_0"] - w["params"][0]) < 3e-4 and abs(row["parameter_1"] - w["params"][1]) < 3e-4, k
+        assert int(row["number_of_points"]) == w["number_of_points"]
+    # the domain followed the material: centre moved by the rounded displacement each frame
+    assert rows[2]["und_center_x"] == pytest.approx(128 + 2 * round(1.3), abs=1.01)
+
+
+def test_rect_subdivisions_batch_equals_serial():
+    truth = (1.1, 0.6, 0.002, -0.001, 0.001, 0.002)
+    frames = [synth.make_image(384, 384, 41, None, (192, 192)), synth.make_image(384, 384, 41, truth, (192, 192))]
+    rect = (32, 32, 352, 352)
+    a = host.run_sequence(frames, rect=rect, subdivisions=(4, 4), pyramid=(0, 1, 2))
+    b = host.run_sequence(frames, rect=rect, subdivisions=(4, 4), pyramid=(0, 1, 2), batch=True)
+    assert a["error"] == 0 and b["error"] == 0
+    # grid-wide launch per sector vs one CTA per sector: same arithmetic per pixel, different
+    # summation tree (fp64 atomics across CTAs vs one CTA), hence a slightly different LM path
+    d = np.abs(a["rows"]["params"] - b["rows"]["params"])
+    assert d[:, :2].max() < 5e-5 and d[:, 2:].max() < 1e-6
+    # sector k sees the global displacement plus the gradient times its centre offset
+    for r in a["rows"]:
+        dx, dy = r["und_center_x"] - 192.0, r["und_center_y"] - 192.0
+        assert abs(r["params"][0] - (truth[0] + truth[2] * dx + truth[3] * dy)) < 0.02
+        assert abs(r["params"][1] - (truth[1] + truth[4] * dx + truth[5] * dy)) < 0.02
