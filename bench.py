@@ -56,6 +56,12 @@ def workload(name):
                     rows=8192, cols=8192, seed=4, model="affine", pyramid=(0, 1, 2),
                     truth=(1.25, -0.75, .0004, -.0003, .0002, .0005), center=(4096.0, 4096.0),
                     domain=("subsets", 64, 8128, 64))
+    if name == "c3":  # BASELINE config 3: frames/s of a 100-frame sequence
+        return dict(name="c3: 100-frame 2048^2 sequence, 64-vertex star blob (mean radius 700), affine, pyramid 0/1/2, "
+                         "Eulerian + first-image reference, constant-velocity initial guess",
+                    rows=2048, cols=2048, seed=3, model="affine", pyramid=(0, 1, 2), frames=100,
+                    rate=(0.8, -0.5, 0.0, -0.0005, 0.0005, 0.0), center=(1024.0, 1024.0),
+                    truth=(0.8, -0.5, 0.0, -0.0005, 0.0005, 0.0), domain=("blob", 1024.0, 1024.0, 700.0, 64))
     if name == "c5":  # BASELINE config 5: one huge domain, row-split across GPUs
         return dict(name="c5: 16384^2 pair, one 15361^2 rect domain, affine, pyramid 0..4, row-split + in-kernel all-reduce",
                     rows=16384, cols=16384, seed=5, model="affine", pyramid=(0, 1, 4),
@@ -183,6 +189,72 @@ def cpu_run(w, und, dfm, threads, sample_levels=None):
     return work, secs, ("reference" if use_ref else "port"), res, sample, t_pyr
 
 
+# ------------------------------------------------------------------------------ config 3: frames / s
+
+def run_c3(args, w):
+    """The frame loop of the headless C++ host (correlation_b200/host/dic_manager.hpp) on pinned host
+    frames: per frame H2D of the next image (second stream, overlapped), pyramid, rotation, GN."""
+    import torch
+    from correlation_b200 import host, synth
+    dev = torch.device("cuda", 0)
+    n = w["frames"]
+    frames = []
+    for k in range(n):
+        t = synth.make_image(w["rows"], w["cols"], w["seed"], None if k == 0 else tuple(k * np.array(w["rate"])),
+                             w["center"], device=dev)
+        pin = torch.empty(t.shape, dtype=torch.uint8, pin_memory=True)
+        pin.copy_(t)
+        frames.append(pin.numpy())
+    torch.cuda.synchronize()
+    d = w["domain"]
+    contour = synth.star_polygon(d[1], d[2], d[3], n_vertices=d[4], seed=w["seed"])
+    mode = 0 if args.mode == "parity" else 1
+    runs = []
+    with ClockSampler(0) as clk:
+        for i in range(args.warmup + args.steps):
+            r = host.run_sequence(frames, contour=contour, pyramid=w["pyramid"], arith_mode=mode)
+            if i >= args.warmup:
+                runs.append(r)
+    secs = sum(r["seconds"] for r in runs) / len(runs)
+    fps = (n - 1) / secs
+    hdr, rows = host.parse_report(runs[-1]["csv"])
+    last = runs[-1]["rows"][0]
+    truth_last = (n - 1) * np.array(w["rate"])
+    line = {"metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic analytic speckle sequence, constant velocity",
+            "config": {"workload": w["name"], "arith_mode": args.mode, "frame_pairs": n - 1,
+                       "points": int(last["number_of_points"]), "errors": int(sum(int(r["error_code"]) != 0 for r in rows)),
+                       "last_frame_params": [float(v) for v in last["params"][:6]],
+                       "last_frame_truth": [float(v) for v in truth_last],
+                       "step": "one step = the whole 99-pair sequence through dic_host_run (C++ host loop)"},
+            "clocks": clk.summary(),
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": n * w["rows"] * w["cols"],
+                    "d2h_bytes_per_step": 176 * (n - 1)},
+            "gpu_launches": (n - 1) * 5,
+            "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "frames/s is a pipeline metric (upload + pyramid + GN per frame); see the c2 / c4 lines for the kernel roofline"}}
+    if not args.no_cpu_baseline:
+        import oracle
+        t0 = time.perf_counter()
+        O = oracle.OracleEngine(n_threads=os.cpu_count() or 1, pyramid=w["pyramid"], real_threads=True)
+        O.set_image("und", frames[0])
+        xy = oracle.blob_points(contour)
+        p = np.zeros(6, np.float32)
+        p_prev = p.copy()
+        nf = 4
+        for k in range(nf):
+            O.set_image("def", frames[k + 1])
+            guess = p + (p - p_prev) if k else p
+            p_prev = p
+            p = O.correlate(guess, xy)["params"]
+        cs = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nf / cs, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"first {nf} frame pairs of the sequence (pyramid + Newton_Raphson each)"}
+    print(json.dumps(line))
+    return 0
+
+
 # ------------------------------------------------------------------------------ main
 
 def main():
@@ -202,6 +274,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = workload(args.workload)
     n_par = 12 if w["model"] == "quad" else 6
+    if args.workload == "c3" and args.impl == "ours":
+        if rank != 0:
+            return 0
+        return run_c3(args, w)
 
     import torch
     dist = None
