@@ -499,27 +499,32 @@ __global__ void solve_step_kernel(const float *tot, float scaling, float lambda,
 
 // ------------------------------------------------------------------ pyramid
 
-// pyramid_class.cpp:52-134. One CTA = 32 x 8 target pixels; the (68 x 20) u8 source footprint is
-// staged in shared memory once, then every target pixel runs the reference's 25 sequential
-// fp32 mul + add (dj outer, di inner, no FMA contraction) and truncates to u8. Target border
-// rows / columns are written as 0 (the reference leaves a zero-initialised border, :98-102).
+// pyramid_class.cpp:52-134. One CTA = 32 x 8 target pixels. The (72 x 19) u8 source footprint is
+// staged ONCE into shared memory as fp32 (aligned 32-bit loads, PRMT + FADD conversion -- no I2F),
+// split into even / odd source columns so that the stride-2 taps of neighbouring lanes hit distinct
+// banks. Every target pixel then runs the reference's 25 sequential fp32 mul + add (dj outer, di
+// inner, no FMA contraction) and truncates to u8. Target border rows / columns are written as 0
+// (the reference leaves a zero-initialised border, :98-102). HBM-bound: 1.25 B per source pixel.
 constexpr int kPyrTX = 32, kPyrTY = 8;
 struct PyrWeights { float w[25]; };
 
 __global__ void __launch_bounds__(kPyrTX *kPyrTY)
 pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int dcols, int dpitch,
                      PyrWeights kw) {
-  constexpr int SW = 2 * kPyrTX + 4, SH = 2 * kPyrTY + 3;
-  __shared__ uint8_t tile[SH][SW];
+  constexpr int SWW = (2 * kPyrTX + 8) / 4, SH = 2 * kPyrTY + 3; // 18 words (72 px) x 19 rows
+  __shared__ float tE[SH][SWW * 2 + 1], tO[SH][SWW * 2 + 1];     // even / odd source columns
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ox = blockIdx.x * kPyrTX, oy = blockIdx.y * kPyrTY; // target origin
-  const int sx0 = 2 * ox - 2, sy0 = 2 * oy - 2;                 // source origin of the tile
-  for (int idx = ty * kPyrTX + tx; idx < SH * SW; idx += kPyrTX * kPyrTY) {
-    int r = idx / SW, c = idx % SW;
-    int sx = sx0 + c, sy = sy0 + r;
-    uint8_t v = 0;
-    if (sx >= 0 && sy >= 0 && sx < src.cols && sy < src.rows) v = __ldg(src.ptr + (size_t)sy * src.pitch + sx);
-    tile[r][c] = v;
+  const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;                 // staged window origin (x 4-aligned)
+  for (int idx = ty * kPyrTX + tx; idx < SH * SWW; idx += kPyrTX * kPyrTY) {
+    const int r = idx / SWW, c4 = idx - r * SWW;
+    const int sx = sx0 + 4 * c4, sy = sy0 + r;
+    uint32_t v = 0;
+    if (sx >= 0 && sy >= 0 && sx + 3 < src.pitch && sy < src.rows)
+      v = __ldg(reinterpret_cast<const uint32_t *>(src.ptr + (size_t)sy * src.pitch + sx));
+    // columns beyond the image inside the pitch are never used by a non-border target pixel
+    tE[r][2 * c4] = u8_to_float(v, 0); tO[r][2 * c4] = u8_to_float(v, 1);
+    tE[r][2 * c4 + 1] = u8_to_float(v, 2); tO[r][2 * c4 + 1] = u8_to_float(v, 3);
   }
   __syncthreads();
   const int ti = ox + tx, tj = oy + ty;
@@ -527,13 +532,16 @@ pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int d
   uint8_t out = 0;
   if (ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1) {
     float addition = 0.f;
+    // source column of tap di: 2 ti - 2 + di = sx0 + (2 tx + 2 + di): even di -> tE[tx + 1 + di/2], odd -> tO[tx + 1 + (di-1)/2]
 #pragma unroll
-    for (int dj = 0; dj < 5; ++dj)
-#pragma unroll
-      for (int di = 0; di < 5; ++di) {
-        float s = (float)tile[2 * ty + dj][2 * tx + di];
-        addition = __fadd_rn(addition, __fmul_rn(s, kw.w[dj * 5 + di]));
-      }
+    for (int dj = 0; dj < 5; ++dj) {
+      const float *rE = tE[2 * ty + dj] + tx + 1, *rO = tO[2 * ty + dj] + tx + 1;
+      addition = __fadd_rn(addition, __fmul_rn(rE[0], kw.w[dj * 5 + 0]));
+      addition = __fadd_rn(addition, __fmul_rn(rO[0], kw.w[dj * 5 + 1]));
+      addition = __fadd_rn(addition, __fmul_rn(rE[1], kw.w[dj * 5 + 2]));
+      addition = __fadd_rn(addition, __fmul_rn(rO[1], kw.w[dj * 5 + 3]));
+      addition = __fadd_rn(addition, __fmul_rn(rE[2], kw.w[dj * 5 + 4]));
+    }
     out = (uint8_t)__float2uint_rz(addition);
   }
   dst[(size_t)tj * dpitch + ti] = out;

@@ -20,6 +20,9 @@
 
 namespace dic {
 
+#ifndef DIC_TILE_CTAS_PER_SM
+#define DIC_TILE_CTAS_PER_SM 2
+#endif
 constexpr int kTileW = 32, kTileH = 16;
 constexpr int kPatchW = 48, kPatchH = 24; // 48 = 32 + halo 3 + strain margin + 8-byte alignment // fp32 staging of the deformed footprint, per warp
 constexpr int kWarpsPerCta = kThreads / 32;
@@ -395,7 +398,7 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, const 
 
 // ---- the solve kernel on tiles (same LM / barrier / solve machinery as gn_solve_kernel)
 template <int MODEL, int MODE, bool GRID>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, DIC_TILE_CTAS_PER_SM)
 gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
                       const SectorTiles *__restrict__ sector_tiles, const float *__restrict__ guesses,
                       dic_result *__restrict__ results, int first_sector, int n_sectors, GridWork *work,
@@ -439,8 +442,9 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
       if (active) {
         const int nw = n_active * kWarpsPerCta;
         const int wg = GRID ? blockIdx.x * kWarpsPerCta + warp : warp;
-        const int per = (n_units + nw - 1) / nw;
-        const int ub = min(n_units, wg * per), ue = min(n_units, ub + per);
+        // balanced contiguous ranges: the first (n_units % nw) warps take one unit more
+        const int base = n_units / nw, rem = n_units - base * nw;
+        const int ub = wg * base + min(wg, rem), ue = ub + base + (wg < rem ? 1 : 0);
         evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, und_tile, warp_acc);
         if (tl.n_extra > 0 && wg == 0) evaluate_extras<MODEL, MODE>(cfg, sec, tl, level, sh.p, warp_acc);
       }
