@@ -451,6 +451,13 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gn_solve_tiles_kernel"]
+        if args.workload == "c2" and args.mode == "fast":
+            traffic = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
+    except Exception:
+        pass
     my_work = stats[2].item()
     achieved = ALGO_BYTES_PER_PIXEL_EVAL * my_work / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     value = work / wall
@@ -478,8 +485,13 @@ def main():
                              "kernel_value_this_rank": o_work / (o_ms * 1e-3) if o_ms > 0 else None,
                              "unit": "pixel*evaluations/s (kernel time, one rank)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "kernel": "gn_solve_kernel", "kernel_ms_per_step": kern_ms / args.steps,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_note": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json); "
+                                     "algorithmic bytes per launch = 10 B x pixel_evaluations_per_step",
+                     "kernel": "gn_solve_tiles_kernel" if n_sectors >= 1 else "gn_solve_kernel",
+                     "kernel_ms_per_step": kern_ms / args.steps,
+                     "fp32_note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md 4.1): sm__inst_executed_pipe_fma 28 % of peak over the "
+                                  "whole launch, ~70 % issue utilisation inside the level-0 passes (profiles/r1_c2_gn_solve_tiles_fast_ncu_full.txt)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_pixel_evaluation": ALGO_BYTES_PER_PIXEL_EVAL},
     }

@@ -344,7 +344,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
 #pragma unroll 2
         for (int r = 0; r < rpu; ++r)
           staged_pixel<MODEL, MODE, false>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
-                                           (float)__ldg(ucol + (size_t)r * und.pitch),
+                                           (float)__ldg(ucol + (size_t)min(r, und.rows - 1 - y0) * und.pitch),
                                            ((colmask >> r) & 1u) != 0, mom);
       }
     } else {
