@@ -61,6 +61,7 @@ struct Mailbox {
 struct GridWork {
   unsigned int arrive;     // worker CTAs that have delivered their partial sums
   unsigned int generation; // bumped by the master after every LM step
+  int abort;               // set when a grid-barrier wait timed out (never expected)
   float pub_p[kMaxParams];
   int pub_level, pub_done;
   double acc[96]; // grid-wide sums of the current evaluation (fp64 atomics), zeroed by the master

@@ -100,8 +100,6 @@ struct dic_engine {
   size_t cap_counts = 0;
   uint8_t *d_stage = nullptr;
   size_t cap_stage = 0;
-  uint8_t *d_stage_img = nullptr; // staging owned by the image stream (nxt uploads)
-  size_t cap_stage_img = 0;
   float last_ms = 0.f;
   bool timing_pending = false;
   std::atomic<long long> launches{0};
@@ -717,7 +715,7 @@ void dic_destroy(dic_engine *e) {
   if (e->h_results) cudaFreeHost(e->h_results);
   if (e->h_guess) cudaFreeHost(e->h_guess);
   cudaFree(e->d_work); cudaFree(e->d_partials); cudaFree(e->d_scratch);
-  cudaFree(e->d_counts); cudaFree(e->d_offsets); cudaFree(e->d_stage); cudaFree(e->d_stage_img);
+  cudaFree(e->d_counts); cudaFree(e->d_offsets); cudaFree(e->d_stage);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_img) cudaEventDestroy(e->ev_img);
@@ -1308,6 +1306,17 @@ static int collect(dic_engine *e, int first, int count, float *guesses_out, dic_
   }
   const int np = np_of(e);
   int worst = DIC_OK;
+  bool aborted = false;
+  for (int i = 0; i < count; ++i) aborted = aborted || e->h_results[first + i].errorCode == DIC_ERROR_CUDA;
+  if (aborted) { // a grid-barrier wait timed out: bring the barrier scratch back to a clean state
+    GridWork w;
+    if (cudaMemcpy(&w, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      w.arrive = 0; w.abort = 0;
+      for (double &a : w.acc) a = 0.0;
+      cudaMemcpy(e->d_work, &w, sizeof(GridWork), cudaMemcpyHostToDevice);
+    }
+    set_error(e, "a grid-barrier wait inside gn_solve timed out (10 s)");
+  }
   for (int i = 0; i < count; ++i) {
     const dic_result &r = e->h_results[first + i];
     e->sectors[first + i].pending = false;

@@ -16,6 +16,7 @@
 namespace dic {
 
 constexpr int kAccStride = 96; // floats per CTA partial record (>= Acc<12>::kN = 92)
+constexpr unsigned long long kSpinTimeoutNs = 10000000000ull; // 10 s: grid-barrier waits are bounded
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
   unsigned int v;
@@ -332,16 +333,31 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
         if (tid == 0) atomicAdd(&work->arrive, 1u);
       }
       if (tid == 0) {
-        while (ld_acquire_u32(&work->generation) == my_gen) { __nanosleep(64); }
+        // bounded wait: a lost master must never hang the GPU (the launch then ends with error_cuda)
+        const unsigned long long t0 = global_ns();
+        unsigned int spins = 0;
+        sh.level = -1;
+        while (ld_acquire_u32(&work->generation) == my_gen) {
+          __nanosleep(64);
+          if ((++spins & 0xfffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) { sh.level = -2; break; }
+        }
       }
       __syncthreads();
-      if (tid < NP) sh.p[tid] = __ldcg(&work->pub_p[tid]);
-      if (tid == 0) { sh.level = __ldcg(&work->pub_level); sh.done = __ldcg(&work->pub_done); }
+      if (sh.level == -2) { // timed out: leave the loop, the host sees the unfinished result record
+        if (tid == 0) { sh.done = 1; atomicExch(&work->abort, 1); }
+      } else {
+        if (tid < NP) sh.p[tid] = __ldcg(&work->pub_p[tid]);
+        if (tid == 0) { sh.level = __ldcg(&work->pub_level); sh.done = __ldcg(&work->pub_done); }
+      }
     } else {
       if (tid == 0) {
         int m = work->n_marks;
         if (m < kMaxMarks) work->marks[m][1] = global_ns();
-        while (ld_acquire_u32(&work->arrive) < (unsigned int)(n_active - 1)) {}
+        const unsigned long long t0 = global_ns();
+        unsigned int spins = 0;
+        while (ld_acquire_u32(&work->arrive) < (unsigned int)(n_active - 1)) {
+          if ((++spins & 0xffffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) { atomicExch(&work->abort, 1); break; }
+        }
         if (m < kMaxMarks) work->marks[m][2] = global_ns();
       }
       __syncthreads();
@@ -360,6 +376,9 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
         lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
         if (work->rs_local != nullptr && work->rs_error && lane == 0) {
           sh.state.done = 1; result->errorCode = DIC_ERROR_MULTITHREAD; // a peer never answered
+        }
+        if (lane == 0 && *((volatile int *)&work->abort)) { // a CTA of this grid timed out
+          sh.state.done = 1; result->errorCode = DIC_ERROR_CUDA;
         }
         if (lane < NP) { float v = sh.state.p[lane]; sh.p[lane] = v; __stcg(&work->pub_p[lane], v); }
         if (lane == 0) {

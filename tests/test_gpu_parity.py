@@ -400,3 +400,74 @@ def test_rowsplit_loopback_and_band_bookkeeping(eng):
         assert r["error_code"] == 0 and r["evaluations"] == plain["evaluations"]
         assert np.array_equal(r["params"], plain["params"]) and r["chi"] == plain["chi"]
     assert rowsplit.equal_row_bands(41, 377, 3) == [(41, 152), (153, 264), (265, 377)]
+
+
+# ---------------------------------------------------------------- full-size configurations
+
+@pytest.mark.parametrize("mode", [engine.MODE_PARITY, engine.MODE_FAST])
+def test_full_size_c2_annulus_quadratic_vs_oracle(eng, mode):
+    """BASELINE config 2 at full size: 4096^2, annulus 600..1800 (9.05 M pixels), 12 parameters,
+    4 levels. Oracle = our 12-parameter extension with fp64 accumulators (parity unpinned by the
+    reference, which has no such model); the annulus centre is the CPU engine's sequential fp32 mean
+    (about 47 px off the geometric centre for this list length), reproduced bit for bit."""
+    import torch
+    import bench
+    w = bench.workload("c2")
+    und_t, dfm_t = bench.make_images(w, torch.device("cuda", 0))
+    und, dfm = und_t.cpu().numpy(), dfm_t.cpu().numpy()
+    eng.set_fitting_model(engine.FM_QUADRATIC)
+    eng.set_arith_mode(mode)
+    eng.resetImagePyramidsDevice(und_t.data_ptr(), dfm_t.data_ptr(), None, 4096, 4096, 4096, pyramid=w["pyramid"])
+    geom = w["domain"][1:]
+    assert eng.resetPolygon(0, *geom) == 0
+    got = eng.correlate(0, np.zeros(12))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    xy = oracle.annulus_points(*geom)
+    o = make_oracle(und, dfm, model=oracle.FM_QUAD, n_threads=20, pyramid=w["pyramid"], accum_double=True,
+                    real_threads=True)
+    want = o.correlate(np.zeros(12), xy)
+    assert got["und_center"] == want["und_center"]          # the reference's fp32 centre, bit for bit
+    assert abs(float(got["und_center"][0]) - 2048.0) > 10   # ... which is NOT the geometric centre
+    assert got["number_of_points"] == want["number_of_points"] == xy.shape[0]
+    assert got["evaluations"][:4] == want["evaluations"][:4]
+    # both arithmetic modes sit at the same distance from the oracle here (chi 1.1e-5 / 1.4e-5):
+    # solver and summation noise on a 12x12 system, not the interpolation form
+    check_result(got, want, tol_chi=2e-5)
+    assert np.abs(got["params"][6:] - want["params"][6:]).max() < 1e-9
+    truth = np.array(w["truth"])
+    assert np.abs(got["params"][6:] - truth[6:]).max() < 2e-7
+
+
+def test_full_size_c4_subsets_follow_the_displacement_field(eng):
+    """BASELINE config 4 at full size: 4096 subsets of 125^2 in one launch; every subset must report
+    the affine truth evaluated at its own centre (linearity of the field), and a sample must match
+    the oracle."""
+    import torch
+    import bench
+    w = bench.workload("c4")
+    und_t, dfm_t = bench.make_images(w, torch.device("cuda", 0))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramidsDevice(und_t.data_ptr(), dfm_t.data_ptr(), None, 8192, 8192, 8192, pyramid=w["pyramid"])
+    boxes = bench.subset_boxes(*w["domain"][1:])
+    for k, bx in enumerate(boxes):
+        assert eng.resetPolygon(k, *bx) == 0
+    _, res = eng.correlate_batch_raw(0, np.zeros((len(boxes), 6), np.float32))
+    assert (res["errorCode"] == 0).all()
+    assert (res["numberOfPoints"] == 125 * 125).all()
+    t = np.array(w["truth"])
+    cx = res["undCenterX"] - 4096.0
+    cy = res["undCenterY"] - 4096.0
+    assert np.abs(res["resultingParameters"][:, 0] - (t[0] + t[2] * cx + t[3] * cy)).max() < 0.02
+    assert np.abs(res["resultingParameters"][:, 1] - (t[1] + t[4] * cx + t[5] * cy)).max() < 0.02
+    assert np.abs(res["resultingParameters"][:, 2:6] - t[2:6]).max() < 5e-4
+    und, dfm = und_t.cpu().numpy(), dfm_t.cpu().numpy()
+    o = make_oracle(und, dfm, n_threads=1, pyramid=w["pyramid"], accum_double=True)
+    for k in (0, 1234, 4095):
+        bx = boxes[k]
+        want = o.correlate(np.zeros(6), oracle.rect_points(*bx), center=((bx[0] + bx[2]) / 2, (bx[1] + bx[3]) / 2))
+        d = np.abs(res["resultingParameters"][k, :6] - want["params"])
+        assert d[:2].max() < TOL_UV and d[2:].max() < TOL_GRAD
+        assert abs(res["iterations"][k] - want["iterations"]) <= 1
+        assert abs(res["chi"][k] - want["chi"]) < 2e-4 * want["chi"]
