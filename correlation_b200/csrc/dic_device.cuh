@@ -420,7 +420,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
   for (int k = 0; k < NP; ++k) {
     const float dk = __shfl_sync(full, a[k], k);
     if (!(dk > 1e-12f)) return false;
-    const float inv = 1.0f / sqrtf(dk);
+    const float inv = rsqrtf(dk); // 2 ulp is far below the fp32 conditioning noise of the system
     const float lik = a[k] * inv;
     a[k] = lik;
 #pragma unroll
@@ -432,7 +432,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
   float lii = 1.f;
 #pragma unroll
   for (int j = 0; j < NP; ++j) lii = (j == i) ? a[j] : lii;
-  const float rinv = 1.0f / lii;
+  const float rinv = __frcp_rn(lii);
   // forward substitution L y = rhs (column oriented)
   float y = rhs;
 #pragma unroll

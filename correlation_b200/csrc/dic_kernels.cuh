@@ -28,6 +28,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -304,8 +307,10 @@ template <int NP> struct SolveShared {
   float solve[NP * NP + NP + 4];
   float p[kMaxParams];
   int level, done;
+  int rowsplit;  // this launch exchanges its sums with other GPUs (read once per sector, not per evaluation)
+  int mark;      // next slot of the master's timeline
+  int timed_out; // a bounded wait expired
   LMState state;
-  double dred[(kThreads / 32) * NACC];
 };
 
 // After one evaluation pass: sh.tot holds this CTA's sums. Produces the next command in
@@ -328,9 +333,9 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
     if (blockIdx.x != 0) {
       if (active) {
         if (tid < NACC) atomicAdd(&work->acc[tid], (double)sh.tot[tid]);
-        __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(&work->arrive, 1u);
+        // release RMW by one thread after the CTA barrier: cumulative over the other threads' atomics
+        if (tid == 0) red_release_add_u32(&work->arrive, 1u);
       }
       if (tid == 0) {
         // bounded wait: a lost master must never hang the GPU (the launch then ends with error_cuda)
@@ -351,12 +356,12 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
       }
     } else {
       if (tid == 0) {
-        int m = work->n_marks;
-        if (m < kMaxMarks) work->marks[m][1] = global_ns();
+        const int m = sh.mark;
         const unsigned long long t0 = global_ns();
+        if (m < kMaxMarks) work->marks[m][1] = t0;
         unsigned int spins = 0;
         while (ld_acquire_u32(&work->arrive) < (unsigned int)(n_active - 1)) {
-          if ((++spins & 0xffffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) { atomicExch(&work->abort, 1); break; }
+          if ((++spins & 0xffffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) { atomicExch(&work->abort, 1); sh.timed_out = 1; break; }
         }
         if (m < kMaxMarks) work->marks[m][2] = global_ns();
       }
@@ -368,16 +373,16 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
         sh.tot[tid] = (float)s;
       }
       __syncthreads();
-      if (work->rs_local != nullptr) {
+      if (sh.rowsplit) {
         if (warp == 0) rowsplit_allreduce<NACC>(work, sh.tot);
         __syncthreads();
       }
       if (warp == 0) {
         lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
-        if (work->rs_local != nullptr && work->rs_error && lane == 0) {
+        if (sh.rowsplit && work->rs_error && lane == 0) {
           sh.state.done = 1; result->errorCode = DIC_ERROR_MULTITHREAD; // a peer never answered
         }
-        if (lane == 0 && *((volatile int *)&work->abort)) { // a CTA of this grid timed out
+        if (lane == 0 && sh.timed_out) { // a worker never arrived
           sh.state.done = 1; result->errorCode = DIC_ERROR_CUDA;
         }
         if (lane < NP) { float v = sh.state.p[lane]; sh.p[lane] = v; __stcg(&work->pub_p[lane], v); }
@@ -385,12 +390,13 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
           sh.level = sh.state.level; sh.done = sh.state.done;
           __stcg(&work->pub_level, sh.state.level); __stcg(&work->pub_done, sh.state.done);
           __stcg(&work->arrive, 0u);
-          int m = work->n_marks;
-          if (m < kMaxMarks) { work->marks[m][3] = global_ns(); work->n_marks = m + 1; }
-          if (m + 1 < kMaxMarks) work->marks[m + 1][0] = work->marks[m][3];
+          const int m = sh.mark;
+          const unsigned long long t3 = global_ns();
+          if (m < kMaxMarks) { work->marks[m][3] = t3; work->n_marks = m + 1; }
+          if (m + 1 < kMaxMarks) work->marks[m + 1][0] = t3;
+          sh.mark = m + 1;
         }
-        __threadfence();
-        __syncwarp();
+        __syncwarp(); // the other lanes' stores happen-before lane 0's release (cumulativity)
         if (lane == 0) st_release_u32(&work->generation, my_gen + 1);
       }
     }
@@ -417,6 +423,7 @@ __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &
   __shared__ unsigned int s_gen;
   if (GRID && tid == 0) s_gen = ld_acquire_u32(&work->generation);
   if ((!GRID || blockIdx.x == 0) && warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, guess);
+  if (tid == 0) { sh.rowsplit = GRID && work->rs_local != nullptr; sh.mark = 0; sh.timed_out = 0; }
   if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->marks[0][0] = global_ns(); }
   if (tid < NP) sh.p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
   if (tid == 0) { sh.level = cfg.stop; sh.done = 0; }

@@ -299,6 +299,11 @@ class CudaEngine:
         self._ck(self.lib.dic_correlate(self.h, iSector, _ptr(g), C.byref(r)), soft=(1, 2, 3, 5))
         return r.as_dict(self.n_params)
 
+    def correlate_raw(self, iSector, guess_inout, result):
+        """Lowest-overhead form: guess_inout (float32[n_params]) and result (DicResult) are caller-owned
+        and reused; returns the error code."""
+        return self.lib.dic_correlate(self.h, iSector, guess_inout.ctypes.data, C.byref(result))
+
     def correlate_async(self, iSector, guess):
         g = np.zeros(self.n_params, np.float32)
         g[:] = np.asarray(guess, np.float32)[:self.n_params]
