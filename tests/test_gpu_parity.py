@@ -471,3 +471,62 @@ def test_full_size_c4_subsets_follow_the_displacement_field(eng):
         assert d[:2].max() < TOL_UV and d[2:].max() < TOL_GRAD
         assert abs(res["iterations"][k] - want["iterations"]) <= 1
         assert abs(res["chi"][k] - want["chi"]) < 2e-4 * want["chi"]
+
+
+# ---------------------------------------------------------------- pyramid ranges, centre modes, read-back
+
+@pytest.mark.parametrize("pyramid", [(1, 1, 2), (0, 2, 2), (0, 1, 0), (2, 1, 2)])
+def test_pyramid_ranges_vs_oracle(eng, golden, pyramid):
+    g = golden
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=pyramid)
+    x0, y0, x1, y1 = (int(v) for v in g["A/rect"])
+    assert eng.resetPolygon(0, x0, y0, x1, y1) == 0
+    guess = np.array([1.5, -0.5, 0, 0, 0, 0], np.float32)
+    got = eng.correlate(0, guess)
+    o = make_oracle(g["A/und"], g["A/def"], n_threads=20, pyramid=pyramid, accum_double=True)
+    want = o.correlate(guess, oracle.rect_points(x0, y0, x1, y1), center=(95.0, 95.0))
+    check_result(got, want, tol_chi=3e-5)
+    assert got["evaluations"] == want["evaluations"][:8]
+
+
+def test_bad_pyramid_range_is_refused(eng, golden):
+    with pytest.raises(engine.DicError):
+        eng.resetImagePyramids(golden["A/und"], golden["A/def"], pyramid=(0, 2, 3))  # (stop - start) % step != 0
+
+
+def test_center_modes_and_override(eng, golden):
+    g = golden
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 2))
+    geom = (20.0, 50.0, 0.0, 2 * np.pi, 96.3, 95.1, 1)
+    eng.set_center_mode(engine.CENTER_EXACT)
+    assert eng.resetPolygon(1, *geom) == 0
+    pts = oracle.annulus_points(*geom)
+    cx, cy = eng.level_center(1, 0)
+    assert abs(cx - pts[:, 0].astype(np.float64).mean()) < 1e-4 and abs(cy - pts[:, 1].astype(np.float64).mean()) < 1e-4
+    eng.set_center_mode(engine.CENTER_REFERENCE)
+    assert eng.resetPolygon(1, *geom) == 0
+    assert eng.level_center(1, 0) == oracle.seq_mean_center(pts)
+    eng.setPolygonCenter(1, 96.0, 95.0)
+    assert eng.level_center(1, 1) == (48.0, 47.5)
+    got = eng.correlate(1, np.zeros(6))
+    o = make_oracle(g["A/und"], g["A/def"], n_threads=20, pyramid=(0, 1, 2), accum_double=True)
+    want = o.correlate(np.zeros(6), pts, center=(96.0, 95.0))
+    check_result(got, want, tol_chi=3e-5)
+
+
+def test_deformed_points_read_back(eng, golden):
+    g = golden
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(g["A/und"], g["A/def"], pyramid=(0, 1, 2))
+    x0, y0, x1, y1 = (int(v) for v in g["A/rect"])
+    eng.resetPolygon(0, x0, y0, x1, y1)
+    r = eng.correlate(0, np.zeros(6))
+    und_xy, def_xy = eng.getUndXY0ToCPU(0), eng.getDefXY0ToCPU(0)
+    assert np.array_equal(und_xy, golden["A/points0"])
+    p = r["params"]
+    dx, dy = und_xy[:, 0] - np.float32(95.0), und_xy[:, 1] - np.float32(95.0)
+    want_x = und_xy[:, 0] + p[0] + p[2] * dx + p[3] * dy   # model_class.cpp:171-172, fp32 left to right
+    want_y = und_xy[:, 1] + p[1] + p[4] * dx + p[5] * dy
+    assert np.array_equal(def_xy[:, 0], want_x.astype(np.float32)) and np.array_equal(def_xy[:, 1], want_y.astype(np.float32))
