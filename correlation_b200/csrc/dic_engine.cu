@@ -523,25 +523,26 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
   const float *guesses = e->d_guess;
   dic_result *results = e->d_results;
   GridWork *work = e->d_work;
-  float *partials = e->d_partials;
   if (grid_mode) {
     auto kern = gn_solve_kernel<MODEL, INTERP, MODE, true>;
-    int per_sm = 0;
-    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    static int per_sm_cached[16] = {0};
+    int &per_sm = per_sm_cached[e->device & 15];
+    if (per_sm == 0) CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
     if (per_sm < 1) { set_error(e, "gn_solve_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }
     // enough CTAs for ~4 pixels per thread at the finest level, never more than co-resident
     long n0 = e->sectors[first].n[e->start];
     int want = (int)std::min<long>((n0 + kThreads * 4 - 1) / (kThreads * 4), (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
-    void *args[] = {&cfg, &sectors, &guesses, &results, &first, &one, &work, &partials};
+    void *args[] = {&cfg, &sectors, &guesses, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, 0, e->stream));
   } else {
     auto kern = gn_solve_kernel<MODEL, INTERP, MODE, false>;
-    int per_sm = 0;
-    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    static int per_sm_cached[16] = {0};
+    int &per_sm = per_sm_cached[e->device & 15];
+    if (per_sm == 0) CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
     int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
-    kern<<<grid, kThreads, 0, e->stream>>>(cfg, sectors, guesses, results, first, count, work, partials);
+    kern<<<grid, kThreads, 0, e->stream>>>(cfg, sectors, guesses, results, first, count, work);
     CU_TRY(e, cudaGetLastError());
   }
   e->launches++;
@@ -562,29 +563,34 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   const float *guesses = e->d_guess;
   dic_result *results = e->d_results;
   GridWork *work = e->d_work;
-  float *partials = e->d_partials;
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
   const size_t smem = tiles_dyn_smem(NACC);
   if (grid_mode) {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, true>;
-    CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    static int per_sm_cached[16] = {0}; // per device: attribute + occupancy queried once, not per launch
+    int &per_sm = per_sm_cached[e->device & 15];
+    if (per_sm == 0) {
+      CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    }
     if (per_sm < 1) { set_error(e, "gn_solve_tiles_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }
     // one warp per ~2 finest-level tiles at most, never more CTAs than are co-resident
     long nt = e->sectors[first].tl[e->start].n_tiles;
     int want = (int)std::min<long>((nt + kWarpsPerCta - 1) / kWarpsPerCta, (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
-    void *args[] = {&cfg, &sectors, &stiles, &guesses, &results, &first, &one, &work, &partials};
+    void *args[] = {&cfg, &sectors, &stiles, &guesses, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, smem, e->stream));
   } else {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, false>;
-    CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    static int per_sm_cached[16] = {0};
+    int &per_sm = per_sm_cached[e->device & 15];
+    if (per_sm == 0) {
+      CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    }
     int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
-    kern<<<grid, kThreads, smem, e->stream>>>(cfg, sectors, stiles, guesses, results, first, count, work, partials);
+    kern<<<grid, kThreads, smem, e->stream>>>(cfg, sectors, stiles, guesses, results, first, count, work);
     CU_TRY(e, cudaGetLastError());
   }
   e->launches++;

@@ -315,16 +315,16 @@ template <int NP> struct SolveShared {
 
 // After one evaluation pass: sh.tot holds this CTA's sums. Produces the next command in
 // sh.p / sh.level / sh.done for every CTA.
-//   GRID: CTA 0 is the master. Workers that took part (`active`) store their sums to `partials`,
-//   fence, and bump `arrive`; the master waits for n_active - 1 arrivals, adds the rows in a
-//   fixed order (double accumulation, deterministic), runs the LM step + solve in its warp 0
+//   GRID: CTA 0 is the master. Workers that took part (`active`) add their sums to work->acc with
+//   fp64 atomics and bump `arrive` with a release RMW; the master waits for n_active - 1
+//   arrivals, adds its own sums, runs the LM step + solve in its warp 0
 //   with the state in ITS shared memory, publishes the command and releases `generation`.
 //   Batch: the CTA owns the sector; only __syncthreads is needed.
 template <int MODEL, bool GRID>
 __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)> &sh, bool active,
                                                 int n_active, const SolveSettings &cfg,
                                                 const SectorDev *sec, dic_result *result,
-                                                GridWork *work, float *partials, unsigned int &my_gen) {
+                                                GridWork *work, unsigned int &my_gen) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   constexpr int kW = kThreads / 32;
@@ -437,7 +437,7 @@ template <int MODEL, int INTERP, int MODE, bool GRID>
 __global__ void __launch_bounds__(kThreads)
 gn_solve_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
                 const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
-                int n_sectors, GridWork *work, float *partials) {
+                int n_sectors, GridWork *work) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   __shared__ float s_red[(kThreads / 32) * NACC];
@@ -472,7 +472,7 @@ gn_solve_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
       }
       __syncthreads();
       block_reduce<NACC>(acc, s_red, sh.tot);
-      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, partials, my_gen);
+      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, my_gen);
       if (sh.done) break;
     }
     __syncthreads();

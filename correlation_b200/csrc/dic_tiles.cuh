@@ -255,7 +255,7 @@ template <int MODEL, int MODE>
 __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const SectorDev *sec,
                                                const TileLevel tl, int level, const float *p,
                                                int unit_begin, int unit_end, int split_log2, float *patch,
-                                               float *und_tile, float *warp_acc) {
+                                               float *warp_acc) {
   constexpr int NP = model_nparams(MODEL);
   using M = Mom<NP>;
   const int lane = threadIdx.x & 31;
@@ -401,8 +401,7 @@ template <int MODEL, int MODE, bool GRID>
 __global__ void __launch_bounds__(kThreads, DIC_TILE_CTAS_PER_SM)
 gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
                       const SectorTiles *__restrict__ sector_tiles, const float *__restrict__ guesses,
-                      dic_result *__restrict__ results, int first_sector, int n_sectors, GridWork *work,
-                      float *partials) {
+                      dic_result *__restrict__ results, int first_sector, int n_sectors, GridWork *work) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   extern __shared__ __align__(16) float dyn_smem[];
@@ -411,7 +410,6 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
   __shared__ SolveShared<NP> sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float *patch = s_patch + warp * kPatchH * kPatchW;
-  float *und_tile = nullptr;
   float *warp_acc = s_wacc + warp * NACC;
 
   for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
@@ -445,7 +443,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
         // balanced contiguous ranges: the first (n_units % nw) warps take one unit more
         const int base = n_units / nw, rem = n_units - base * nw;
         const int ub = wg * base + min(wg, rem), ue = ub + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, und_tile, warp_acc);
+        evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, warp_acc);
         if (tl.n_extra > 0 && wg == 0) evaluate_extras<MODEL, MODE>(cfg, sec, tl, level, sh.p, warp_acc);
       }
       __syncthreads();
@@ -456,7 +454,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
         sh.tot[k] = s;
       }
       __syncthreads();
-      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, partials, my_gen);
+      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, my_gen);
       if (sh.done) break;
     }
     __syncthreads();
