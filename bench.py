@@ -511,7 +511,7 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_pixel_evaluation": ALGO_BYTES_PER_PIXEL_EVAL},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             und, dfm = und_pin.numpy(), dfm_pin.numpy()
             threads = os.cpu_count() or 1

@@ -30,7 +30,25 @@ constexpr int kWarpsPerCta = kThreads / 32;
 struct Tile {
   int x0, y0;             // level coordinates of the tile's first pixel
   uint32_t rows[kTileH];  // bit l of rows[r] <=> pixel (x0 + l, y0 + r) belongs to the domain
+  uint16_t cols[kTileW];  // the same membership transposed: bit r of cols[l]
+  uint32_t full_rows;     // bit r set <=> rows[r] == 0xffffffff
+  uint32_t pad;
 };
+
+// fills the derived fields of a tile from rows[]
+__device__ __forceinline__ void tile_finish(Tile &t) {
+  uint32_t full = 0;
+#pragma unroll
+  for (int r = 0; r < kTileH; ++r) full |= (t.rows[r] == 0xffffffffu ? 1u : 0u) << r;
+  t.full_rows = full;
+  t.pad = 0;
+  for (int l = 0; l < kTileW; ++l) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < kTileH; ++r) c |= ((t.rows[r] >> l) & 1u) << r;
+    t.cols[l] = (uint16_t)c;
+  }
+}
 
 struct TileLevel {
   const Tile *tiles;
@@ -286,12 +304,9 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
     const int r0 = (u & ((1 << split_log2) - 1)) * rpu;
     const int x0 = __ldg(&tp->x0), y0 = __ldg(&tp->y0) + r0;
     // this lane's column of the membership mask: bit r <=> pixel (x0 + lane, y0 + r)
-    uint32_t colmask = 0, all_rows = 0xffffffffu;
-    for (int r = 0; r < rpu; ++r) {
-      const uint32_t m = __ldg(&tp->rows[r0 + r]);
-      colmask |= ((m >> lane) & 1u) << r;
-      all_rows &= m;
-    }
+    const uint32_t unit_rows = ((1u << rpu) - 1u) << r0;
+    const uint32_t colmask = ((uint32_t)__ldg(&tp->cols[lane]) & unit_rows) >> r0;
+    const bool unit_full = (__ldg(&tp->full_rows) & unit_rows) == unit_rows;
     if (__all_sync(0xffffffffu, colmask == 0)) continue; // empty row chunk of a partial tile
     if (x0 != cur_x0) {
       if (cur_x0 != INT_MIN) flush_moments<NP>(mom, X, warp_acc);
@@ -300,23 +315,26 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
       X = __fsub_rn(xf, ccx);
       lw.set(p, xf, X);
     }
-    // footprint of the unit under the current parameters (corners, widened for curvature)
+    // footprint of the unit under the current parameters: one corner per lane (lanes 0-3), min / max
+    // by shuffle, widened for the curvature of the quadratic model
     float bx0, bx1, by0, by1;
     {
-      const float Xa = (float)x0 - ccx, Xb = (float)(x0 + kTileW - 1) - ccx;
-      const float Ya = (float)y0 - ccy, Yb = (float)(y0 + rpu - 1) - ccy;
-      bx0 = by0 = 3.0e38f; bx1 = by1 = -3.0e38f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float Xc = (c & 1) ? Xb : Xa, Yc = (c & 2) ? Yb : Ya;
-        float xd = Xc + ccx + p[0] + p[2] * Xc + p[3] * Yc;
-        float yd = Yc + ccy + p[1] + p[4] * Xc + p[5] * Yc;
-        if (NP == 12) {
-          xd += 0.5f * p[6] * Xc * Xc + p[7] * Xc * Yc + 0.5f * p[8] * Yc * Yc;
-          yd += 0.5f * p[9] * Xc * Xc + p[10] * Xc * Yc + 0.5f * p[11] * Yc * Yc;
-        }
-        bx0 = fminf(bx0, xd); bx1 = fmaxf(bx1, xd); by0 = fminf(by0, yd); by1 = fmaxf(by1, yd);
+      const float Xc = ((lane & 1) ? (float)(x0 + kTileW - 1) : (float)x0) - ccx;
+      const float Yc = ((lane & 2) ? (float)(y0 + rpu - 1) : (float)y0) - ccy;
+      float xd = Xc + ccx + p[0] + p[2] * Xc + p[3] * Yc;
+      float yd = Yc + ccy + p[1] + p[4] * Xc + p[5] * Yc;
+      if (NP == 12) {
+        xd += 0.5f * p[6] * Xc * Xc + p[7] * Xc * Yc + 0.5f * p[8] * Yc * Yc;
+        yd += 0.5f * p[9] * Xc * Xc + p[10] * Xc * Yc + 0.5f * p[11] * Yc * Yc;
       }
+      bx0 = bx1 = xd; by0 = by1 = yd;
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+      }
+      bx0 = __shfl_sync(0xffffffffu, bx0, 0); bx1 = __shfl_sync(0xffffffffu, bx1, 0);
+      by0 = __shfl_sync(0xffffffffu, by0, 0); by1 = __shfl_sync(0xffffffffu, by1, 0);
       float slack = 0.01f;
       if (NP == 12)
         slack += 128.f * (fabsf(p[6]) + fabsf(p[9])) + 32.f * (fabsf(p[8]) + fabsf(p[11]));
@@ -335,7 +353,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
     const uint8_t *ucol = und.ptr + (size_t)y0 * und.pitch + x0 + lane;
 
     if (staged) {
-      if (all_rows == 0xffffffffu) {
+      if (unit_full) {
 #pragma unroll 2
         for (int r = 0; r < rpu; ++r)
           staged_pixel<MODEL, MODE, true>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
@@ -494,6 +512,7 @@ struct TilePred {
     for (int r = 0; r < kTileH; ++r) { out.rows[r] = m[r]; any |= m[r]; }
     int tx = (int)(idx / nty), ty = (int)(idx % nty);
     out.x0 = gx0 + tx * kTileW; out.y0 = gy0 + ty * kTileH;
+    if (any != 0) tile_finish(out);
     return any != 0;
   }
 };
@@ -541,6 +560,7 @@ __global__ void rect_tiles_kernel(Tile *__restrict__ out, int ntx, int nty, int 
   uint32_t m = wcols >= 32 ? 0xffffffffu : ((1u << wcols) - 1u);
 #pragma unroll
   for (int r = 0; r < kTileH; ++r) q.rows[r] = r < hrows ? m : 0u;
+  tile_finish(q);
   out[t] = q;
 }
 
