@@ -1,0 +1,31 @@
+"""CPU suite: the reference arm of bench.py runs without a GPU and prints the contract's JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().split("\n")[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True
+    assert line["metric"] == "domain pixel*GN-evaluations/s" and line["unit"] == "pixel*evaluations/s"
+    assert line["value"] > 0 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "c1" in line["config"]["workload"]
+
+
+def test_subset_boxes_follow_manager_arithmetic():
+    sys.path.insert(0, ROOT)
+    import bench
+    boxes = bench.subset_boxes(64, 8128, 64)
+    assert len(boxes) == 4096
+    w = {b[2] - b[0] + 1 for b in boxes} | {b[3] - b[1] + 1 for b in boxes}
+    assert w == {125}                       # (8064 / 64 - 1) / 2 = 62 -> 2 * 62 + 1
+    assert boxes[0][:2] == (65, 65) and boxes[1][0] == boxes[0][0]  # centre int(.5 + 64 + 62.5) = 127; sector = i * vs + j, j (y) fastest
+    assert all(b[0] >= 64 and b[2] <= 8128 for b in boxes)
