@@ -62,6 +62,7 @@ struct GridWork {
   unsigned int arrive;     // worker CTAs that have delivered their partial sums
   unsigned int generation; // bumped by the master after every LM step
   int abort;               // set when a grid-barrier wait timed out (never expected)
+  unsigned int slow_units; // units of the last launch that took the per-pixel (non-staged) path
   float pub_p[kMaxParams];
   int pub_level, pub_done;
   double acc[96]; // grid-wide sums of the current evaluation (fp64 atomics), zeroed by the master

@@ -1531,6 +1531,7 @@ int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap) {
   if (cudaMemcpy(&h, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   int n = std::min(std::min(h.n_marks, cap), kMaxMarks);
   memcpy(marks, h.marks, sizeof(unsigned long long) * 4 * n);
+  if (n < cap) marks[4 * n] = h.slow_units; // one extra word: units that took the per-pixel path
   return n;
 }
 float dic_last_correlate_ms(dic_engine *e) { return e ? e->last_ms : 0.f; }

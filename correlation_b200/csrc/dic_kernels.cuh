@@ -424,7 +424,7 @@ __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &
   if (GRID && tid == 0) s_gen = ld_acquire_u32(&work->generation);
   if ((!GRID || blockIdx.x == 0) && warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, guess);
   if (tid == 0) { sh.rowsplit = GRID && work->rs_local != nullptr; sh.mark = 0; sh.timed_out = 0; }
-  if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->marks[0][0] = global_ns(); }
+  if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->slow_units = 0; work->marks[0][0] = global_ns(); }
   if (tid < NP) sh.p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
   if (tid == 0) { sh.level = cfg.stop; sh.done = 0; }
   __syncthreads();

@@ -273,7 +273,7 @@ template <int MODEL, int MODE>
 __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const SectorDev *sec,
                                                const TileLevel tl, int level, const float *p,
                                                int unit_begin, int unit_end, int split_log2, float *patch,
-                                               float *warp_acc) {
+                                               float *warp_acc, unsigned int *slow_counter) {
   constexpr int NP = model_nparams(MODEL);
   using M = Mom<NP>;
   const int lane = threadIdx.x & 31;
@@ -366,6 +366,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
                                            ((colmask >> r) & 1u) != 0, mom);
       }
     } else {
+      if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
       // footprint leaves the image or the staging buffer: per-pixel path with the reference's
       // own bounds test (error 2 + zero contribution, interpolation_class.cpp:129-137)
 #pragma unroll 1
@@ -461,7 +462,8 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
         // balanced contiguous ranges: the first (n_units % nw) warps take one unit more
         const int base = n_units / nw, rem = n_units - base * nw;
         const int ub = wg * base + min(wg, rem), ue = ub + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, warp_acc);
+        evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, warp_acc,
+                                    GRID ? &work->slow_units : nullptr);
         if (tl.n_extra > 0 && wg == 0) evaluate_extras<MODEL, MODE>(cfg, sec, tl, level, sh.p, warp_acc);
       }
       __syncthreads();

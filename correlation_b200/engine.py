@@ -394,8 +394,9 @@ class CudaEngine:
         return float(self.lib.dic_last_correlate_ms(self.h))
 
     def timeline(self):
-        m = np.zeros((128, 4), np.uint64)
-        n = self.lib.dic_get_timeline(self.h, _ptr(m), 128)
+        m = np.zeros((129, 4), np.uint64)
+        n = self.lib.dic_get_timeline(self.h, _ptr(m), 129)
+        self.slow_units = int(m[n, 0]) if n < 129 else -1
         return m[:n].astype(np.int64)
 
     def kernel_launches(self):

@@ -18,6 +18,7 @@ for mode, variant in ((engine.MODE_FAST, 0), (engine.MODE_FAST, 1)):
         r = eng.correlate(0, np.zeros(npar, np.float32))
     t = eng.timeline()
     print(f"{name} kernel={'list' if variant else 'tiles'} total {eng.last_correlate_ms():.3f} ms, evals {r['evaluations'][:4]}, points {r['points_per_level'][:4]}")
+    print("  units on the per-pixel (non-staged) path over the whole launch:", getattr(eng, "slow_units", None))
     print("  eval:  own-pass  wait-others  sum+LM   (us)")
     for i, m in enumerate(t):
         print(f"  {i:3d}  {(m[1]-m[0])/1e3:8.1f} {(m[2]-m[1])/1e3:8.1f} {(m[3]-m[2])/1e3:8.1f}")
