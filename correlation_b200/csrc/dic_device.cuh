@@ -131,26 +131,13 @@ __device__ __forceinline__ void hermite_to_monomial(float f1, float f2, float d1
   c[3] = 2.f * f1 - 2.f * f2 + d1 + d2;
 }
 
-__device__ __forceinline__ void bicubic_parity(const float p[4][4], float xdef, float ydef, int ix,
-                                               int iy, float &w, float &wx, float &wy) {
-  // x pass: for each image row r, cubic in x through columns 1,2 with central-difference slopes
-  float cx[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-    hermite_to_monomial(p[r][1], p[r][2], (p[r][2] - p[r][0]) * 0.5f, (p[r][3] - p[r][1]) * 0.5f,
-                        cx[r]);
-  // y pass: a[jk][ik]
-  float a[4][4];
-#pragma unroll
-  for (int ik = 0; ik < 4; ++ik) {
-    float c[4];
-    hermite_to_monomial(cx[1][ik], cx[2][ik], (cx[2][ik] - cx[0][ik]) * 0.5f,
-                        (cx[3][ik] - cx[1][ik]) * 0.5f, c);
-#pragma unroll
-    for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
-  }
-  float dx = __fadd_rn(__fsub_rn(xdef, (float)ix), 1.f);
-  float dy = __fadd_rn(__fsub_rn(ydef, (float)iy), 1.f);
+// The 40 terms of interpolation_class.cpp:108-126 in the reference's order, unfused mul / add.
+// Exact shortcuts only: x * 1 is skipped, (2 a) * y == 2 (a * y) and acc + 2 t == fma(2, t, acc)
+// bit for bit (power-of-two scaling commutes with rounding), 3 a is exact (|a| < 2^20, quarter units).
+__device__ __forceinline__ void parity_eval(const float a[4][4], float xdef, float ydef, int ix, int iy,
+                                            float &w, float &wx, float &wy) {
+  const float dx = __fadd_rn(__fsub_rn(xdef, (float)ix), 1.f);
+  const float dy = __fadd_rn(__fsub_rn(ydef, (float)iy), 1.f);
   float px[4], py[4];
   px[0] = 1.f; px[1] = dx; px[2] = __fmul_rn(dx, dx); px[3] = __fmul_rn(px[2], dx);
   py[0] = 1.f; py[1] = dy; py[2] = __fmul_rn(dy, dy); py[3] = __fmul_rn(py[2], dy);
@@ -159,23 +146,99 @@ __device__ __forceinline__ void bicubic_parity(const float p[4][4], float xdef, 
   for (int jk = 0; jk < 4; ++jk) {
 #pragma unroll
     for (int ik = 0; ik < 4; ++ik) {
-      float c = a[jk][ik];
-      // w += (a * py[jk]) * px[ik]
-      float u = jk == 0 ? c : __fmul_rn(c, py[jk]);
-      rw = __fadd_rn(rw, ik == 0 ? u : __fmul_rn(u, px[ik]));
-      if (ik > 0) { // wx += ((ik * a) * py[jk]) * px[ik-1]
-        float t = __fmul_rn((float)ik, c);
+      const float c = a[jk][ik];
+      const float u = jk == 0 ? c : __fmul_rn(c, py[jk]);            // a * py[jk]
+      rw = __fadd_rn(rw, ik == 0 ? u : __fmul_rn(u, px[ik]));        // w += (a * py[jk]) * px[ik]
+      // wx += ((ik * a) * py[jk]) * px[ik - 1]
+      if (ik == 1) rx = __fadd_rn(rx, u);
+      if (ik == 2) rx = __fmaf_rn(2.f, __fmul_rn(u, px[1]), rx);
+      if (ik == 3) {
+        float t = __fmul_rn(3.f, c);
         t = jk == 0 ? t : __fmul_rn(t, py[jk]);
-        t = ik == 1 ? t : __fmul_rn(t, px[ik - 1]);
-        rx = __fadd_rn(rx, t);
+        rx = __fadd_rn(rx, __fmul_rn(t, px[2]));
       }
-      if (jk > 0) { // wy += ((jk * a) * py[jk-1]) * px[ik]
-        float t = __fmul_rn((float)jk, c);
-        t = jk == 1 ? t : __fmul_rn(t, py[jk - 1]);
-        t = ik == 0 ? t : __fmul_rn(t, px[ik]);
-        ry = __fadd_rn(ry, t);
+      // wy += ((jk * a) * py[jk - 1]) * px[ik]
+      if (jk == 1) ry = __fadd_rn(ry, ik == 0 ? c : __fmul_rn(c, px[ik]));
+      if (jk == 2) {
+        const float v = __fmul_rn(c, py[1]);
+        ry = __fmaf_rn(2.f, ik == 0 ? v : __fmul_rn(v, px[ik]), ry);
+      }
+      if (jk == 3) {
+        const float t = __fmul_rn(__fmul_rn(3.f, c), py[2]);
+        ry = __fadd_rn(ry, ik == 0 ? t : __fmul_rn(t, px[ik]));
       }
     }
+  }
+  w = rw; wx = rx; wy = ry;
+}
+
+// y pass of the separable coefficient stage: rows r0..r3 hold the x-direction monomial
+// coefficients (in s = 1 + t) of image rows iy-1 .. iy+2.
+__device__ __forceinline__ void bicubic_parity_rows(const float *r0, const float *r1, const float *r2,
+                                                    const float *r3, float xdef, float ydef, int ix, int iy,
+                                                    float &w, float &wx, float &wy) {
+  float a[4][4];
+#pragma unroll
+  for (int ik = 0; ik < 4; ++ik) {
+    float c[4];
+    hermite_to_monomial(r1[ik], r2[ik], (r2[ik] - r0[ik]) * 0.5f, (r3[ik] - r1[ik]) * 0.5f, c);
+#pragma unroll
+    for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
+  }
+  parity_eval(a, xdef, ydef, ix, iy, w, wx, wy);
+}
+
+__device__ __forceinline__ void bicubic_parity(const float p[4][4], float xdef, float ydef, int ix,
+                                               int iy, float &w, float &wx, float &wy) {
+  // x pass: for each image row r, cubic in x through columns 1,2 with central-difference slopes
+  float cx[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    hermite_to_monomial(p[r][1], p[r][2], (p[r][2] - p[r][0]) * 0.5f, (p[r][3] - p[r][1]) * 0.5f,
+                        cx[r]);
+  bicubic_parity_rows(cx[0], cx[1], cx[2], cx[3], xdef, ydef, ix, iy, w, wx, wy);
+}
+
+// x-direction cubic of one image row on [e, e+1) from pixels q[0..3] = p[e-1 .. e+2].
+//  PARITY: the reference's monomial coefficients in s = 1 + t (= hermite_to_monomial of the row),
+//          written with differences; every intermediate is a small multiple of 1/2: exact in fp32.
+//  FAST:   Catmull-Rom coefficients in t (well conditioned).
+template <int MODE>
+__device__ __forceinline__ void row_coeffs(const float *q, float c[4]) {
+  const float p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
+  if (MODE == DIC_MODE_PARITY) {
+    const float a = p1 - p2, b = p3 - p0, d = p1 - p0;
+    c[3] = 0.5f * b + 1.5f * a;
+    c[0] = p0 - b - 3.f * a;
+    c[1] = 2.5f * b + 8.f * a + 1.5f * d;
+    c[2] = -2.f * b - 6.5f * a - 0.5f * d;
+  } else {
+    c[0] = p1;
+    c[1] = 0.5f * (p2 - p0);
+    c[2] = p0 - 2.5f * p1 + 2.f * p2 - 0.5f * p3;
+    c[3] = 0.5f * (p3 - p0) + 1.5f * (p1 - p2);
+  }
+}
+
+// Fast mode on row coefficients: value and x-derivative of each row by Horner, then Catmull-Rom
+// weights in y.
+__device__ __forceinline__ void cr_weights(float t, float w[4], float d[4]);
+__device__ __forceinline__ void bicubic_fast_rows(const float *r0, const float *r1, const float *r2,
+                                                  const float *r3, float tx, float ty, float &w, float &wx,
+                                                  float &wy) {
+  const float t2 = tx + tx, t3 = 3.f * tx * tx;
+  float wyw[4], wyd[4];
+  cr_weights(ty, wyw, wyd);
+  const float *rows[4] = {r0, r1, r2, r3};
+  float rw = 0.f, rx = 0.f, ry = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float *c = rows[k];
+    const float v = fmaf(fmaf(fmaf(c[3], tx, c[2]), tx, c[1]), tx, c[0]);
+    const float dv = fmaf(c[3], t3, fmaf(c[2], t2, c[1]));
+    rw = fmaf(wyw[k], v, rw);
+    rx = fmaf(wyw[k], dv, rx);
+    ry = fmaf(wyd[k], v, ry);
   }
   w = rw; wx = rx; wy = ry;
 }

@@ -234,12 +234,17 @@ template <int NP> struct LaneWarp {
   }
 };
 
-// One staged pixel: deformed position from the lane constants, 4x4 fp32 gather from the staged
-// patch, bicubic, residual, moments. `mf` is 1 for member pixels and 0 otherwise (FULL: no mask).
-template <int MODEL, int MODE, bool FULL>
+// One staged pixel. The lane walks down a column, so consecutive pixels normally share three of
+// their four window rows: the x-direction cubic coefficients of the window rows are kept in
+// registers (cw, slot-rotated by the static step S) and only the new bottom row is read from the
+// staged patch (4 LDS) and converted; a lane whose window moved differently (ix changed, iy did not
+// advance by exactly one, first row of a unit) rebuilds all four rows. `member` masks pixels outside
+// the domain (FULL: every pixel of the unit is a member).
+template <int MODEL, int MODE, bool FULL, int S>
 __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<model_nparams(MODEL)> &lw,
                                              float xf, float yf, float ccx, float ccy, const float *patch,
-                                             int px0, int py0, float und_w, bool member, float *mom) {
+                                             int px0, int py0, float und_w, bool member, float (&cw)[4][4],
+                                             int &wix, int &wiy, float *mom) {
   constexpr int NP = model_nparams(MODEL);
   const float Y = __fsub_rn(yf, ccy);
   float xd, yd;
@@ -253,14 +258,20 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
   int ix, iy;
   const float fx = floor_magic(xd, ix), fy = floor_magic(yd, iy);
   const float *q = patch + (iy - 1 - py0) * kPatchW + (ix - 1 - px0);
-  float pp[4][4];
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) pp[rr][cc] = q[rr * kPatchW + cc];
+  if (ix == wix && iy == wiy + 1) {
+    row_coeffs<MODE>(q + 3 * kPatchW, cw[(3 + S) & 3]);
+  } else {
+    row_coeffs<MODE>(q, cw[(0 + S) & 3]);
+    row_coeffs<MODE>(q + kPatchW, cw[(1 + S) & 3]);
+    row_coeffs<MODE>(q + 2 * kPatchW, cw[(2 + S) & 3]);
+    row_coeffs<MODE>(q + 3 * kPatchW, cw[(3 + S) & 3]);
+  }
+  wix = ix; wiy = iy;
   float w, wx, wy;
-  if (MODE == DIC_MODE_PARITY) bicubic_parity(pp, xd, yd, ix, iy, w, wx, wy);
-  else bicubic_fast(pp, xd - fx, yd - fy, w, wx, wy);
+  if (MODE == DIC_MODE_PARITY)
+    bicubic_parity_rows(cw[(0 + S) & 3], cw[(1 + S) & 3], cw[(2 + S) & 3], cw[(3 + S) & 3], xd, yd, ix, iy, w, wx, wy);
+  else
+    bicubic_fast_rows(cw[(0 + S) & 3], cw[(1 + S) & 3], cw[(2 + S) & 3], cw[(3 + S) & 3], xd - fx, yd - fy, w, wx, wy);
   float V = und_w - w;
   if (!FULL) { V = member ? V : 0.f; wx = member ? wx : 0.f; wy = member ? wy : 0.f; }
   accumulate_moments<NP>(mom, V, wx, wy, Y);
@@ -353,18 +364,20 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
     const uint8_t *ucol = und.ptr + (size_t)y0 * und.pitch + x0 + lane;
 
     if (staged) {
+      float cw[4][4];
+      int wix = INT_MIN, wiy = INT_MIN; // no window yet: the first row rebuilds all four
+#define DIC_STEP(FULLV, SV, R)                                                                            \
+  staged_pixel<MODEL, MODE, FULLV, SV>(pw, lw, xf, (float)(y0 + (R)), ccx, ccy, patch, px0, py0,           \
+                                       (float)__ldg(ucol + (size_t)min((R), und.rows - 1 - y0) * und.pitch), \
+                                       FULLV || ((colmask >> (R)) & 1u) != 0, cw, wix, wiy, mom)
       if (unit_full) {
-#pragma unroll 2
-        for (int r = 0; r < rpu; ++r)
-          staged_pixel<MODEL, MODE, true>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
-                                          (float)__ldg(ucol + (size_t)r * und.pitch), true, mom);
+#pragma unroll 1
+        for (int r = 0; r < rpu; r += 4) { DIC_STEP(true, 0, r); DIC_STEP(true, 1, r + 1); DIC_STEP(true, 2, r + 2); DIC_STEP(true, 3, r + 3); }
       } else {
-#pragma unroll 2
-        for (int r = 0; r < rpu; ++r)
-          staged_pixel<MODEL, MODE, false>(pw, lw, xf, (float)(y0 + r), ccx, ccy, patch, px0, py0,
-                                           (float)__ldg(ucol + (size_t)min(r, und.rows - 1 - y0) * und.pitch),
-                                           ((colmask >> r) & 1u) != 0, mom);
+#pragma unroll 1
+        for (int r = 0; r < rpu; r += 4) { DIC_STEP(false, 0, r); DIC_STEP(false, 1, r + 1); DIC_STEP(false, 2, r + 2); DIC_STEP(false, 3, r + 3); }
       }
+#undef DIC_STEP
     } else {
       if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
       // footprint leaves the image or the staging buffer: per-pixel path with the reference's
