@@ -123,6 +123,14 @@ int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt_dev, int rows, 
 /* replace only the deformed image (host convenience for frame loops without a nxt slot) */
 int dic_reset_def_pyramid(dic_engine *e, const uint8_t *def, int rows, int cols);
 int dic_reset_def_pyramid_device(dic_engine *e, const void *def_dev, int rows, int cols, int pitch);
+/* extension: double-buffered ingest of whole image pairs. dic_stage_next_pair enqueues the upload
+ * and the pyramid build of the NEXT (und, def) pair on the image stream and returns at once: both
+ * host buffers must stay untouched until the dic_advance_pair that makes the staged pair current
+ * (a stream-side wait, no host sync). A loop `advance; stage(k + 1); correlate(k)` overlaps the
+ * PCIe transfer of pair k + 1 with the solve of pair k -- the same overlap the reference gets from
+ * resetNextPyramid on its loader thread (manager_class.cpp:1438-1447), for both images. */
+int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols);
+int dic_advance_pair(dic_engine *e);
 /* ---- CudaClass::makeUndPyramidFromDef / makeDefPyramidFromNxt (cuda_class.cu:607-613):
  *      pointer rotation, no copy */
 int dic_make_und_pyramid_from_def(dic_engine *e);

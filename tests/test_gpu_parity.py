@@ -530,3 +530,33 @@ def test_deformed_points_read_back(eng, golden):
     want_x = und_xy[:, 0] + p[0] + p[2] * dx + p[3] * dy   # model_class.cpp:171-172, fp32 left to right
     want_y = und_xy[:, 1] + p[1] + p[4] * dx + p[5] * dy
     assert np.array_equal(def_xy[:, 0], want_x.astype(np.float32)) and np.array_equal(def_xy[:, 1], want_y.astype(np.float32))
+
+
+def test_staged_pairs_double_buffer_equals_direct_upload(eng, golden):
+    """dic_stage_next_pair / dic_advance_pair: two different pairs alternate through the staging slots;
+    every correlate must equal the one after a plain resetImagePyramids of the same pair."""
+    import torch
+    und_a, def_a = golden["A/und"], golden["A/def"]
+    und_b, def_b = synth.make_pair(und_a.shape[0], und_a.shape[1], 77, (0.9, -1.1, 0.002, 0.001, -0.001, 0.003),
+                                   center=(95, 95))
+    x0, y0, x1, y1 = (int(v) for v in golden["A/rect"])
+    want = []
+    for u, d in ((und_a, def_a), (und_b, def_b)):
+        eng.resetImagePyramids(u, d, pyramid=(0, 1, 2))
+        eng.resetPolygon(0, x0, y0, x1, y1)
+        want.append(eng.correlate(0, np.zeros(6, np.float32)))
+    pins = [[torch.from_numpy(np.ascontiguousarray(im)).pin_memory() for im in pr]
+            for pr in ((und_a, def_a), (und_b, def_b))]
+    rows, cols = und_a.shape
+    eng.stageNextPair(pins[0][0].data_ptr(), pins[0][1].data_ptr(), rows, cols)
+    for k in range(5):
+        eng.advancePair()
+        nxt = pins[(k + 1) % 2]
+        eng.stageNextPair(nxt[0].data_ptr(), nxt[1].data_ptr(), rows, cols)
+        got = eng.correlate(0, np.zeros(6, np.float32))
+        w = want[k % 2]
+        assert np.array_equal(got["params"], w["params"]) and got["chi"] == w["chi"], (k, got, w)
+        assert got["iterations"] == w["iterations"]
+    with pytest.raises(engine.DicError):
+        eng.advancePair()
+        eng.advancePair()  # nothing staged any more
