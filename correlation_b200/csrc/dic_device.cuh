@@ -199,27 +199,6 @@ __device__ __forceinline__ void bicubic_parity(const float p[4][4], float xdef, 
   bicubic_parity_rows(cx[0], cx[1], cx[2], cx[3], xdef, ydef, ix, iy, w, wx, wy);
 }
 
-// x-direction cubic of one image row on [e, e+1) from pixels q[0..3] = p[e-1 .. e+2].
-//  PARITY: the reference's monomial coefficients in s = 1 + t (= hermite_to_monomial of the row),
-//          written with differences; every intermediate is a small multiple of 1/2: exact in fp32.
-//  FAST:   Catmull-Rom coefficients in t (well conditioned).
-template <int MODE>
-__device__ __forceinline__ void row_coeffs(const float *q, float c[4]) {
-  const float p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
-  if (MODE == DIC_MODE_PARITY) {
-    const float a = p1 - p2, b = p3 - p0, d = p1 - p0;
-    c[3] = 0.5f * b + 1.5f * a;
-    c[0] = p0 - b - 3.f * a;
-    c[1] = 2.5f * b + 8.f * a + 1.5f * d;
-    c[2] = -2.f * b - 6.5f * a - 0.5f * d;
-  } else {
-    c[0] = p1;
-    c[1] = 0.5f * (p2 - p0);
-    c[2] = p0 - 2.5f * p1 + 2.f * p2 - 0.5f * p3;
-    c[3] = 0.5f * (p3 - p0) + 1.5f * (p1 - p2);
-  }
-}
-
 // Fast mode on row coefficients: value and x-derivative of each row by Horner, then Catmull-Rom
 // weights in y.
 __device__ __forceinline__ void cr_weights(float t, float w[4], float d[4]);

@@ -5,6 +5,7 @@
 // here: three image pyramids (und / def / nxt, rotated by index like pyramid_class.cpp:211-258),
 // per-sector pixel lists for every used pyramid level, and a few hundred bytes of LM state.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -53,6 +54,8 @@ struct PyramidSlot {
   uint8_t *base = nullptr;
   size_t cap = 0;
   LevelImage lev[kMaxLevels] = {};
+  // TMA descriptors of every level for the two box shapes the tile kernel stages
+  CUtensorMap tm_patch[kMaxLevels], tm_tile[kMaxLevels];
   int rows = 0, cols = 0;
   bool valid = false;
 };
@@ -139,6 +142,37 @@ PyrWeights pyramid_weights() {
   return w;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// u8 image, box_w x box_h bytes, no swizzle, out-of-image elements read as 0
+int encode_level_map(dic_engine *e, CUtensorMap *map, const LevelImage &li, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error(e, "cuTensorMapEncodeTiled is not available from this driver"); return DIC_ERROR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)li.cols, (cuuint64_t)li.rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)li.pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(li.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error(e, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return DIC_ERROR_CUDA; }
+  return DIC_OK;
+}
+
 // (Re)shape a pyramid slot for rows x cols, levels 0..stop.
 int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
   size_t total = 0;
@@ -162,7 +196,17 @@ int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
     CU_TRY(e, cudaMalloc(&s.base, total));
     s.cap = total;
   }
-  for (int l = 0; l <= stop; ++l) { lev[l].ptr = s.base + off[l]; s.lev[l] = lev[l]; }
+  for (int l = 0; l <= stop; ++l) {
+    lev[l].ptr = s.base + off[l];
+    const bool same = s.lev[l].ptr == lev[l].ptr && s.lev[l].rows == lev[l].rows && s.lev[l].cols == lev[l].cols &&
+                      s.lev[l].pitch == lev[l].pitch;
+    s.lev[l] = lev[l];
+    if (!same && lev[l].rows > 0 && lev[l].cols > 0) {
+      int rc = encode_level_map(e, &s.tm_patch[l], lev[l], kPatchW, kPatchH);
+      if (!rc) rc = encode_level_map(e, &s.tm_tile[l], lev[l], kUndW, kTileH);
+      if (rc) return rc;
+    }
+  }
   for (int l = stop + 1; l < kMaxLevels; ++l) s.lev[l] = LevelImage{};
   s.rows = rows; s.cols = cols;
   return DIC_OK;
@@ -569,6 +613,9 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   const float *guesses = e->d_guess;
   dic_result *results = e->d_results;
   GridWork *work = e->d_work;
+  TileMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int l = 0; l <= e->stop; ++l) { maps.def[l] = d.tm_patch[l]; maps.und[l] = u.tm_tile[l]; }
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
   const size_t smem = tiles_dyn_smem(NACC);
   if (grid_mode) {
@@ -585,7 +632,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     int want = (int)std::min<long>((nt + kWarpsPerCta - 1) / kWarpsPerCta, (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
-    void *args[] = {&cfg, &sectors, &stiles, &guesses, &results, &first, &one, &work};
+    void *args[] = {&cfg, &maps, &sectors, &stiles, &guesses, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, smem, e->stream));
   } else {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, false>;
@@ -596,7 +643,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
       CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     }
     int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
-    kern<<<grid, kThreads, smem, e->stream>>>(cfg, sectors, stiles, guesses, results, first, count, work);
+    kern<<<grid, kThreads, smem, e->stream>>>(cfg, maps, sectors, stiles, guesses, results, first, count, work);
     CU_TRY(e, cudaGetLastError());
   }
   e->launches++;

@@ -16,6 +16,8 @@
 // The moments are expanded to the full upper-triangular A, b with the lane's dx powers only when
 // the warp changes strip or the evaluation ends.
 #pragma once
+#include <cuda.h>
+
 #include "dic_kernels.cuh"
 
 namespace dic {
@@ -24,8 +26,56 @@ namespace dic {
 #define DIC_TILE_CTAS_PER_SM 2
 #endif
 constexpr int kTileW = 32, kTileH = 16;
-constexpr int kPatchW = 48, kPatchH = 24; // 48 = 32 + halo 3 + strain margin + 8-byte alignment // fp32 staging of the deformed footprint, per warp
+// Per-warp staging, filled by TMA (cp.async.bulk.tensor.2d) one unit ahead of the arithmetic:
+//   the deformed-image footprint of a unit as u8, kPatchW x kPatchH bytes,
+//   the reference-image pixels of the unit's tile, kUndW x kTileH bytes.
+// The innermost TMA coordinate must be a multiple of 16 bytes (measured on B200: any other value
+// faults with "illegal instruction"), so both boxes start at x & ~15 and carry 15 spare columns:
+// 64 = 15 + 32 + 3 halo + 1 + 13 for strain / rotation across the unit; 48 = 15 + 32 + 1.
+// Two buffers of each per warp and one mbarrier per buffer.
+constexpr int kPatchW = 64, kPatchH = 24, kUndW = 48;
+constexpr int kPatchBytes = kPatchW * kPatchH, kUndBytes = kUndW * kTileH;
+constexpr int kStageBytes = kPatchBytes + kUndBytes;          // one buffer: 2304 B = 18 x 128
+constexpr int kWarpStageBytes = 2 * kStageBytes;              // per warp
 constexpr int kWarpsPerCta = kThreads / 32;
+static_assert(kStageBytes % 128 == 0 && kPatchBytes % 128 == 0, "TMA destinations must be 128-byte aligned");
+
+// Tensor maps of the pyramid levels the launch reads (kernel parameter, __grid_constant__).
+struct alignas(64) TileMaps {
+  CUtensorMap def[kMaxLevels]; // deformed image, box kPatchW x kPatchH
+  CUtensorMap und[kMaxLevels]; // reference image, box kUndW x kTileH
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded: a transfer that never lands must end the launch with an error, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  unsigned int spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// A warp's staging state: buffer k & 1 serves the k-th staged unit, its mbarrier phase is (k >> 1) & 1.
+struct WarpStage {
+  uint8_t *buf;   // [2][kStageBytes]: patch then und tile
+  uint64_t *bar;  // [2]
+  uint32_t issued, consumed;
+};
 
 struct Tile {
   int x0, y0;             // level coordinates of the tile's first pixel
@@ -186,32 +236,6 @@ __device__ __forceinline__ void flush_moments(float *mom, float X, float *warp_a
   for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
 }
 
-// ---- staging: u8 rows -> fp32 shared memory, 8 pixels per lane per step (one 64-bit load, eight
-// PRMT + FADD conversions, two 128-bit shared stores); 8 lanes per row, 4 rows per step. Pixels
-// outside the image are stored as 0; they are never used by an in-bounds sample.
-__device__ __forceinline__ void stage_rows(const LevelImage &img, int px0 /*multiple of 8*/, int py0,
-                                           int width8 /*8-pixel groups per row, <= 8*/, int height,
-                                           float *dst, int dst_pitch) {
-  const int lane = threadIdx.x & 31;
-  const int c8 = lane & 7, sub = lane >> 3;
-  const int x = px0 + 8 * c8;
-  const bool col_ok = c8 < width8 && x >= 0 && x < img.pitch - 7;
-  for (int r = sub; r < height; r += 4) {
-    const int y = py0 + r;
-    if (c8 < width8) {
-      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-      if (col_ok && y >= 0 && y < img.rows) {
-        uint2 v = __ldg(reinterpret_cast<const uint2 *>(img.ptr + (size_t)y * img.pitch + x));
-        f0 = make_float4(u8_to_float(v.x, 0), u8_to_float(v.x, 1), u8_to_float(v.x, 2), u8_to_float(v.x, 3));
-        f1 = make_float4(u8_to_float(v.y, 0), u8_to_float(v.y, 1), u8_to_float(v.y, 2), u8_to_float(v.y, 3));
-      }
-      float4 *d = reinterpret_cast<float4 *>(dst + r * dst_pitch + 8 * c8);
-      d[0] = f0;
-      d[1] = f1;
-    }
-  }
-}
-
 __device__ __forceinline__ float floor_magic(float x, int &i) {
   // floor for 0 <= x < 2^22 without the conversion pipe: round-down add of 2^23
   float m = __fadd_rd(x, 8388608.0f);
@@ -234,15 +258,49 @@ template <int NP> struct LaneWarp {
   }
 };
 
+// x-direction cubic of one window row from its four u8 pixels p0..p3 (columns ix-1 .. ix+2), packed in
+// `win`. PRMT builds 2^23 + p (exact); the bias cancels in every difference, so one FADD removes it
+// where the value itself is needed.
+//  PARITY: the reference's monomial coefficients in s = 1 + t (the row's part of a = (B (x) B) v,
+//          interpolation_class.cpp:296-336); every intermediate is a small multiple of 1/2: exact.
+//  FAST:   Catmull-Rom coefficients in t.
+template <int MODE>
+__device__ __forceinline__ void row_coeffs_u8(uint32_t win, float c[4]) {
+  const float f0 = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7650u));
+  const float f1 = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7651u));
+  const float f2 = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7652u));
+  const float f3 = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7653u));
+  if (MODE == DIC_MODE_PARITY) {
+    const float a = f1 - f2, b = f3 - f0, d = f1 - f0, p0 = f0 - 8388608.0f;
+    c[3] = 0.5f * b + 1.5f * a;
+    c[0] = p0 - b - 3.f * a;
+    c[1] = 2.5f * b + 8.f * a + 1.5f * d;
+    c[2] = -2.f * b - 6.5f * a - 0.5f * d;
+  } else {
+    const float d0 = f0 - f1, d2 = f2 - f1, d3 = f3 - f1;
+    c[0] = f1 - 8388608.0f;
+    c[1] = 0.5f * (d2 - d0);
+    c[2] = fmaf(-0.5f, d3, fmaf(2.f, d2, d0));
+    c[3] = fmaf(-1.5f, d2, 0.5f * (d3 - d0));
+  }
+}
+
+// four consecutive bytes at byte offset `o` of the warp's patch (any alignment)
+__device__ __forceinline__ uint32_t patch_window(const uint8_t *patch, int o) {
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(patch + (o & ~3));
+  return __funnelshift_r(w[0], w[1], (o & 3) * 8);
+}
+
 // One staged pixel. The lane walks down a column, so consecutive pixels normally share three of
 // their four window rows: the x-direction cubic coefficients of the window rows are kept in
 // registers (cw, slot-rotated by the static step S) and only the new bottom row is read from the
-// staged patch (4 LDS) and converted; a lane whose window moved differently (ix changed, iy did not
-// advance by exactly one, first row of a unit) rebuilds all four rows. `member` masks pixels outside
-// the domain (FULL: every pixel of the unit is a member).
+// staged patch (two LDS + funnel shift) and converted. When any lane's window moved differently
+// (ix changed, iy did not advance by exactly one, first row of a unit) the whole warp rebuilds its
+// four rows: the branch is warp-uniform. `member` masks pixels outside the domain (FULL: every pixel
+// of the unit is a member).
 template <int MODEL, int MODE, bool FULL, int S>
 __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<model_nparams(MODEL)> &lw,
-                                             float xf, float yf, float ccx, float ccy, const float *patch,
+                                             float xf, float yf, float ccx, float ccy, const uint8_t *patch,
                                              int px0, int py0, float und_w, bool member, float (&cw)[4][4],
                                              int &wix, int &wiy, float *mom) {
   constexpr int NP = model_nparams(MODEL);
@@ -257,14 +315,15 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
   }
   int ix, iy;
   const float fx = floor_magic(xd, ix), fy = floor_magic(yd, iy);
-  const float *q = patch + (iy - 1 - py0) * kPatchW + (ix - 1 - px0);
-  if (ix == wix && iy == wiy + 1) {
-    row_coeffs<MODE>(q + 3 * kPatchW, cw[(3 + S) & 3]);
+  const int o = (iy - 1 - py0) * kPatchW + (ix - 1 - px0); // byte offset of the window's first row
+  const bool slide = ix == wix && iy == wiy + 1;
+  if (__all_sync(0xffffffffu, slide)) {
+    row_coeffs_u8<MODE>(patch_window(patch, o + 3 * kPatchW), cw[(3 + S) & 3]);
   } else {
-    row_coeffs<MODE>(q, cw[(0 + S) & 3]);
-    row_coeffs<MODE>(q + kPatchW, cw[(1 + S) & 3]);
-    row_coeffs<MODE>(q + 2 * kPatchW, cw[(2 + S) & 3]);
-    row_coeffs<MODE>(q + 3 * kPatchW, cw[(3 + S) & 3]);
+    row_coeffs_u8<MODE>(patch_window(patch, o), cw[(0 + S) & 3]);
+    row_coeffs_u8<MODE>(patch_window(patch, o + kPatchW), cw[(1 + S) & 3]);
+    row_coeffs_u8<MODE>(patch_window(patch, o + 2 * kPatchW), cw[(2 + S) & 3]);
+    row_coeffs_u8<MODE>(patch_window(patch, o + 3 * kPatchW), cw[(3 + S) & 3]);
   }
   wix = ix; wiy = iy;
   float w, wx, wy;
@@ -277,19 +336,90 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
   accumulate_moments<NP>(mom, V, wx, wy, Y);
 }
 
-// ---- one evaluation over a range of work units of one level. A unit is `rpu` consecutive rows
-// of one tile (rpu = 16 >> split_log2): coarse levels and small subsets split their tiles so
-// that every resident warp has work; units keep the column-major strip order.
+// What a warp needs to know about a work unit before touching its pixels. A unit is `rpu` consecutive
+// rows of one tile (rpu = 16 >> split_log2).
+struct UnitPlan {
+  int x0, y0;       // level coordinates of the unit's first pixel
+  uint32_t colmask; // this lane's column of the membership mask: bit r <=> pixel (x0 + lane, y0 + r)
+  int px0, py0;     // origin of the staged deformed-image patch
+  bool full, empty, staged;
+};
+
+template <int NP>
+__device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int u, int split_log2, const float *p,
+                                              float ccx, float ccy, const LevelImage &def) {
+  const int lane = threadIdx.x & 31;
+  const int rpu = kTileH >> split_log2;
+  UnitPlan q;
+  const Tile *tp = tl.tiles + (u >> split_log2);
+  const int r0 = (u & ((1 << split_log2) - 1)) * rpu;
+  q.x0 = __ldg(&tp->x0); q.y0 = __ldg(&tp->y0) + r0;
+  const uint32_t unit_rows = ((1u << rpu) - 1u) << r0;
+  q.colmask = ((uint32_t)__ldg(&tp->cols[lane]) & unit_rows) >> r0;
+  q.full = (__ldg(&tp->full_rows) & unit_rows) == unit_rows;
+  q.empty = __all_sync(0xffffffffu, q.colmask == 0); // empty row chunk of a partial tile
+  // footprint of the unit under the current parameters: one corner per lane (lanes 0-3), min / max by
+  // shuffle, widened for the curvature of the quadratic model
+  float bx0, bx1, by0, by1;
+  {
+    const float Xc = ((lane & 1) ? (float)(q.x0 + kTileW - 1) : (float)q.x0) - ccx;
+    const float Yc = ((lane & 2) ? (float)(q.y0 + rpu - 1) : (float)q.y0) - ccy;
+    float xd = Xc + ccx + p[0] + p[2] * Xc + p[3] * Yc;
+    float yd = Yc + ccy + p[1] + p[4] * Xc + p[5] * Yc;
+    if (NP == 12) {
+      xd += 0.5f * p[6] * Xc * Xc + p[7] * Xc * Yc + 0.5f * p[8] * Yc * Yc;
+      yd += 0.5f * p[9] * Xc * Xc + p[10] * Xc * Yc + 0.5f * p[11] * Yc * Yc;
+    }
+    bx0 = bx1 = xd; by0 = by1 = yd;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+      by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    bx0 = __shfl_sync(0xffffffffu, bx0, 0); bx1 = __shfl_sync(0xffffffffu, bx1, 0);
+    by0 = __shfl_sync(0xffffffffu, by0, 0); by1 = __shfl_sync(0xffffffffu, by1, 0);
+    float slack = 0.01f;
+    if (NP == 12)
+      slack += 128.f * (fabsf(p[6]) + fabsf(p[9])) + 32.f * (fabsf(p[8]) + fabsf(p[11]));
+    bx0 -= slack; by0 -= slack; bx1 += slack; by1 += slack;
+  }
+  // staged window: columns [px0, px0 + kPatchW), rows [py0, py0 + kPatchH) must hold every 4 x 4 window
+  const bool inside = bx0 > 1.f && by0 > 1.f && bx1 < (float)def.cols - 2.f && by1 < (float)def.rows - 2.f;
+  q.px0 = ((int)floorf(bx0) - 1) & ~15; q.py0 = (int)floorf(by0) - 1;
+  const int pxe = (int)floorf(bx1) + 3, pye = (int)floorf(by1) + 3; // exclusive
+  q.staged = inside && pxe - q.px0 <= kPatchW && pye - q.py0 <= kPatchH;
+  return q;
+}
+
+// lane 0 starts the two bulk tensor copies of a planned unit into the warp's next staging buffer
+__device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, const CUtensorMap *map_def,
+                                           const CUtensorMap *map_und) {
+  if (!q.empty && q.staged) {
+    if ((threadIdx.x & 31) == 0) {
+      uint8_t *dst = st.buf + (st.issued & 1) * kStageBytes;
+      uint64_t *bar = st.bar + (st.issued & 1);
+      mbar_expect_tx(bar, kStageBytes);
+      tma_load_2d(dst, map_def, q.px0, q.py0, bar);
+      tma_load_2d(dst + kPatchBytes, map_und, q.x0 & ~15, q.y0, bar);
+    }
+    ++st.issued;
+  }
+}
+
+// ---- one evaluation over a range of work units of one level. Coarse levels and small subsets split
+// their tiles into row chunks so that every resident warp has work; units keep the column-major strip
+// order. The staging of unit u + 1 is in flight while unit u is being evaluated.
 template <int MODEL, int MODE>
-__device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const SectorDev *sec,
+__device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const TileMaps &maps, const SectorDev *sec,
                                                const TileLevel tl, int level, const float *p,
-                                               int unit_begin, int unit_end, int split_log2, float *patch,
+                                               int unit_begin, int unit_end, int split_log2, WarpStage &st,
                                                float *warp_acc, unsigned int *slow_counter) {
   constexpr int NP = model_nparams(MODEL);
   using M = Mom<NP>;
   const int lane = threadIdx.x & 31;
   const LevelImage und = cfg.und[level];
   const LevelImage def = cfg.def[level];
+  const CUtensorMap *map_def = &maps.def[level], *map_und = &maps.und[level];
   const float inv = 1.f / (float)(1 << level);
   const float ccx = sec->cx * inv, ccy = sec->cy * inv;
   const int rpu = kTileH >> split_log2;
@@ -310,15 +440,19 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
   LaneWarp<NP> lw;
   lw.set(p, 0.f, 0.f);
 
+  UnitPlan nxt;
+  if (unit_begin < unit_end) {
+    nxt = plan_unit<NP>(tl, unit_begin, split_log2, p, ccx, ccy, def);
+    issue_unit(st, nxt, map_def, map_und);
+  }
   for (int u = unit_begin; u < unit_end; ++u) {
-    const Tile *tp = tl.tiles + (u >> split_log2);
-    const int r0 = (u & ((1 << split_log2) - 1)) * rpu;
-    const int x0 = __ldg(&tp->x0), y0 = __ldg(&tp->y0) + r0;
-    // this lane's column of the membership mask: bit r <=> pixel (x0 + lane, y0 + r)
-    const uint32_t unit_rows = ((1u << rpu) - 1u) << r0;
-    const uint32_t colmask = ((uint32_t)__ldg(&tp->cols[lane]) & unit_rows) >> r0;
-    const bool unit_full = (__ldg(&tp->full_rows) & unit_rows) == unit_rows;
-    if (__all_sync(0xffffffffu, colmask == 0)) continue; // empty row chunk of a partial tile
+    const UnitPlan q = nxt;
+    if (u + 1 < unit_end) {
+      nxt = plan_unit<NP>(tl, u + 1, split_log2, p, ccx, ccy, def);
+      issue_unit(st, nxt, map_def, map_und);
+    }
+    if (q.empty) continue;
+    const int x0 = q.x0, y0 = q.y0;
     if (x0 != cur_x0) {
       if (cur_x0 != INT_MIN) flush_moments<NP>(mom, X, warp_acc);
       cur_x0 = x0;
@@ -326,51 +460,20 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
       X = __fsub_rn(xf, ccx);
       lw.set(p, xf, X);
     }
-    // footprint of the unit under the current parameters: one corner per lane (lanes 0-3), min / max
-    // by shuffle, widened for the curvature of the quadratic model
-    float bx0, bx1, by0, by1;
-    {
-      const float Xc = ((lane & 1) ? (float)(x0 + kTileW - 1) : (float)x0) - ccx;
-      const float Yc = ((lane & 2) ? (float)(y0 + rpu - 1) : (float)y0) - ccy;
-      float xd = Xc + ccx + p[0] + p[2] * Xc + p[3] * Yc;
-      float yd = Yc + ccy + p[1] + p[4] * Xc + p[5] * Yc;
-      if (NP == 12) {
-        xd += 0.5f * p[6] * Xc * Xc + p[7] * Xc * Yc + 0.5f * p[8] * Yc * Yc;
-        yd += 0.5f * p[9] * Xc * Xc + p[10] * Xc * Yc + 0.5f * p[11] * Yc * Yc;
-      }
-      bx0 = bx1 = xd; by0 = by1 = yd;
-#pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
-        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-      }
-      bx0 = __shfl_sync(0xffffffffu, bx0, 0); bx1 = __shfl_sync(0xffffffffu, bx1, 0);
-      by0 = __shfl_sync(0xffffffffu, by0, 0); by1 = __shfl_sync(0xffffffffu, by1, 0);
-      float slack = 0.01f;
-      if (NP == 12)
-        slack += 128.f * (fabsf(p[6]) + fabsf(p[9])) + 32.f * (fabsf(p[8]) + fabsf(p[11]));
-      bx0 -= slack; by0 -= slack; bx1 += slack; by1 += slack;
-    }
-    // staged window: columns [px0, px0 + 4*w4), rows [py0, py0 + h)
-    const int px0 = ((int)floorf(bx0) - 1) & ~7, py0 = (int)floorf(by0) - 1;
-    const int pxe = (int)floorf(bx1) + 3, pye = (int)floorf(by1) + 3; // exclusive
-    const int w8 = (pxe - px0 + 7) >> 3, h = pye - py0;
-    const bool inside = bx0 > 1.f && by0 > 1.f && bx1 < (float)def.cols - 2.f && by1 < (float)def.rows - 2.f;
-    const bool staged = inside && w8 * 8 <= kPatchW && h <= kPatchH && w8 > 0 && h > 0;
-    __syncwarp();
-    if (staged) stage_rows(def, px0, py0, w8, h, patch, kPatchW);
-    __syncwarp();
-    // reference-image pixels of this lane's column: one coalesced byte per warp-row
-    const uint8_t *ucol = und.ptr + (size_t)y0 * und.pitch + x0 + lane;
-
-    if (staged) {
+    const uint32_t colmask = q.colmask;
+    if (q.staged) {
+      const uint8_t *patch = st.buf + (st.consumed & 1) * kStageBytes;
+      const uint8_t *ucol = patch + kPatchBytes + (x0 & 15) + lane; // reference pixels of this lane's column
+      mbar_wait(st.bar + (st.consumed & 1), (st.consumed >> 1) & 1);
+      ++st.consumed;
+      const int px0 = q.px0, py0 = q.py0;
       float cw[4][4];
       int wix = INT_MIN, wiy = INT_MIN; // no window yet: the first row rebuilds all four
-#define DIC_STEP(FULLV, SV, R)                                                                            \
-  staged_pixel<MODEL, MODE, FULLV, SV>(pw, lw, xf, (float)(y0 + (R)), ccx, ccy, patch, px0, py0,           \
-                                       (float)__ldg(ucol + (size_t)min((R), und.rows - 1 - y0) * und.pitch), \
-                                       FULLV || ((colmask >> (R)) & 1u) != 0, cw, wix, wiy, mom)
-      if (unit_full) {
+#define DIC_STEP(FULLV, SV, R)                                                                       \
+  staged_pixel<MODEL, MODE, FULLV, SV>(pw, lw, xf, (float)(y0 + (R)), ccx, ccy, patch, px0, py0,      \
+                                       (float)ucol[(R) * kUndW], FULLV || ((colmask >> (R)) & 1u) != 0, \
+                                       cw, wix, wiy, mom)
+      if (q.full) {
 #pragma unroll 1
         for (int r = 0; r < rpu; r += 4) { DIC_STEP(true, 0, r); DIC_STEP(true, 1, r + 1); DIC_STEP(true, 2, r + 2); DIC_STEP(true, 3, r + 3); }
       } else {
@@ -378,10 +481,12 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const S
         for (int r = 0; r < rpu; r += 4) { DIC_STEP(false, 0, r); DIC_STEP(false, 1, r + 1); DIC_STEP(false, 2, r + 2); DIC_STEP(false, 3, r + 3); }
       }
 #undef DIC_STEP
+      __syncwarp(); // every lane is done with this buffer before lane 0 hands it to the next copy
     } else {
       if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
       // footprint leaves the image or the staging buffer: per-pixel path with the reference's
       // own bounds test (error 2 + zero contribution, interpolation_class.cpp:129-137)
+      const uint8_t *ucol = und.ptr + (size_t)y0 * und.pitch + x0 + lane;
 #pragma unroll 1
       for (int r = 0; r < rpu; ++r) {
         if (!((colmask >> r) & 1u)) continue;
@@ -431,18 +536,30 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, const 
 // ---- the solve kernel on tiles (same LM / barrier / solve machinery as gn_solve_kernel)
 template <int MODEL, int MODE, bool GRID>
 __global__ void __launch_bounds__(kThreads, DIC_TILE_CTAS_PER_SM)
-gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
-                      const SectorTiles *__restrict__ sector_tiles, const float *__restrict__ guesses,
-                      dic_result *__restrict__ results, int first_sector, int n_sectors, GridWork *work) {
+gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps maps,
+                      const SectorDev *__restrict__ sectors, const SectorTiles *__restrict__ sector_tiles,
+                      const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
+                      int n_sectors, GridWork *work) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
-  extern __shared__ __align__(16) float dyn_smem[];
-  float *s_patch = dyn_smem;                                          // [warps][kPatchH*kPatchW]
-  float *s_wacc = s_patch + kWarpsPerCta * kPatchH * kPatchW;        // [warps][NACC]
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  uint8_t *s_stage = dyn_smem;                                                    // [warps][kWarpStageBytes]
+  float *s_wacc = reinterpret_cast<float *>(dyn_smem + kWarpsPerCta * kWarpStageBytes); // [warps][NACC]
   __shared__ SolveShared<NP> sh;
+  __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float *patch = s_patch + warp * kPatchH * kPatchW;
   float *warp_acc = s_wacc + warp * NACC;
+  WarpStage st;
+  st.buf = s_stage + warp * kWarpStageBytes;
+  st.bar = s_bar[warp];
+  st.issued = st.consumed = 0;
+  if (lane == 0) {
+    mbar_init(&st.bar[0], 1);
+    mbar_init(&st.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
 
   for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
     const SectorDev *sec = sectors + first_sector + si;
@@ -475,7 +592,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
         // balanced contiguous ranges: the first (n_units % nw) warps take one unit more
         const int base = n_units / nw, rem = n_units - base * nw;
         const int ub = wg * base + min(wg, rem), ue = ub + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE>(cfg, sec, tl, level, sh.p, ub, ue, split_log2, patch, warp_acc,
+        evaluate_tiles<MODEL, MODE>(cfg, maps, sec, tl, level, sh.p, ub, ue, split_log2, st, warp_acc,
                                     GRID ? &work->slow_units : nullptr);
         if (tl.n_extra > 0 && wg == 0) evaluate_extras<MODEL, MODE>(cfg, sec, tl, level, sh.p, warp_acc);
       }
@@ -495,7 +612,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sec
 }
 
 constexpr size_t tiles_dyn_smem(int nacc) {
-  return sizeof(float) * (size_t)kWarpsPerCta * (kPatchH * kPatchW + nacc);
+  return (size_t)kWarpsPerCta * kWarpStageBytes + sizeof(float) * (size_t)kWarpsPerCta * nacc;
 }
 
 // ------------------------------------------------------------------ tile construction
