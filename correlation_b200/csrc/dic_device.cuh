@@ -19,6 +19,7 @@ constexpr int kMaxParams = DIC_MAX_PARAMS;
 constexpr int kThreads = 256; // threads per CTA of the GN kernels
 constexpr int kMaxMarks = 128;
 constexpr int kMaxRanks = 8;
+constexpr int kMaxCtaMarks = 1024;
 
 // ------------------------------------------------------------------ descriptors
 
@@ -56,16 +57,18 @@ struct Mailbox {
   unsigned int seq[2][kMaxRanks]; // written last (release): evaluation number + 1
 };
 
-// Grid-wide reduction / barrier scratch (grid mode). CTA 0 is the master: it owns the LM state in
-// its shared memory and publishes only the next command (parameters, level, done).
+// Grid-wide reduction / barrier scratch (grid mode). Every evaluation ends with an all-reduce: each CTA
+// adds its sums to acc[e % 3] with fp64 atomics and bumps `arrive` (release); every CTA then waits for
+// the count, reads the same totals and runs the SAME LM step + solve on its own copy of the state in
+// shared memory -- bitwise identical decisions everywhere, no master, no publish / re-read hop.
+// The host zeroes `arrive` and `acc` before each launch; CTA 0 clears acc[(e + 2) % 3] after barrier e.
 struct GridWork {
-  unsigned int arrive;     // worker CTAs that have delivered their partial sums
-  unsigned int generation; // bumped by the master after every LM step
+  unsigned int arrive;     // CTAs that have delivered their sums, cumulative over the launch
+  unsigned int generation; // row-split only: bumped by CTA 0 after it has published the cross-GPU totals
   int abort;               // set when a grid-barrier wait timed out (never expected)
   unsigned int slow_units; // units of the last launch that took the per-pixel (non-staged) path
-  float pub_p[kMaxParams];
-  int pub_level, pub_done;
-  double acc[96]; // grid-wide sums of the current evaluation (fp64 atomics), zeroed by the master
+  float pub_tot[96];       // row-split only: totals over all GPUs, published by CTA 0
+  double acc[3][96];       // grid-wide sums of evaluations e % 3 (fp64 atomics)
   // row-split of one domain over several GPUs: every rank's master adds its sums to
   // every peer's mailbox over NVLink, then all ranks add the rows in rank order (bitwise identical)
   int rs_rank, rs_world;
@@ -73,10 +76,11 @@ struct GridWork {
   int rs_error;                    // set when a peer did not answer in time
   struct Mailbox *rs_local;        // this rank's mailbox (peers write into it)
   struct Mailbox *rs_peer[kMaxRanks]; // peer-mapped mailboxes, index = rank
-  // master-side timeline of the last launch (ns, %globaltimer): per evaluation
-  // [0] pass started, [1] own pass done, [2] all workers arrived, [3] LM step published
+  // CTA 0's timeline of the last launch (ns, %globaltimer): per evaluation
+  // [0] pass started, [1] own pass done, [2] all CTAs arrived, [3] LM step done
   int n_marks;
   unsigned long long marks[kMaxMarks][4];
+  unsigned long long cta_done[kMaxCtaMarks]; // per CTA: when its pass of the LAST evaluation ended (load-balance probe)
 };
 
 struct SolveSettings {

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -584,6 +585,7 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
     int want = (int)std::min<long>((n0 + kThreads * 4 - 1) / (kThreads * 4), (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
+    CU_TRY(e, cudaMemsetAsync(work, 0, offsetof(GridWork, rs_rank), e->stream)); // arrive, abort, acc
     void *args[] = {&cfg, &sectors, &guesses, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, 0, e->stream));
   } else {
@@ -632,6 +634,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     int want = (int)std::min<long>((nt + kWarpsPerCta - 1) / kWarpsPerCta, (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
+    CU_TRY(e, cudaMemsetAsync(work, 0, offsetof(GridWork, rs_rank), e->stream)); // arrive, abort, acc
     void *args[] = {&cfg, &maps, &sectors, &stiles, &guesses, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, smem, e->stream));
   } else {
@@ -1411,15 +1414,7 @@ static int collect(dic_engine *e, int first, int count, float *guesses_out, dic_
   int worst = DIC_OK;
   bool aborted = false;
   for (int i = 0; i < count; ++i) aborted = aborted || e->h_results[first + i].errorCode == DIC_ERROR_CUDA;
-  if (aborted) { // a grid-barrier wait timed out: bring the barrier scratch back to a clean state
-    GridWork w;
-    if (cudaMemcpy(&w, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      w.arrive = 0; w.abort = 0;
-      for (double &a : w.acc) a = 0.0;
-      cudaMemcpy(e->d_work, &w, sizeof(GridWork), cudaMemcpyHostToDevice);
-    }
-    set_error(e, "a grid-barrier wait inside gn_solve timed out (10 s)");
-  }
+  if (aborted) set_error(e, "a grid-barrier wait inside gn_solve timed out (10 s)"); // scratch is re-zeroed per launch
   for (int i = 0; i < count; ++i) {
     const dic_result &r = e->h_results[first + i];
     e->sectors[first + i].pending = false;
@@ -1629,6 +1624,14 @@ int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap) {
   int n = std::min(std::min(h.n_marks, cap), kMaxMarks);
   memcpy(marks, h.marks, sizeof(unsigned long long) * 4 * n);
   if (n < cap) marks[4 * n] = h.slow_units; // one extra word: units that took the per-pixel path
+  return n;
+}
+int dic_get_cta_times(dic_engine *e, unsigned long long *out, int cap) {
+  if (!e || !out) return 0;
+  cudaSetDevice(e->device);
+  int n = std::min(cap, kMaxCtaMarks);
+  if (cudaMemcpy(out, (const char *)e->d_work + offsetof(GridWork, cta_done), sizeof(unsigned long long) * n,
+                 cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return n;
 }
 float dic_last_correlate_ms(dic_engine *e) { return e ? e->last_ms : 0.f; }

@@ -42,7 +42,7 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
 // one element per lane.
 template <int MODEL>
 __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
-                        const SectorDev *sec, dic_result *result, float *smem) {
+                        const SectorDev *sec, dic_result *result, float *smem, bool writer = true) {
   constexpr int NP = model_nparams(MODEL);
   using L = Acc<NP>;
   const int lane = threadIdx.x & 31;
@@ -169,7 +169,7 @@ __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
   if (act) {
     s->p[li] = e_p; s->mp[li] = e_mp; s->last_good[li] = e_lg;
     s->tentative[li] = e_tent; s->saved[li] = e_saved;
-    if (finish) result->resultingParameters[li] = e_mp;
+    if (finish && writer) result->resultingParameters[li] = e_mp;
   }
   if (lane == 0) {
     s->evals[this_level] = evals;
@@ -180,7 +180,7 @@ __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
     s->error_code = error_code; s->reached_iterations = reached;
     s->lambda = lambda; s->last_good_chi = last_good_chi; s->scaling = scaling;
     s->done = finish ? 1 : 0;
-    if (finish) {
+    if (finish && writer) {
       for (int i = NP; i < kMaxParams; ++i) result->resultingParameters[i] = 0.f;
       result->chi = last_good_chi;
       result->numberOfPoints = sec->n_total[0];
@@ -308,17 +308,18 @@ template <int NP> struct SolveShared {
   float p[kMaxParams];
   int level, done;
   int rowsplit;  // this launch exchanges its sums with other GPUs (read once per sector, not per evaluation)
-  int mark;      // next slot of the master's timeline
+  int mark;      // next slot of CTA 0's timeline
   int timed_out; // a bounded wait expired
+  unsigned int arrive_target; // value of GridWork::arrive that completes the current evaluation
+  unsigned int rs_gen;        // row-split: GridWork::generation before CTA 0's next publication
   LMState state;
 };
 
 // After one evaluation pass: sh.tot holds this CTA's sums. Produces the next command in
 // sh.p / sh.level / sh.done for every CTA.
-//   GRID: CTA 0 is the master. Workers that took part (`active`) add their sums to work->acc with
-//   fp64 atomics and bump `arrive` with a release RMW; the master waits for n_active - 1
-//   arrivals, adds its own sums, runs the LM step + solve in its warp 0
-//   with the state in ITS shared memory, publishes the command and releases `generation`.
+//   GRID: all-reduce through GridWork (see there), then every CTA's warp 0 runs the LM step + solve
+//   on its own state; CTA 0 alone writes the result record and the timeline. With a row-split over
+//   GPUs, CTA 0 additionally exchanges the totals with the peers and publishes them to the others.
 //   Batch: the CTA owns the sector; only __syncthreads is needed.
 template <int MODEL, bool GRID>
 __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)> &sh, bool active,
@@ -327,77 +328,76 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
                                                 GridWork *work, unsigned int &my_gen) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
-  constexpr int kW = kThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (GRID) {
-    if (blockIdx.x != 0) {
-      if (active) {
-        if (tid < NACC) atomicAdd(&work->acc[tid], (double)sh.tot[tid]);
-        __syncthreads();
-        // release RMW by one thread after the CTA barrier: cumulative over the other threads' atomics
-        if (tid == 0) red_release_add_u32(&work->arrive, 1u);
-      }
-      if (tid == 0) {
-        // bounded wait: a lost master must never hang the GPU (the launch then ends with error_cuda)
-        const unsigned long long t0 = global_ns();
-        unsigned int spins = 0;
-        sh.level = -1;
-        while (ld_acquire_u32(&work->generation) == my_gen) {
-          __nanosleep(64);
-          if ((++spins & 0xfffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) { sh.level = -2; break; }
+    const bool lead = blockIdx.x == 0;
+    double *acc = work->acc[my_gen % 3u];
+    if (active && tid < NACC) atomicAdd(&acc[tid], (double)sh.tot[tid]);
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned long long t0 = global_ns();
+      const int m = sh.mark;
+      if (lead && m < kMaxMarks) work->marks[m][1] = t0;
+      if (blockIdx.x < kMaxCtaMarks) work->cta_done[blockIdx.x] = t0;
+      // release RMW by one thread after the CTA barrier: cumulative over the other threads' atomics
+      // (and over their reads of the previous evaluation's totals)
+      red_release_add_u32(&work->arrive, 1u);
+      const unsigned int target = sh.arrive_target + gridDim.x;
+      sh.arrive_target = target;
+      // bounded wait: a lost CTA must never hang the GPU (the launch then ends with error_cuda)
+      unsigned int spins = 0;
+      while ((int)(ld_acquire_u32(&work->arrive) - target) < 0) {
+        if ((++spins & 0xffffu) == 0 && (global_ns() - t0 > kSpinTimeoutNs || *(volatile int *)&work->abort)) {
+          atomicExch(&work->abort, 1); sh.timed_out = 1; break;
         }
       }
-      __syncthreads();
-      if (sh.level == -2) { // timed out: leave the loop, the host sees the unfinished result record
-        if (tid == 0) { sh.done = 1; atomicExch(&work->abort, 1); }
+      if (lead && m < kMaxMarks) work->marks[m][2] = global_ns();
+    }
+    __syncthreads();
+    // order-independent to well below fp32 ulp; every CTA reads the same bits
+    if (tid < NACC) sh.tot[tid] = (float)__ldcg(&acc[tid]);
+    if (lead && tid < NACC) __stcg(&work->acc[(my_gen + 2u) % 3u][tid], 0.0);
+    __syncthreads();
+    if (sh.rowsplit) {
+      if (lead) {
+        if (warp == 0) {
+          rowsplit_allreduce<NACC>(work, sh.tot);
+          for (int k = lane; k < NACC; k += 32) __stcg(&work->pub_tot[k], sh.tot[k]);
+          __syncwarp(); // the other lanes' stores happen-before lane 0's release (cumulativity)
+          if (lane == 0) st_release_u32(&work->generation, sh.rs_gen + 1);
+        }
       } else {
-        if (tid < NP) sh.p[tid] = __ldcg(&work->pub_p[tid]);
-        if (tid == 0) { sh.level = __ldcg(&work->pub_level); sh.done = __ldcg(&work->pub_done); }
-      }
-    } else {
-      if (tid == 0) {
-        const int m = sh.mark;
-        const unsigned long long t0 = global_ns();
-        if (m < kMaxMarks) work->marks[m][1] = t0;
-        unsigned int spins = 0;
-        while (ld_acquire_u32(&work->arrive) < (unsigned int)(n_active - 1)) {
-          if ((++spins & 0xffffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) { atomicExch(&work->abort, 1); sh.timed_out = 1; break; }
+        if (tid == 0) {
+          const unsigned long long t0 = global_ns();
+          unsigned int spins = 0;
+          while (ld_acquire_u32(&work->generation) == sh.rs_gen) {
+            __nanosleep(64);
+            if ((++spins & 0xfffu) == 0 && (global_ns() - t0 > 2 * kSpinTimeoutNs + 20000000000ull)) { sh.timed_out = 1; break; }
+          }
         }
-        if (m < kMaxMarks) work->marks[m][2] = global_ns();
-      }
-      __syncthreads();
-      if (tid < NACC) {
-        // workers' sums arrive through fp64 atomics (order-independent to well below fp32 ulp)
-        double s = (double)sh.tot[tid] + __ldcg(&work->acc[tid]);
-        __stcg(&work->acc[tid], 0.0);
-        sh.tot[tid] = (float)s;
-      }
-      __syncthreads();
-      if (sh.rowsplit) {
-        if (warp == 0) rowsplit_allreduce<NACC>(work, sh.tot);
         __syncthreads();
+        if (tid < NACC) sh.tot[tid] = __ldcg(&work->pub_tot[tid]);
       }
-      if (warp == 0) {
-        lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
-        if (sh.rowsplit && work->rs_error && lane == 0) {
-          sh.state.done = 1; result->errorCode = DIC_ERROR_MULTITHREAD; // a peer never answered
-        }
-        if (lane == 0 && sh.timed_out) { // a worker never arrived
-          sh.state.done = 1; result->errorCode = DIC_ERROR_CUDA;
-        }
-        if (lane < NP) { float v = sh.state.p[lane]; sh.p[lane] = v; __stcg(&work->pub_p[lane], v); }
-        if (lane == 0) {
-          sh.level = sh.state.level; sh.done = sh.state.done;
-          __stcg(&work->pub_level, sh.state.level); __stcg(&work->pub_done, sh.state.done);
-          __stcg(&work->arrive, 0u);
+      if (tid == 0) sh.rs_gen += 1;
+      __syncthreads();
+    }
+    if (warp == 0) {
+      lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve, lead);
+      if (lane == 0) {
+        if (sh.rowsplit && work->rs_error) { sh.state.done = 1; if (lead) result->errorCode = DIC_ERROR_MULTITHREAD; } // a peer never answered
+        if (sh.timed_out) { sh.state.done = 1; if (lead) result->errorCode = DIC_ERROR_CUDA; } // a CTA never arrived
+      }
+      __syncwarp();
+      if (lane < NP) sh.p[lane] = sh.state.p[lane];
+      if (lane == 0) {
+        sh.level = sh.state.level; sh.done = sh.state.done;
+        if (lead) {
           const int m = sh.mark;
           const unsigned long long t3 = global_ns();
           if (m < kMaxMarks) { work->marks[m][3] = t3; work->n_marks = m + 1; }
           if (m + 1 < kMaxMarks) work->marks[m + 1][0] = t3;
           sh.mark = m + 1;
         }
-        __syncwarp(); // the other lanes' stores happen-before lane 0's release (cumulativity)
-        if (lane == 0) st_release_u32(&work->generation, my_gen + 1);
       }
     }
     ++my_gen;
@@ -420,15 +420,17 @@ __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &
                                              unsigned int &my_gen) {
   constexpr int NP = model_nparams(MODEL);
   const int tid = threadIdx.x, warp = tid >> 5;
-  __shared__ unsigned int s_gen;
-  if (GRID && tid == 0) s_gen = ld_acquire_u32(&work->generation);
-  if ((!GRID || blockIdx.x == 0) && warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, guess);
-  if (tid == 0) { sh.rowsplit = GRID && work->rs_local != nullptr; sh.mark = 0; sh.timed_out = 0; }
+  if (warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, guess); // grid mode: every CTA keeps its own copy
+  if (tid == 0) {
+    sh.rowsplit = GRID && work->rs_local != nullptr;
+    sh.rs_gen = sh.rowsplit ? ld_acquire_u32(&work->generation) : 0u;
+    sh.mark = 0; sh.timed_out = 0; sh.arrive_target = 0;
+  }
   if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->slow_units = 0; work->marks[0][0] = global_ns(); }
   if (tid < NP) sh.p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
   if (tid == 0) { sh.level = cfg.stop; sh.done = 0; }
   __syncthreads();
-  my_gen = GRID ? s_gen : 0u;
+  my_gen = 0u; // evaluations done by this launch
 }
 
 // GRID = true : every CTA of a cooperative launch works on ONE sector (large domains).

@@ -72,7 +72,7 @@ EXPORTS = [
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
-    "dic_last_correlate_ms", "dic_get_timeline", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
+    "dic_last_correlate_ms", "dic_get_timeline", "dic_get_cta_times", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
 ]
 
 
@@ -132,6 +132,7 @@ def load_library():
         "dic_solve_step": (I, [P, P, P, F, F, P]),
         "dic_last_correlate_ms": (F, [P]),
         "dic_get_timeline": (I, [P, P, I]),
+        "dic_get_cta_times": (I, [P, P, I]),
         "dic_kernel_launches": (I64, [P]),
         "dic_correlation_stream": (P, [P]),
         "dic_synchronize": (I, [P]),
@@ -408,6 +409,11 @@ class CudaEngine:
         n = self.lib.dic_get_timeline(self.h, _ptr(m), 129)
         self.slow_units = int(m[n, 0]) if n < 129 else -1
         return m[:n].astype(np.int64)
+
+    def cta_times(self, n=296):
+        m = np.zeros(n, np.uint64)
+        k = self.lib.dic_get_cta_times(self.h, _ptr(m), n)
+        return m[:k].astype(np.int64)
 
     def kernel_launches(self):
         return int(self.lib.dic_kernel_launches(self.h))

@@ -214,6 +214,9 @@ float dic_last_correlate_ms(dic_engine *e);
 /* master-CTA timeline of the last single-sector correlate: per evaluation 4 device timestamps (ns):
  * pass start, own pass done, all CTAs arrived, LM step published. Returns the evaluation count. */
 int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap);
+/* load-balance probe: per CTA of the last single-sector correlate, the device time (ns) at which its
+ * pass of the last evaluation ended. Returns the number of entries written (<= cap, <= 1024). */
+int dic_get_cta_times(dic_engine *e, unsigned long long *out, int cap);
 int64_t dic_kernel_launches(const dic_engine *e);
 /* the CUDA stream handle (cudaStream_t as void*) the GN kernels run on, for event timing */
 void *dic_correlation_stream(dic_engine *e);

@@ -20,3 +20,10 @@ print(f"{name} mode={mode} total {eng.last_correlate_ms():.3f} ms, evals {r['eva
 print("  eval:  own-pass  wait-others  sum+LM   (us)   since start")
 for i, m in enumerate(t):
     print(f"  {i:3d}  {(m[1]-m[0])/1e3:8.1f} {(m[2]-m[1])/1e3:8.1f} {(m[3]-m[2])/1e3:8.1f}   {(m[3]-t[0][0])/1e3:8.1f}")
+ct = eng.cta_times(296)
+ct = (ct - t[-1][0]) / 1e3  # us since the start of the last pass
+ct = ct[ct > 0]
+print("last pass: per-CTA end times (us): n", len(ct), "min %.1f p10 %.1f median %.1f p90 %.1f max %.1f" % (ct.min(), np.percentile(ct, 10), np.median(ct), np.percentile(ct, 90), ct.max()))
+print("  first 8 CTAs", np.round(ct[:8], 1), " last 8", np.round(ct[-8:], 1))
+order = np.argsort(ct)
+print("  slowest CTAs", order[-8:], np.round(ct[order[-8:]], 1))
