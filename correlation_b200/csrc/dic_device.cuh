@@ -135,6 +135,16 @@ __device__ __forceinline__ void hermite_to_monomial(float f1, float f2, float d1
   c[3] = 2.f * f1 - 2.f * f2 + d1 + d2;
 }
 
+// hermite_to_monomial(p1, p2, (p2 - p0) / 2, (p3 - p1) / 2) written with differences: 13 operations
+// instead of 20, identical results because every intermediate is exact (see above).
+__device__ __forceinline__ void monomial_from_samples(float p0, float p1, float p2, float p3, float c[4]) {
+  const float a = p1 - p2, b = p3 - p0, d = p1 - p0;
+  c[3] = 0.5f * b + 1.5f * a;
+  c[0] = p0 - b - 3.f * a;
+  c[1] = 2.5f * b + 8.f * a + 1.5f * d;
+  c[2] = -2.f * b - 6.5f * a - 0.5f * d;
+}
+
 // The 40 terms of interpolation_class.cpp:108-126 in the reference's order, unfused mul / add.
 // Exact shortcuts only: x * 1 is skipped, (2 a) * y == 2 (a * y) and acc + 2 t == fma(2, t, acc)
 // bit for bit (power-of-two scaling commutes with rounding), 3 a is exact (|a| < 2^20, quarter units).
@@ -185,7 +195,7 @@ __device__ __forceinline__ void bicubic_parity_rows(const float *r0, const float
 #pragma unroll
   for (int ik = 0; ik < 4; ++ik) {
     float c[4];
-    hermite_to_monomial(r1[ik], r2[ik], (r2[ik] - r0[ik]) * 0.5f, (r3[ik] - r1[ik]) * 0.5f, c);
+    monomial_from_samples(r0[ik], r1[ik], r2[ik], r3[ik], c);
 #pragma unroll
     for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
   }

@@ -473,13 +473,27 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   staged_pixel<MODEL, MODE, FULLV, SV>(pw, lw, xf, (float)(y0 + (R)), ccx, ccy, patch, px0, py0,      \
                                        (float)ucol[(R) * kUndW], FULLV || ((colmask >> (R)) & 1u) != 0, \
                                        cw, wix, wiy, mom)
-      if (q.full) {
+      // fast mode: four pixels per trip so that the window rotation is a static renaming of registers.
+      // parity mode: one pixel per trip and an explicit 12-register shift -- its per-pixel code is
+      // 2.4x longer and the unrolled body overflowed the instruction cache (10 % no-instruction stalls).
+#define DIC_SHIFT()                                                                                  \
+  _Pragma("unroll") for (int k_ = 0; k_ < 4; ++k_) { cw[0][k_] = cw[1][k_]; cw[1][k_] = cw[2][k_]; cw[2][k_] = cw[3][k_]; }
+      if (MODE == DIC_MODE_PARITY) {
+        if (q.full) {
+#pragma unroll 1
+          for (int r = 0; r < rpu; ++r) { DIC_STEP(true, 0, r); DIC_SHIFT(); }
+        } else {
+#pragma unroll 1
+          for (int r = 0; r < rpu; ++r) { DIC_STEP(false, 0, r); DIC_SHIFT(); }
+        }
+      } else if (q.full) {
 #pragma unroll 1
         for (int r = 0; r < rpu; r += 4) { DIC_STEP(true, 0, r); DIC_STEP(true, 1, r + 1); DIC_STEP(true, 2, r + 2); DIC_STEP(true, 3, r + 3); }
       } else {
 #pragma unroll 1
         for (int r = 0; r < rpu; r += 4) { DIC_STEP(false, 0, r); DIC_STEP(false, 1, r + 1); DIC_STEP(false, 2, r + 2); DIC_STEP(false, 3, r + 3); }
       }
+#undef DIC_SHIFT
 #undef DIC_STEP
       __syncwarp(); // every lane is done with this buffer before lane 0 hands it to the next copy
     } else {
