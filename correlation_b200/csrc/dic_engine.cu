@@ -221,7 +221,7 @@ int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st) {
     const LevelImage &dst = s.lev[l];
     if (dst.rows <= 0 || dst.cols <= 0) break;
     dim3 block(kPyrTX, kPyrTY);
-    dim3 grid((dst.cols + kPyrTX - 1) / kPyrTX, (dst.rows + kPyrTY - 1) / kPyrTY);
+    dim3 grid((dst.cols + kPyrTX - 1) / kPyrTX, (dst.rows + kPyrTY * kPyrK - 1) / (kPyrTY * kPyrK));
     pyramid_level_kernel<<<grid, block, 0, st>>>(src, const_cast<uint8_t *>(dst.ptr), dst.rows,
                                                  dst.cols, dst.pitch, kw);
     e->launches++;

@@ -527,23 +527,28 @@ __global__ void solve_step_kernel(const float *tot, float scaling, float lambda,
 
 // ------------------------------------------------------------------ pyramid
 
-// pyramid_class.cpp:52-134. One CTA = 32 x 8 target pixels. The (72 x 19) u8 source footprint is
-// staged ONCE into shared memory as fp32 (aligned 32-bit loads, PRMT + FADD conversion -- no I2F),
-// split into even / odd source columns so that the stride-2 taps of neighbouring lanes hit distinct
-// banks. Every target pixel then runs the reference's 25 sequential fp32 mul + add (dj outer, di
-// inner, no FMA contraction) and truncates to u8. Target border rows / columns are written as 0
-// (the reference leaves a zero-initialised border, :98-102). HBM-bound: 1.25 B per source pixel.
-constexpr int kPyrTX = 32, kPyrTY = 8;
+// pyramid_class.cpp:52-134. One CTA = 32 x 32 target pixels, one thread = 4 vertically adjacent
+// targets. The (72 x 67) u8 source footprint is staged ONCE into shared memory as fp32 (aligned 32-bit
+// loads, PRMT + FADD conversion -- no I2F), split into even / odd source columns so that the stride-2
+// taps of neighbouring lanes hit distinct banks. A thread walks down its 11 source rows, loads the
+// five taps of a row once and feeds every target whose 5 x 5 window contains that row: each target
+// still runs the reference's 25 sequential fp32 mul + add in the reference's order (dj outer, di
+// inner, no FMA contraction), the four chains are independent (ILP 4) and a tap is read from shared
+// memory 55 / 4 times per target instead of 25. Truncation to u8; target border rows / columns are
+// written as 0 (the reference leaves a zero-initialised border, :98-102).
+// HBM-bound by design (1.25 B per source pixel), FP32-issue bound in practice: 50 unfused ops per target.
+constexpr int kPyrTX = 32, kPyrTY = 8, kPyrK = 4; // threads x, threads y, targets per thread
 struct PyrWeights { float w[25]; };
 
 __global__ void __launch_bounds__(kPyrTX *kPyrTY)
 pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int dcols, int dpitch,
                      PyrWeights kw) {
-  constexpr int SWW = (2 * kPyrTX + 8) / 4, SH = 2 * kPyrTY + 3; // 18 words (72 px) x 19 rows
+  constexpr int TH = kPyrTY * kPyrK;                             // 32 target rows per CTA
+  constexpr int SWW = (2 * kPyrTX + 8) / 4, SH = 2 * TH + 3;     // 18 words (72 px) x 67 rows
   __shared__ float tE[SH][SWW * 2 + 1], tO[SH][SWW * 2 + 1];     // even / odd source columns
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int ox = blockIdx.x * kPyrTX, oy = blockIdx.y * kPyrTY; // target origin
-  const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;                 // staged window origin (x 4-aligned)
+  const int ox = blockIdx.x * kPyrTX, oy = blockIdx.y * TH;      // target origin
+  const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;                  // staged window origin (x 4-aligned)
   for (int idx = ty * kPyrTX + tx; idx < SH * SWW; idx += kPyrTX * kPyrTY) {
     const int r = idx / SWW, c4 = idx - r * SWW;
     const int sx = sx0 + 4 * c4, sy = sy0 + r;
@@ -555,24 +560,35 @@ pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int d
     tE[r][2 * c4 + 1] = u8_to_float(v, 2); tO[r][2 * c4 + 1] = u8_to_float(v, 3);
   }
   __syncthreads();
-  const int ti = ox + tx, tj = oy + ty;
-  if (ti >= dcols || tj >= drows) return;
-  uint8_t out = 0;
-  if (ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1) {
-    float addition = 0.f;
-    // source column of tap di: 2 ti - 2 + di = sx0 + (2 tx + 2 + di): even di -> tE[tx + 1 + di/2], odd -> tO[tx + 1 + (di-1)/2]
+  const int ti = ox + tx, tj0 = oy + ty * kPyrK;
+  if (ti >= dcols) return;
+  float acc[kPyrK];
 #pragma unroll
-    for (int dj = 0; dj < 5; ++dj) {
-      const float *rE = tE[2 * ty + dj] + tx + 1, *rO = tO[2 * ty + dj] + tx + 1;
-      addition = __fadd_rn(addition, __fmul_rn(rE[0], kw.w[dj * 5 + 0]));
-      addition = __fadd_rn(addition, __fmul_rn(rO[0], kw.w[dj * 5 + 1]));
-      addition = __fadd_rn(addition, __fmul_rn(rE[1], kw.w[dj * 5 + 2]));
-      addition = __fadd_rn(addition, __fmul_rn(rO[1], kw.w[dj * 5 + 3]));
-      addition = __fadd_rn(addition, __fmul_rn(rE[2], kw.w[dj * 5 + 4]));
+  for (int t = 0; t < kPyrK; ++t) acc[t] = 0.f;
+  // source column of tap di: 2 ti - 2 + di = sx0 + (2 tx + 2 + di): even di -> tE[tx + 1 + di/2], odd -> tO[tx + 1 + (di-1)/2]
+#pragma unroll
+  for (int r = 0; r < 2 * kPyrK + 3; ++r) {
+    const float *rE = tE[2 * ty * kPyrK + r] + tx + 1, *rO = tO[2 * ty * kPyrK + r] + tx + 1;
+    const float s0 = rE[0], s1 = rO[0], s2 = rE[1], s3 = rO[1], s4 = rE[2];
+#pragma unroll
+    for (int t = 0; t < kPyrK; ++t) {
+      const int dj = r - 2 * t; // row of target t's window
+      if (dj >= 0 && dj < 5) {
+        acc[t] = __fadd_rn(acc[t], __fmul_rn(s0, kw.w[dj * 5 + 0]));
+        acc[t] = __fadd_rn(acc[t], __fmul_rn(s1, kw.w[dj * 5 + 1]));
+        acc[t] = __fadd_rn(acc[t], __fmul_rn(s2, kw.w[dj * 5 + 2]));
+        acc[t] = __fadd_rn(acc[t], __fmul_rn(s3, kw.w[dj * 5 + 3]));
+        acc[t] = __fadd_rn(acc[t], __fmul_rn(s4, kw.w[dj * 5 + 4]));
+      }
     }
-    out = (uint8_t)__float2uint_rz(addition);
   }
-  dst[(size_t)tj * dpitch + ti] = out;
+#pragma unroll
+  for (int t = 0; t < kPyrK; ++t) {
+    const int tj = tj0 + t;
+    if (tj >= drows) break;
+    const bool interior = ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1;
+    dst[(size_t)tj * dpitch + ti] = interior ? (uint8_t)__float2uint_rz(acc[t]) : (uint8_t)0;
+  }
 }
 
 // level-0 upload helper: tightly packed (or pitched) u8 rows -> engine pitch
