@@ -95,24 +95,54 @@ def subset_boxes(lo, hi, n):
 # ------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region on a side thread.
+    NVML in-process (what nvidia-smi itself reads; ~10 us per sample, no fork inside the timed region);
+    falls back to the nvidia-smi command line when the binding is missing."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], False
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(self.handle))
+            return [str(sm), str(mx)] + ["Active" if mask & bit else "Not Active" for _, bit in self.BITS]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        return [x.strip() for x in out.strip().split(",")]
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+                f = self._sample()
                 if len(f) >= 6:
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02 if self.nvml is not None else 0.05)
 
     def __enter__(self):
         self.t.start()
@@ -126,10 +156,9 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        reasons = [n for k, (n, _) in enumerate(self.BITS) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
@@ -388,9 +417,20 @@ def main():
         eng.lib.dic_correlate_batch(eng.h, 0, n_sectors, guess_buf.ctypes.data, res_buf.ctypes.data)
         return None, eng.last_correlate_ms(), res_buf  # work is read from the records after the loop
 
+    # a rank that owns a band of the image (sharded subsets, row-split domain) transfers only its rows plus
+    # a halo for displacement, bicubic support and pyramid support (dic_stage_next_pair_rows)
+    band = None
+    if world > 1 and d[0] in ("rowsplit", "subsets"):
+        halo = 64 << w["pyramid"][2] if d[0] == "rowsplit" else 128
+        if d[0] == "rowsplit":
+            band = (max(0, b0 - halo), min(rows, b1 + 1 + halo))
+        else:
+            band = (max(0, min(bx[1] for bx in boxes) - halo), min(rows, max(bx[3] for bx in boxes) + 1 + halo))
+    h2d_bytes = 2 * cols * ((band[1] - band[0]) if band else rows)
+
     def stage_pair():
         # this step's inputs: both images from pinned host memory, upload + pyramids on the image stream
-        eng.stageNextPair(und_pin.data_ptr(), dfm_pin.data_ptr(), rows, cols)
+        eng.stageNextPair(und_pin.data_ptr(), dfm_pin.data_ptr(), rows, cols, row_range=band)
 
     def e2e_loop(n):
         # double-buffered ingest (dic_stage_next_pair / dic_advance_pair): the PCIe transfer of pair k + 1
@@ -507,9 +547,10 @@ def main():
                                    if scaling == "strong" else f"{world} independent domain(s), one per GPU")},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_work / e2e_wall, "unit": "pixel*evaluations/s",
-                "h2d_bytes_per_step": 2 * rows * cols, "d2h_bytes_per_step": 176 * n_sectors,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 176 * n_sectors,
                 "ms_per_step": 1e3 * e2e_wall / args.steps,
-                "pipeline": "dic_stage_next_pair(k + 1) on the image stream overlaps dic_correlate(k); H2D of both images every step"},
+                "pipeline": "dic_stage_next_pair(k + 1) on the copy / image streams overlaps dic_correlate(k); H2D of both images every step"
+                            + ("" if band is None else f" (this rank's row band {band[0]}..{band[1]} of {rows}; bytes are per rank)")},
         "gpu_launches": launches,
         "other_arith_mode": {"arith_mode": "parity" if other == engine.MODE_PARITY else "fast",
                              "kernel_value_this_rank": o_work / (o_ms * 1e-3) if o_ms > 0 else None,

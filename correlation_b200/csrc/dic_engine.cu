@@ -213,18 +213,27 @@ int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
   return DIC_OK;
 }
 
-// Level 0 -> levels 1..stop on `st`.
-int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st) {
+// Level 0 -> levels 1..stop on `st`. With a row band [row_begin, row_end) of level 0 only the target
+// rows whose whole 5-row support lies inside the band are rebuilt at each level (the band shrinks by
+// two rows per level at either end unless it touches the image border).
+int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st, int row_begin = 0, int row_end = -1) {
   static const PyrWeights kw = pyramid_weights();
+  int rb = row_begin, re = row_end < 0 ? s.lev[0].rows : row_end;
   for (int l = 1; l <= stop; ++l) {
     const LevelImage &src = s.lev[l - 1];
     const LevelImage &dst = s.lev[l];
     if (dst.rows <= 0 || dst.cols <= 0) break;
-    dim3 block(kPyrTX, kPyrTY);
-    dim3 grid((dst.cols + kPyrTX - 1) / kPyrTX, (dst.rows + kPyrTY * kPyrK - 1) / (kPyrTY * kPyrK));
-    pyramid_level_kernel<<<grid, block, 0, st>>>(src, const_cast<uint8_t *>(dst.ptr), dst.rows,
-                                                 dst.cols, dst.pitch, kw);
-    e->launches++;
+    // target row t reads source rows 2t-2 .. 2t+2
+    const int tb = rb <= 0 ? 0 : (rb + 2 + 1) / 2;
+    const int te = re >= src.rows ? dst.rows : std::min(dst.rows, (re - 1 - 2) / 2 + 1);
+    if (te > tb) {
+      dim3 block(kPyrTX, kPyrTY);
+      dim3 grid((dst.cols + kPyrTX - 1) / kPyrTX, (te - tb + kPyrTY * kPyrK - 1) / (kPyrTY * kPyrK));
+      pyramid_level_kernel<<<grid, block, 0, st>>>(src, const_cast<uint8_t *>(dst.ptr), dst.rows,
+                                                   dst.cols, dst.pitch, kw, tb, te);
+      e->launches++;
+    }
+    rb = tb; re = std::max(tb, te);
   }
   CU_TRY(e, cudaGetLastError());
   s.valid = true;
@@ -908,8 +917,11 @@ int dic_make_def_pyramid_from_nxt(dic_engine *e) {
 
 // Double-buffered ingest of whole image pairs: the upload and the pyramid build of pair k + 1 run on
 // the image stream while the solve of pair k runs on the correlation stream.
-int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols) {
+static int stage_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols,
+                           int row_begin, int row_end) {
   if (!e || !und || !def || rows < 8 || cols < 8) return DIC_ERROR_BAD_ARGUMENT;
+  row_begin = std::max(0, row_begin); row_end = std::min(rows, row_end);
+  if (row_end <= row_begin) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
   // the staging slots may still be read by solves enqueued before the last dic_advance_pair
   CU_TRY(e, cudaEventRecord(e->ev_gn, e->stream));
@@ -920,13 +932,26 @@ int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, i
   for (int k = 0; k < 2; ++k) {
     PyramidSlot &s = e->pyr[e->role[3 + k]];
     if ((rc = shape_slot(e, s, rows, cols, e->stop))) return rc;
-    if ((rc = upload_level0(e, s, k == 0 ? und : def, rows, cols, cols, false, e->copy_stream))) return rc;
+    const uint8_t *src = (k == 0 ? und : def) + (size_t)row_begin * cols;
+    uint8_t *dst = const_cast<uint8_t *>(s.lev[0].ptr) + (size_t)row_begin * s.lev[0].pitch;
+    const int nr = row_end - row_begin;
+    if (s.lev[0].pitch == cols)
+      CU_TRY(e, cudaMemcpyAsync(dst, src, (size_t)nr * cols, cudaMemcpyHostToDevice, e->copy_stream));
+    else
+      CU_TRY(e, cudaMemcpy2DAsync(dst, s.lev[0].pitch, src, cols, cols, nr, cudaMemcpyHostToDevice, e->copy_stream));
   }
   CU_TRY(e, cudaEventRecord(e->ev_copy, e->copy_stream));
   CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_copy, 0));
   for (int k = 0; k < 2; ++k)
-    if ((rc = build_levels(e, e->pyr[e->role[3 + k]], e->stop, e->img_stream))) return rc;
+    if ((rc = build_levels(e, e->pyr[e->role[3 + k]], e->stop, e->img_stream, row_begin, row_end))) return rc;
   return DIC_OK;
+}
+int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols) {
+  return stage_pair_rows(e, und, def, rows, cols, 0, rows);
+}
+int dic_stage_next_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols,
+                             int row_begin, int row_end) {
+  return stage_pair_rows(e, und, def, rows, cols, row_begin, row_end);
 }
 int dic_advance_pair(dic_engine *e) {
   if (!e) return DIC_ERROR_BAD_ARGUMENT;

@@ -542,12 +542,13 @@ struct PyrWeights { float w[25]; };
 
 __global__ void __launch_bounds__(kPyrTX *kPyrTY)
 pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int dcols, int dpitch,
-                     PyrWeights kw) {
+                     PyrWeights kw, int trow_begin, int trow_end) {
   constexpr int TH = kPyrTY * kPyrK;                             // 32 target rows per CTA
   constexpr int SWW = (2 * kPyrTX + 8) / 4, SH = 2 * TH + 3;     // 18 words (72 px) x 67 rows
   __shared__ float tE[SH][SWW * 2 + 1], tO[SH][SWW * 2 + 1];     // even / odd source columns
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int ox = blockIdx.x * kPyrTX, oy = blockIdx.y * TH;      // target origin
+  // only target rows [trow_begin, trow_end) are produced (a GPU that holds a band of the image)
+  const int ox = blockIdx.x * kPyrTX, oy = trow_begin + blockIdx.y * TH; // target origin
   const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;                  // staged window origin (x 4-aligned)
   for (int idx = ty * kPyrTX + tx; idx < SH * SWW; idx += kPyrTX * kPyrTY) {
     const int r = idx / SWW, c4 = idx - r * SWW;
@@ -585,7 +586,7 @@ pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int d
 #pragma unroll
   for (int t = 0; t < kPyrK; ++t) {
     const int tj = tj0 + t;
-    if (tj >= drows) break;
+    if (tj >= drows || tj >= trow_end) break;
     const bool interior = ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1;
     dst[(size_t)tj * dpitch + ti] = interior ? (uint8_t)__float2uint_rz(acc[t]) : (uint8_t)0;
   }

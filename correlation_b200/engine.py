@@ -68,7 +68,7 @@ EXPORTS = [
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
     "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_points", "dic_set_polygon_center",
-    "dic_stage_next_pair", "dic_advance_pair",
+    "dic_stage_next_pair", "dic_stage_next_pair_rows", "dic_advance_pair",
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
@@ -107,6 +107,7 @@ def load_library():
         "dic_reset_def_pyramid_device": (I, [P, P, I, I, I]),
         "dic_make_und_pyramid_from_def": (I, [P]),
         "dic_stage_next_pair": (I, [P, P, P, I, I]),
+        "dic_stage_next_pair_rows": (I, [P, P, P, I, I, I, I]),
         "dic_advance_pair": (I, [P]),
         "dic_make_def_pyramid_from_nxt": (I, [P]),
         "dic_reset_polygon_rect": (I, [P, I, I, I, I, I]),
@@ -239,9 +240,13 @@ class CudaEngine:
         dfm = self._img(dfm)
         self._ck(self.lib.dic_reset_def_pyramid(self.h, _ptr(dfm), dfm.shape[0], dfm.shape[1]))
 
-    def stageNextPair(self, und_ptr, def_ptr, rows, cols):
-        """Enqueue upload + pyramids of the next pair from (pinned) host pointers; returns at once."""
-        self._ck(self.lib.dic_stage_next_pair(self.h, und_ptr, def_ptr, rows, cols))
+    def stageNextPair(self, und_ptr, def_ptr, rows, cols, row_range=None):
+        """Enqueue upload + pyramids of the next pair from (pinned) host pointers; returns at once.
+        row_range = (begin, end): transfer only that band of rows (see dic_stage_next_pair_rows)."""
+        if row_range is None:
+            self._ck(self.lib.dic_stage_next_pair(self.h, und_ptr, def_ptr, rows, cols))
+        else:
+            self._ck(self.lib.dic_stage_next_pair_rows(self.h, und_ptr, def_ptr, rows, cols, int(row_range[0]), int(row_range[1])))
 
     def advancePair(self):
         self._ck(self.lib.dic_advance_pair(self.h))

@@ -131,6 +131,13 @@ int dic_reset_def_pyramid_device(dic_engine *e, const void *def_dev, int rows, i
  * resetNextPyramid on its loader thread (manager_class.cpp:1438-1447), for both images. */
 int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols);
 int dic_advance_pair(dic_engine *e);
+/* same for a GPU that works on a band of the image only (sharded subsets, row-split domain): `und` and
+ * `def` still point at the FULL host images, but only rows [row_begin, row_end) are transferred and only
+ * the pyramid rows they fully determine are rebuilt (two level-rows fewer per level at each cut). Rows
+ * outside keep whatever the slot held before: the caller's band must cover its domains plus their
+ * displacement, the 2-pixel bicubic halo and 2^(level + 2) rows of pyramid support. */
+int dic_stage_next_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols,
+                             int row_begin, int row_end);
 /* ---- CudaClass::makeUndPyramidFromDef / makeDefPyramidFromNxt (cuda_class.cu:607-613):
  *      pointer rotation, no copy */
 int dic_make_und_pyramid_from_def(dic_engine *e);

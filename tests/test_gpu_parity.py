@@ -560,3 +560,37 @@ def test_staged_pairs_double_buffer_equals_direct_upload(eng, golden):
     with pytest.raises(engine.DicError):
         eng.advancePair()
         eng.advancePair()  # nothing staged any more
+
+
+def test_staged_row_band_equals_full_upload_inside_the_band(eng, golden):
+    """dic_stage_next_pair_rows: only a band of rows is transferred and rebuilt; a domain well inside the
+    band must give bit-identical results to a full upload even when the rest of the slot holds junk."""
+    import torch
+    rows = cols = 512
+    truth = (0.8, -0.6, 0.001, -0.002, 0.0015, 0.001)
+    und, dfm = synth.make_pair(rows, cols, 31, truth, center=(256, 256))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    eng.resetPolygon(0, 200, 230, 330, 300)
+    want = eng.correlate(0, np.zeros(6, np.float32))
+    want_pyr = [eng.pyramid_level(1, lv) for lv in (0, 1, 2)]
+    rng = np.random.default_rng(5)
+    junk = [torch.from_numpy(rng.integers(0, 256, (rows, cols), dtype=np.uint8)).pin_memory() for _ in range(2)]
+    pin = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory() for im in (und, dfm)]
+    band = (160, 380)
+    for _ in range(2):  # both staging slot pairs get junk first, then the band
+        eng.stageNextPair(junk[0].data_ptr(), junk[1].data_ptr(), rows, cols)
+        eng.advancePair()
+    for k in range(2):
+        eng.stageNextPair(pin[0].data_ptr(), pin[1].data_ptr(), rows, cols, row_range=band)
+        eng.advancePair()
+        got = eng.correlate(0, np.zeros(6, np.float32))
+        assert np.array_equal(got["params"], want["params"]) and got["chi"] == want["chi"], (k, got, want)
+        for lv in (0, 1, 2):
+            lo = (band[0] >> lv) + (4 if lv else 0)
+            hi = (band[1] >> lv) - (4 if lv else 0)
+            assert np.array_equal(eng.pyramid_level(1, lv)[lo:hi], want_pyr[lv][lo:hi]), lv
+        # rows far outside the band still hold the junk image's pyramid: the band upload did not touch them
+        assert not np.array_equal(eng.pyramid_level(1, 0)[:100], want_pyr[0][:100])
+        eng.stageNextPair(junk[0].data_ptr(), junk[1].data_ptr(), rows, cols)
+        eng.advancePair()
