@@ -522,8 +522,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:  # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gn_solve_tiles_kernel"]
-        if args.workload == "c2" and args.mode == "fast":
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gn_solve_tiles_kernel"].get(f"{args.workload} {args.mode}")
+        if tr:
             traffic = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
     except Exception:
         pass
@@ -561,8 +561,11 @@ def main():
                                      "algorithmic bytes per launch = 10 B x pixel_evaluations_per_step",
                      "kernel": "gn_solve_tiles_kernel" if n_sectors >= 1 else "gn_solve_kernel",
                      "kernel_ms_per_step": kern_ms / args.steps,
-                     "fp32_note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md 4.1): sm__inst_executed_pipe_fma 28 % of peak over the "
-                                  "whole launch, ~70 % issue utilisation inside the level-0 passes (profiles/r1_c2_gn_solve_tiles_fast_ncu_full.txt)",
+                     "fp32_note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md 4.1): parity mode replays the reference's "
+                                  "~270 unfused fp32 operations per pixel (369 issued instructions per pixel*evaluation over the whole "
+                                  "launch, FMA pipe 47 % of peak, issue slots 62 % incl. the per-evaluation grid all-reduce); the level "
+                                  "data stays L2-resident across evaluations (31 MB of DRAM reads for 369 MB of algorithmic traffic). "
+                                  "profiles/r1_c2_gn_solve_tiles_parity_ncu_full.txt, profiles/r1_l0_pass_ncu_full.txt",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_pixel_evaluation": ALGO_BYTES_PER_PIXEL_EVAL},
     }
