@@ -22,9 +22,13 @@
 
 namespace dic {
 
-#ifndef DIC_TILE_CTAS_PER_SM
-#define DIC_TILE_CTAS_PER_SM 2
+// Resident CTAs per SM the tile kernel is compiled for. 2 CTAs = 16 warps per SM at 128 registers.
+// Measured on B200 (c4 / c5, affine): 3 CTAs at 80 registers (20-170 bytes of spill) is 10 % slower in
+// parity mode and within +-5 % in fast mode; the quadratic model spills ~1 KB per thread at 80.
+#ifndef DIC_TILE_CTAS_AFFINE
+#define DIC_TILE_CTAS_AFFINE 2
 #endif
+constexpr int tile_ctas_per_sm(int model) { return model == DIC_FM_QUADRATIC ? 2 : DIC_TILE_CTAS_AFFINE; }
 constexpr int kTileW = 32, kTileH = 16;
 // Per-warp staging, filled by TMA (cp.async.bulk.tensor.2d) one unit ahead of the arithmetic:
 //   the deformed-image footprint of a unit as u8, kPatchW x kPatchH bytes,
@@ -549,7 +553,7 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, const 
 
 // ---- the solve kernel on tiles (same LM / barrier / solve machinery as gn_solve_kernel)
 template <int MODEL, int MODE, bool GRID>
-__global__ void __launch_bounds__(kThreads, DIC_TILE_CTAS_PER_SM)
+__global__ void __launch_bounds__(kThreads, tile_ctas_per_sm(MODEL))
 gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps maps,
                       const SectorDev *__restrict__ sectors, const SectorTiles *__restrict__ sector_tiles,
                       const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
