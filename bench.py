@@ -388,8 +388,8 @@ def main():
         # independent subsets shard across ranks in contiguous blocks, images replicated
         from correlation_b200 import sharding
         boxes = subset_boxes(d[1], d[2], d[3])
-        sb, se = sharding.shard_range(len(boxes), world, rank)
-        boxes = boxes[sb:se]
+        # whole rows of subsets per rank: each rank then needs only a band of image rows (e2e upload)
+        boxes = [boxes[i] for i in sharding.shard_grid_rows(d[3], d[3], world, rank)]
         for k, bx in enumerate(boxes):
             eng.resetPolygon(k, *bx)
         n_sectors = len(boxes)
@@ -543,7 +543,7 @@ def main():
                    "domain_build_s": t_dom,
                    "parallelism": (f"one domain in {world} row band(s), per-evaluation all-reduce of the normal equations inside the kernel (NVLink peer mailboxes)"
                                    if d[0] == "rowsplit" else
-                                   f"{d[3] * d[3]} subsets in contiguous blocks over {world} GPU(s), no collective"
+                                   f"{d[3] * d[3]} subsets, whole rows of subsets per GPU, over {world} GPU(s), no collective"
                                    if scaling == "strong" else f"{world} independent domain(s), one per GPU")},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_work / e2e_wall, "unit": "pixel*evaluations/s",

@@ -27,6 +27,15 @@ def owner_of(unit: int, n_units: int, world: int) -> int:
     return unit * world // n_units
 
 
+def shard_grid_rows(n_h: int, n_v: int, world: int, rank: int) -> list[int]:
+    """Sector ids (reference order: id = ih * n_v + iv, horizontal index outer, manager_class.cpp:304-310)
+    of the subdivisions whose VERTICAL index lies in rank's block: every rank then owns a band of image
+    rows, so it needs only that band of the images (dic_stage_next_pair_rows) -- the PCIe bytes per rank
+    fall with the number of GPUs instead of being replicated. Still no collective on the data path."""
+    vb, ve = shard_range(n_v, world, rank)
+    return [ih * n_v + iv for iv in range(vb, ve) for ih in range(n_h)]
+
+
 def gather_results(local: np.ndarray, n_units: int, dist=None, dst: int = 0):
     """Gather per-rank structured result arrays (RESULT_DTYPE) into one array of n_units on `dst`.
 

@@ -24,6 +24,19 @@ def test_shard_range_is_a_partition_and_matches_owner_rule():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_grid_rows_partitions_into_row_bands():
+    for n_h, n_v in ((64, 64), (3, 5), (1, 7)):
+        for world in (1, 2, 4, 8):
+            seen = np.zeros(n_h * n_v, int)
+            for r in range(world):
+                ids = sharding.shard_grid_rows(n_h, n_v, world, r)
+                seen[ids] += 1
+                ivs = sorted({i % n_v for i in ids})
+                assert ivs == list(range(ivs[0], ivs[-1] + 1)) if ivs else True  # one contiguous band of rows
+                assert all(sum(1 for i in ids if i % n_v == iv) == n_h for iv in ivs)  # whole rows of sectors
+            assert (seen == 1).all()
+
+
 def test_band_rows_balances_pixels():
     rows = np.zeros(1000)
     yy = np.arange(1000) - 500.0
