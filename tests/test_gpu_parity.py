@@ -376,6 +376,35 @@ def test_tile_kernel_equals_list_kernel(eng, model, mode, domain):
     assert abs(a["chi"] - b["chi"]) < (2e-5 if mode == engine.MODE_PARITY else 1e-4) * b["chi"]
 
 
+@pytest.mark.parametrize("mode", [engine.MODE_PARITY, engine.MODE_FAST])
+@pytest.mark.parametrize("truth", [(3.2, -2.1, 0.03, 0.05, -0.05, 0.025),      # 3 % strain + 0.05 rad rotation
+                                   (-1.4, 2.6, -0.02, 0.12, -0.12, -0.015)])   # 0.12 rad rotation
+def test_tile_kernel_under_large_strain_and_rotation(eng, mode, truth):
+    """Windows that repeat / skip rows and change column inside a unit (the warp-wide window rebuild) and
+    footprints that outgrow the staged patch (per-pixel fallback): tile kernel == pixel-list kernel."""
+    und, dfm = synth.make_pair(480, 512, 77, truth, center=(256, 240))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(mode)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    assert eng.resetPolygon(0, 96, 80, 416, 400) == 0
+    res = {}
+    for variant in (1, 0):
+        eng.set_kernel_variant(variant)
+        # a user guess near the answer (imageLabel's manual initial guess): 0.12 rad is far outside the
+        # capture range of a zero guess, and the point here is the kernels' paths, not the LM basin
+        res[variant] = eng.correlate(0, 0.93 * np.array(truth, np.float32))
+    eng.set_kernel_variant(0)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    a, b = res[1], res[0]
+    assert a["error_code"] == b["error_code"] == 0, (a, b)
+    assert a["evaluations"] == b["evaluations"]
+    d = np.abs(a["params"] - b["params"])
+    tol = (2e-5, 2e-7) if mode == engine.MODE_PARITY else (1e-4, 1e-6)
+    assert d[:2].max() < tol[0] and d[2:6].max() < tol[1], (a["params"], b["params"])
+    assert abs(a["chi"] - b["chi"]) < (2e-5 if mode == engine.MODE_PARITY else 1e-4) * b["chi"]
+    assert np.abs(b["params"] - np.array(truth)).max() < 5e-3  # and it is the right answer
+
+
 # ---------------------------------------------------------------- row-split machinery (one GPU: loop-back)
 
 def test_rowsplit_loopback_and_band_bookkeeping(eng):
