@@ -102,8 +102,11 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, world=1):
+        # every rank samples its own GPU; the period grows with the number of ranks so that the box-wide
+        # rate of driver queries stays the same (NVML calls serialise on a driver lock shared by all GPUs)
         self.index, self.samples, self.stop = index, [], False
+        self.period = 0.02 * max(1, world)
         self.t = threading.Thread(target=self._run, daemon=True)
         self.nvml = self.handle = None
         try:
@@ -142,7 +145,7 @@ class ClockSampler:
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.02 if self.nvml is not None else 0.05)
+            time.sleep(self.period if self.nvml is not None else max(0.05, self.period))
 
     def __enter__(self):
         self.t.start()
@@ -456,7 +459,7 @@ def main():
     launches0 = eng.kernel_launches()
     barrier()
     work = kern_ms = wall = 0.0
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, world) as clk:
         for _ in range(args.steps):
             flush.fill_(1)
             torch.cuda.synchronize()
