@@ -424,7 +424,8 @@ def main():
     # a halo for displacement, bicubic support and pyramid support (dic_stage_next_pair_rows)
     band = None
     if world > 1 and d[0] in ("rowsplit", "subsets"):
-        halo = 64 << w["pyramid"][2] if d[0] == "rowsplit" else 128
+        # displacement of the workload (<= 64 px) + bicubic halo + 2^(level + 2) rows of pyramid support per cut
+        halo = 64 + (8 << w["pyramid"][2])
         if d[0] == "rowsplit":
             band = (max(0, b0 - halo), min(rows, b1 + 1 + halo))
         else:
