@@ -75,6 +75,23 @@ def run_sequence(frames, *, rect=None, subdivisions=(1, 1), annulus=None, contou
     return dict(csv=csv.value.decode(), seconds=secs.value, rows=out[:written.value], error=rc)
 
 
+def deform_points(model, params, center, xy):
+    """managerClass::deformPoints (manager_class.cpp:2527-2600): contour points carried by a result."""
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} missing: run __graft_entry__.build()")
+    lib = C.CDLL(LIB_PATH)
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    p = np.zeros(12, np.float32)
+    p[: len(params)] = params
+    out = np.zeros_like(xy)
+    lib.dic_host_deform_points.restype = C.c_int
+    lib.dic_host_deform_points.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+    rc = lib.dic_host_deform_points(int(model), p.ctypes.data, float(center[0]), float(center[1]), xy.ctypes.data, len(xy), out.ctypes.data)
+    if rc != 0:
+        raise ValueError("dic_host_deform_points: bad argument")
+    return out
+
+
 def parse_report(csv_text):
     """CSV report -> list of dict rows (floats where possible)."""
     lines = [l for l in csv_text.strip().split("\n") if l]

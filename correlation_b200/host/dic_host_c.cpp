@@ -102,6 +102,16 @@ int dic_host_run(const dic_host_config *c, const uint8_t *const *frames, int n_f
   }
 }
 
+// managerClass::deformPoints (manager_class.cpp:2527-2600) for FFI callers: n points (x, y interleaved)
+// moved by `params` of `model` about the centre (cx, cy). No GPU involved.
+int dic_host_deform_points(int model, const float *params, float cx, float cy, const float *xy_in, int n,
+                           float *xy_out) {
+  if (!params || !xy_in || !xy_out || n < 0 || model < fm_U || model > fm_UVUxUyVxVyQuad) return -1;
+  for (int i = 0; i < n; ++i)
+    dic_host::distort_point(model, xy_in[2 * i], xy_in[2 * i + 1], cx, cy, params, xy_out[2 * i], xy_out[2 * i + 1]);
+  return 0;
+}
+
 } // extern "C"
 
 #ifdef DIC_HEADLESS_MAIN

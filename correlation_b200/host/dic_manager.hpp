@@ -63,6 +63,20 @@ struct SectorState {
 
 inline int n_params_of(fittingModelEnum m) { return m == fm_U ? 1 : m == fm_UV ? 2 : m == fm_UVQ ? 3 : m == fm_UVUxUyVxVy ? 6 : 12; }
 
+// interpolation_class.cpp:3-43 (+ quadratic extension): the model applied to one point
+inline void distort_point(int model, float x, float y, float cx, float cy, const float *p, float &xd, float &yd) {
+  float dx = x - cx, dy = y - cy;
+  switch (model) {
+  case fm_U: xd = x + p[0]; yd = y; break;
+  case fm_UV: xd = x + p[0]; yd = y + p[1]; break;
+  case fm_UVQ: xd = x + p[0] - dy * p[2]; yd = y + p[1] + dx * p[2]; break;
+  case fm_UVUxUyVxVy: xd = x + p[0] + dx * p[2] + dy * p[3]; yd = y + p[1] + dx * p[4] + dy * p[5]; break;
+  default:
+    xd = x + p[0] + dx * p[2] + dy * p[3] + 0.5f * p[6] * dx * dx + p[7] * dx * dy + 0.5f * p[8] * dy * dy;
+    yd = y + p[1] + dx * p[4] + dy * p[5] + 0.5f * p[9] * dx * dx + p[10] * dx * dy + 0.5f * p[11] * dy * dy;
+  }
+}
+
 class HeadlessManager {
   Config cfg_;
   CudaClass cuda_;
@@ -71,18 +85,21 @@ class HeadlessManager {
   std::ostringstream report_;
   static constexpr float PI = 3.14159265359f; // parameters.hpp:23
 
-  // interpolation_class.cpp:3-43 (+ quadratic extension): the model applied to one point
   void distort(float x, float y, float cx, float cy, const float *p, float &xd, float &yd) const {
-    float dx = x - cx, dy = y - cy;
-    switch (cfg_.model) {
-    case fm_U: xd = x + p[0]; yd = y; break;
-    case fm_UV: xd = x + p[0]; yd = y + p[1]; break;
-    case fm_UVQ: xd = x + p[0] - dy * p[2]; yd = y + p[1] + dx * p[2]; break;
-    case fm_UVUxUyVxVy: xd = x + p[0] + dx * p[2] + dy * p[3]; yd = y + p[1] + dx * p[4] + dy * p[5]; break;
-    default:
-      xd = x + p[0] + dx * p[2] + dy * p[3] + 0.5f * p[6] * dx * dx + p[7] * dx * dy + 0.5f * p[8] * dy * dy;
-      yd = y + p[1] + dx * p[4] + dy * p[5] + 0.5f * p[9] * dx * dx + p[10] * dx * dy + 0.5f * p[11] * dy * dy;
+    distort_point(cfg_.model, x, y, cx, cy, p, xd, yd);
+  }
+
+  // manager_class.cpp:2527-2600 deformPoints: a contour (domain outline for plotting, def_contour of
+  // :504 / :764 / :1207) carried along with a sector's result
+  v_points deformPoints(const v_points &contour, float cx, float cy, const float *model_parameters) const {
+    v_points out;
+    out.reserve(contour.size());
+    for (const auto &q : contour) {
+      float xd, yd;
+      distort(q.first, q.second, cx, cy, model_parameters, xd, yd);
+      out.push_back(std::make_pair(xd, yd));
     }
+    return out;
   }
 
   // manager_class.cpp:2602-2707

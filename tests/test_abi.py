@@ -38,3 +38,24 @@ def test_no_cpu_fallback_without_gpu():
             assert "no CPU fallback" in str(e)
         else:
             raise AssertionError("engine construction must fail loudly without a GPU")
+
+
+def test_host_deform_points_restates_the_reference_distort_functions():
+    """managerClass::deformPoints (manager_class.cpp:2527-2600) over interpolation_class.cpp:3-43, fp32,
+    left-to-right like the reference; no GPU involved."""
+    import numpy as np
+    from correlation_b200 import host
+    rng = np.random.default_rng(3)
+    xy = rng.uniform(0, 500, (50, 2)).astype(np.float32)
+    p = np.array([1.5, -0.75, 0.01, -0.02, 0.03, 0.005], np.float32)
+    cx, cy = np.float32(250.0), np.float32(240.0)
+    x, y = xy[:, 0], xy[:, 1]
+    want = {
+        0: (x + p[0], y),
+        1: (x + p[0], y + p[1]),
+        2: (x + p[0] - (y - cy) * p[2], y + p[1] + (x - cx) * p[2]),
+        3: (x + p[0] + (x - cx) * p[2] + (y - cy) * p[3], y + p[1] + (x - cx) * p[4] + (y - cy) * p[5]),
+    }
+    for model, (wx, wy) in want.items():
+        got = host.deform_points(model, p, (cx, cy), xy)
+        assert np.array_equal(got[:, 0], wx.astype(np.float32)) and np.array_equal(got[:, 1], wy.astype(np.float32)), model
