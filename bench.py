@@ -283,7 +283,7 @@ def run_c3(args, w):
         cs = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": nf / cs, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"first {nf} frame pairs of the sequence (pyramid + Newton_Raphson each)"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -352,7 +352,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "pixel*evaluations/s", "cores": threads, "kind": kind,
                                  "sample": sample},
                 "e2e": {"value": v, "unit": "pixel*evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -607,7 +607,7 @@ def main():
                 "note": "CPU side accumulates in fp32 per thread (its chi moves ~2e-4 with the thread count, SURVEY H1)"}
         except Exception as ex:  # the baseline is reported, never allowed to sink the bench line
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -38,6 +38,10 @@ def run_sequence(frames, *, rect=None, subdivisions=(1, 1), annulus=None, contou
         raise RuntimeError(f"{LIB_PATH} missing: run __graft_entry__.build()")
     lib = C.CDLL(LIB_PATH)
     lib.dic_host_run.restype = C.c_int
+    # explicit prototype: csv_cap is a long long -- an undeclared Python int travels as a 32-bit int and leaves
+    # the upper half of the register undefined (seen as an intermittently empty report)
+    lib.dic_host_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
     rows, cols = frames[0].shape
     c = HostConfig()
@@ -68,8 +72,8 @@ def run_sequence(frames, *, rect=None, subdivisions=(1, 1), annulus=None, contou
     csv = C.create_string_buffer(max(1 << 16, 600 * n_sectors * len(frames)))
     need, secs, written = C.c_longlong(), C.c_double(), C.c_int()
     out = np.zeros(n_sectors, ROW_DTYPE)
-    rc = lib.dic_host_run(C.byref(c), ptrs, len(frames), rows, cols, csv, len(csv), C.byref(need), C.byref(secs),
-                          out.ctypes.data_as(C.c_void_p), n_sectors, C.byref(written))
+    rc = lib.dic_host_run(C.addressof(c), C.addressof(ptrs), len(frames), rows, cols, C.addressof(csv), len(csv),
+                          C.addressof(need), C.addressof(secs), out.ctypes.data, n_sectors, C.addressof(written))
     if rc < 0:
         raise RuntimeError("dic_host_run failed (no GPU?)")
     return dict(csv=csv.value.decode(), seconds=secs.value, rows=out[:written.value], error=rc)
