@@ -414,7 +414,7 @@ __device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, con
 // their tiles into row chunks so that every resident warp has work; units keep the column-major strip
 // order. The staging of unit u + 1 is in flight while unit u is being evaluated.
 template <int MODEL, int MODE>
-__device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const TileMaps &maps, const SectorDev *sec,
+__device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const TileMaps &maps, float cx0, float cy0,
                                                const TileLevel tl, int level, const float *p,
                                                int unit_begin, int unit_end, int split_log2, WarpStage &st,
                                                float *warp_acc, unsigned int *slow_counter) {
@@ -425,7 +425,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   const LevelImage def = cfg.def[level];
   const CUtensorMap *map_def = &maps.def[level], *map_und = &maps.und[level];
   const float inv = 1.f / (float)(1 << level);
-  const float ccx = sec->cx * inv, ccy = sec->cy * inv;
+  const float ccx = cx0 * inv, ccy = cy0 * inv;
   const int rpu = kTileH >> split_log2;
   float mom[M::kN];
 #pragma unroll
@@ -521,7 +521,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
 
 // Duplicate pixels of a blob list (beyond their first occurrence), handled by one warp.
 template <int MODEL, int MODE>
-__device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, const SectorDev *sec,
+__device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float cx0, float cy0,
                                                 const TileLevel tl, int level, const float *p,
                                                 float *warp_acc) {
   constexpr int NP = model_nparams(MODEL);
@@ -530,7 +530,7 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, const 
   const LevelImage und = cfg.und[level];
   const LevelImage def = cfg.def[level];
   const float inv = 1.f / (float)(1 << level);
-  const float ccx = sec->cx * inv, ccy = sec->cy * inv;
+  const float ccx = cx0 * inv, ccy = cy0 * inv;
   float mom[M::kN];
 #pragma unroll
   for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
@@ -565,6 +565,8 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   float *s_wacc = reinterpret_cast<float *>(dyn_smem + kWarpsPerCta * kWarpStageBytes); // [warps][NACC]
   __shared__ SolveShared<NP> sh;
   __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][2];
+  __shared__ SectorTiles s_tiles; // this sector's tile lists and centre: read once, not once per evaluation
+  __shared__ float s_center[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float *warp_acc = s_wacc + warp * NACC;
   WarpStage st;
@@ -585,14 +587,14 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
     const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
     dic_result *result = results + first_sector + si;
     unsigned int my_gen;
-    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, work, my_gen);
+    if (tid < kMaxLevels) s_tiles.lev[tid] = stl->lev[tid];
+    if (tid == kMaxLevels) { s_center[0] = sec->cx; s_center[1] = sec->cy; }
+    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, work, my_gen); // ends with a CTA barrier
     while (true) {
       const int level = sh.level;
       for (int k = lane; k < NACC; k += 32) warp_acc[k] = 0.f;
       __syncwarp();
-      TileLevel tl;
-      tl.tiles = stl->lev[level].tiles; tl.n_tiles = stl->lev[level].n_tiles;
-      tl.extra = stl->lev[level].extra; tl.n_extra = stl->lev[level].n_extra;
+      const TileLevel tl = s_tiles.lev[level];
       // split tiles into row chunks until every warp that can take part has a unit (rpu >= 4)
       const int warps_avail = GRID ? (int)gridDim.x * kWarpsPerCta : kWarpsPerCta;
       int split_log2 = 0;
@@ -610,9 +612,10 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
         // balanced contiguous ranges: the first (n_units % nw) warps take one unit more
         const int base = n_units / nw, rem = n_units - base * nw;
         const int ub = wg * base + min(wg, rem), ue = ub + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE>(cfg, maps, sec, tl, level, sh.p, ub, ue, split_log2, st, warp_acc,
-                                    GRID ? &work->slow_units : nullptr);
-        if (tl.n_extra > 0 && wg == 0) evaluate_extras<MODEL, MODE>(cfg, sec, tl, level, sh.p, warp_acc);
+        evaluate_tiles<MODEL, MODE>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, ub, ue, split_log2, st,
+                                    warp_acc, GRID ? &work->slow_units : nullptr);
+        if (tl.n_extra > 0 && wg == 0)
+          evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);
       }
       __syncthreads();
       for (int k = tid; k < NACC; k += kThreads) {
