@@ -528,9 +528,9 @@ __global__ void solve_step_kernel(const float *tot, float scaling, float lambda,
 // ------------------------------------------------------------------ pyramid
 
 // pyramid_class.cpp:52-134. One CTA = 32 x 32 target pixels, one thread = 4 vertically adjacent
-// targets. The (72 x 67) u8 source footprint is staged ONCE into shared memory as fp32 (aligned 32-bit
-// loads, PRMT + FADD conversion -- no I2F), split into even / odd source columns so that the stride-2
-// taps of neighbouring lanes hit distinct banks. A thread walks down its 11 source rows, loads the
+// targets. The (96 x 67) u8 source footprint is staged ONCE into shared memory as fp32 (aligned 128-bit
+// loads, PRMT + FADD conversion -- no I2F, 128-bit shared stores), split into even / odd source columns
+// so that the stride-2 taps of neighbouring lanes hit distinct banks. A thread walks down its 11 source rows, loads the
 // five taps of a row once and feeds every target whose 5 x 5 window contains that row: each target
 // still runs the reference's 25 sequential fp32 mul + add in the reference's order (dj outer, di
 // inner, no FMA contraction), the four chains are independent (ILP 4) and a tap is read from shared
@@ -544,21 +544,26 @@ __global__ void __launch_bounds__(kPyrTX *kPyrTY)
 pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int dcols, int dpitch,
                      PyrWeights kw, int trow_begin, int trow_end) {
   constexpr int TH = kPyrTY * kPyrK;                             // 32 target rows per CTA
-  constexpr int SWW = (2 * kPyrTX + 8) / 4, SH = 2 * TH + 3;     // 18 words (72 px) x 67 rows
-  __shared__ float tE[SH][SWW * 2 + 1], tO[SH][SWW * 2 + 1];     // even / odd source columns
+  constexpr int SW16 = 6, SH = 2 * TH + 3;                       // 6 x 16 px = 96 source columns x 67 rows
+  constexpr int SP = SW16 * 8;                                   // floats per row of each half
+  __shared__ __align__(16) float tE[SH][SP], tO[SH][SP];         // even / odd source columns
   const int tx = threadIdx.x, ty = threadIdx.y;
   // only target rows [trow_begin, trow_end) are produced (a GPU that holds a band of the image)
   const int ox = blockIdx.x * kPyrTX, oy = trow_begin + blockIdx.y * TH; // target origin
-  const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;                  // staged window origin (x 4-aligned)
-  for (int idx = ty * kPyrTX + tx; idx < SH * SWW; idx += kPyrTX * kPyrTY) {
-    const int r = idx / SWW, c4 = idx - r * SWW;
-    const int sx = sx0 + 4 * c4, sy = sy0 + r;
-    uint32_t v = 0;
-    if (sx >= 0 && sy >= 0 && sx + 3 < src.pitch && sy < src.rows)
-      v = __ldg(reinterpret_cast<const uint32_t *>(src.ptr + (size_t)sy * src.pitch + sx));
+  const int sx0 = 2 * ox - 16, sy0 = 2 * oy - 2;                 // staged window origin (x 16-byte aligned)
+  for (int idx = ty * kPyrTX + tx; idx < SH * SW16; idx += kPyrTX * kPyrTY) {
+    const int r = idx / SW16, c16 = idx - r * SW16;
+    const int sx = sx0 + 16 * c16, sy = sy0 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    // a 16-byte chunk is either wholly inside the pitch or wholly outside (pitch is a multiple of 128);
     // columns beyond the image inside the pitch are never used by a non-border target pixel
-    tE[r][2 * c4] = u8_to_float(v, 0); tO[r][2 * c4] = u8_to_float(v, 1);
-    tE[r][2 * c4 + 1] = u8_to_float(v, 2); tO[r][2 * c4 + 1] = u8_to_float(v, 3);
+    if (sx >= 0 && sy >= 0 && sx + 15 < src.pitch && sy < src.rows)
+      v = __ldg(reinterpret_cast<const uint4 *>(src.ptr + (size_t)sy * src.pitch + sx));
+    float4 *e = reinterpret_cast<float4 *>(&tE[r][8 * c16]), *o = reinterpret_cast<float4 *>(&tO[r][8 * c16]);
+    e[0] = make_float4(u8_to_float(v.x, 0), u8_to_float(v.x, 2), u8_to_float(v.y, 0), u8_to_float(v.y, 2));
+    o[0] = make_float4(u8_to_float(v.x, 1), u8_to_float(v.x, 3), u8_to_float(v.y, 1), u8_to_float(v.y, 3));
+    e[1] = make_float4(u8_to_float(v.z, 0), u8_to_float(v.z, 2), u8_to_float(v.w, 0), u8_to_float(v.w, 2));
+    o[1] = make_float4(u8_to_float(v.z, 1), u8_to_float(v.z, 3), u8_to_float(v.w, 1), u8_to_float(v.w, 3));
   }
   __syncthreads();
   const int ti = ox + tx, tj0 = oy + ty * kPyrK;
@@ -566,10 +571,10 @@ pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int d
   float acc[kPyrK];
 #pragma unroll
   for (int t = 0; t < kPyrK; ++t) acc[t] = 0.f;
-  // source column of tap di: 2 ti - 2 + di = sx0 + (2 tx + 2 + di): even di -> tE[tx + 1 + di/2], odd -> tO[tx + 1 + (di-1)/2]
+  // source column of tap di: 2 ti - 2 + di = sx0 + (2 tx + 14 + di): even di -> tE[tx + 7 + di/2], odd -> tO[tx + 7 + (di-1)/2]
 #pragma unroll
   for (int r = 0; r < 2 * kPyrK + 3; ++r) {
-    const float *rE = tE[2 * ty * kPyrK + r] + tx + 1, *rO = tO[2 * ty * kPyrK + r] + tx + 1;
+    const float *rE = tE[2 * ty * kPyrK + r] + tx + 7, *rO = tO[2 * ty * kPyrK + r] + tx + 7;
     const float s0 = rE[0], s1 = rO[0], s2 = rE[1], s3 = rO[1], s4 = rE[2];
 #pragma unroll
     for (int t = 0; t < kPyrK; ++t) {
