@@ -57,6 +57,7 @@ struct PyramidSlot {
   LevelImage lev[kMaxLevels] = {};
   // TMA descriptors of every level for the two box shapes the tile kernel stages
   CUtensorMap tm_patch[kMaxLevels], tm_tile[kMaxLevels];
+  CUtensorMap tm_pyr[kMaxLevels]; // the level as the SOURCE of the pyramid kernel (box kPyrSW x kPyrSH)
   int rows = 0, cols = 0;
   bool valid = false;
 };
@@ -205,6 +206,7 @@ int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
     if (!same && lev[l].rows > 0 && lev[l].cols > 0) {
       int rc = encode_level_map(e, &s.tm_patch[l], lev[l], kPatchW, kPatchH);
       if (!rc) rc = encode_level_map(e, &s.tm_tile[l], lev[l], kUndW, kTileH);
+      if (!rc) rc = encode_level_map(e, &s.tm_pyr[l], lev[l], kPyrSW, kPyrSH);
       if (rc) return rc;
     }
   }
@@ -227,10 +229,16 @@ int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st, int r
     const int tb = rb <= 0 ? 0 : (rb + 2 + 1) / 2;
     const int te = re >= src.rows ? dst.rows : std::min(dst.rows, (re - 1 - 2) / 2 + 1);
     if (te > tb) {
+      static bool attr_set[16] = {false};
+      if (!attr_set[e->device & 15]) {
+        CU_TRY(e, cudaFuncSetAttribute(pyramid_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPyrSmem));
+        attr_set[e->device & 15] = true;
+      }
       dim3 block(kPyrTX, kPyrTY);
-      dim3 grid((dst.cols + kPyrTX - 1) / kPyrTX, (te - tb + kPyrTY * kPyrK - 1) / (kPyrTY * kPyrK));
-      pyramid_level_kernel<<<grid, block, 0, st>>>(src, const_cast<uint8_t *>(dst.ptr), dst.rows,
-                                                   dst.cols, dst.pitch, kw, tb, te);
+      const int n_tiles = ((dst.cols + kPyrTX - 1) / kPyrTX) * ((te - tb + kPyrTH - 1) / kPyrTH);
+      const int grid = std::max(1, std::min(n_tiles, e->num_sms * 5)); // persistent: 5 CTAs of 38 KB fit an SM
+      pyramid_level_kernel<<<grid, block, kPyrSmem, st>>>(s.tm_pyr[l - 1], const_cast<uint8_t *>(dst.ptr), dst.rows,
+                                                          dst.cols, dst.pitch, kw, tb, te);
       e->launches++;
     }
     rb = tb; re = std::max(tb, te);

@@ -527,73 +527,101 @@ __global__ void solve_step_kernel(const float *tot, float scaling, float lambda,
 
 // ------------------------------------------------------------------ pyramid
 
-// pyramid_class.cpp:52-134. One CTA = 32 x 32 target pixels, one thread = 4 vertically adjacent
-// targets. The (96 x 67) u8 source footprint is staged ONCE into shared memory as fp32 (aligned 128-bit
-// loads, PRMT + FADD conversion -- no I2F, 128-bit shared stores), split into even / odd source columns
-// so that the stride-2 taps of neighbouring lanes hit distinct banks. A thread walks down its 11 source rows, loads the
-// five taps of a row once and feeds every target whose 5 x 5 window contains that row: each target
-// still runs the reference's 25 sequential fp32 mul + add in the reference's order (dj outer, di
-// inner, no FMA contraction), the four chains are independent (ILP 4) and a tap is read from shared
-// memory 55 / 4 times per target instead of 25. Truncation to u8; target border rows / columns are
-// written as 0 (the reference leaves a zero-initialised border, :98-102).
+// pyramid_class.cpp:52-134. Persistent CTAs walk over 32 x 32 target tiles; one thread = 4 vertically
+// adjacent targets. The (96 x 67) u8 source footprint of the NEXT tile is fetched by TMA
+// (cp.async.bulk.tensor.2d, out-of-image = 0) into a double buffer while the current tile is computed.
+// The landed u8 tile is converted once to fp32 in shared memory (PRMT + FADD -- no I2F), split into
+// even / odd source columns so that the stride-2 taps of neighbouring lanes hit distinct banks.
+// A thread walks down its 11 source rows, loads the five taps of a row once and feeds every target whose
+// 5 x 5 window contains that row: each target still runs the reference's 25 sequential fp32 mul + add in
+// the reference's order (dj outer, di inner, no FMA contraction), the four chains are independent (ILP 4)
+// and a tap is read from shared memory 55 / 4 times per target instead of 25. Truncation to u8; target
+// border rows / columns are written as 0 (the reference leaves a zero-initialised border, :98-102).
 // HBM-bound by design (1.25 B per source pixel), FP32-issue bound in practice: 50 unfused ops per target.
 constexpr int kPyrTX = 32, kPyrTY = 8, kPyrK = 4; // threads x, threads y, targets per thread
+constexpr int kPyrTH = kPyrTY * kPyrK;            // 32 target rows per tile
+constexpr int kPyrSW = 96, kPyrSH = 2 * kPyrTH + 3; // staged source window: 96 columns x 67 rows
+constexpr int kPyrSrcBytes = (kPyrSW * kPyrSH + 127) / 128 * 128; // one u8 buffer, 128-byte multiple
+constexpr int kPyrHalf = kPyrSW / 2;              // floats per row of each fp32 half
+constexpr size_t kPyrSmem = 2 * (size_t)kPyrSrcBytes + 2 * sizeof(float) * kPyrSH * kPyrHalf;
 struct PyrWeights { float w[25]; };
 
 __global__ void __launch_bounds__(kPyrTX *kPyrTY)
-pyramid_level_kernel(LevelImage src, uint8_t *__restrict__ dst, int drows, int dcols, int dpitch,
-                     PyrWeights kw, int trow_begin, int trow_end) {
-  constexpr int TH = kPyrTY * kPyrK;                             // 32 target rows per CTA
-  constexpr int SW16 = 6, SH = 2 * TH + 3;                       // 6 x 16 px = 96 source columns x 67 rows
-  constexpr int SP = SW16 * 8;                                   // floats per row of each half
-  __shared__ __align__(16) float tE[SH][SP], tO[SH][SP];         // even / odd source columns
-  const int tx = threadIdx.x, ty = threadIdx.y;
+pyramid_level_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t *__restrict__ dst, int drows, int dcols,
+                     int dpitch, PyrWeights kw, int trow_begin, int trow_end) {
+  extern __shared__ __align__(128) uint8_t pyr_smem[];
+  uint8_t *raw = pyr_smem;                                                        // [2][kPyrSrcBytes]
+  float(*tE)[kPyrHalf] = reinterpret_cast<float(*)[kPyrHalf]>(pyr_smem + 2 * kPyrSrcBytes); // even source columns
+  float(*tO)[kPyrHalf] = tE + kPyrSH;                                             // odd source columns
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kPyrTX + tx;
   // only target rows [trow_begin, trow_end) are produced (a GPU that holds a band of the image)
-  const int ox = blockIdx.x * kPyrTX, oy = trow_begin + blockIdx.y * TH; // target origin
-  const int sx0 = 2 * ox - 16, sy0 = 2 * oy - 2;                 // staged window origin (x 16-byte aligned)
-  for (int idx = ty * kPyrTX + tx; idx < SH * SW16; idx += kPyrTX * kPyrTY) {
-    const int r = idx / SW16, c16 = idx - r * SW16;
-    const int sx = sx0 + 16 * c16, sy = sy0 + r;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    // a 16-byte chunk is either wholly inside the pitch or wholly outside (pitch is a multiple of 128);
-    // columns beyond the image inside the pitch are never used by a non-border target pixel
-    if (sx >= 0 && sy >= 0 && sx + 15 < src.pitch && sy < src.rows)
-      v = __ldg(reinterpret_cast<const uint4 *>(src.ptr + (size_t)sy * src.pitch + sx));
-    float4 *e = reinterpret_cast<float4 *>(&tE[r][8 * c16]), *o = reinterpret_cast<float4 *>(&tO[r][8 * c16]);
-    e[0] = make_float4(u8_to_float(v.x, 0), u8_to_float(v.x, 2), u8_to_float(v.y, 0), u8_to_float(v.y, 2));
-    o[0] = make_float4(u8_to_float(v.x, 1), u8_to_float(v.x, 3), u8_to_float(v.y, 1), u8_to_float(v.y, 3));
-    e[1] = make_float4(u8_to_float(v.z, 0), u8_to_float(v.z, 2), u8_to_float(v.w, 0), u8_to_float(v.w, 2));
-    o[1] = make_float4(u8_to_float(v.z, 1), u8_to_float(v.z, 3), u8_to_float(v.w, 1), u8_to_float(v.w, 3));
+  const int ntx = (dcols + kPyrTX - 1) / kPyrTX, nty = (trow_end - trow_begin + kPyrTH - 1) / kPyrTH;
+  const int n_tiles = ntx * nty;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const int ti = ox + tx, tj0 = oy + ty * kPyrK;
-  if (ti >= dcols) return;
-  float acc[kPyrK];
+  // staged window of a tile: columns from 2 ox - 16 (16-byte aligned for TMA), rows from 2 oy - 2
+  auto issue = [&](int tile, int b) {
+    const int bx = tile % ntx, by = tile / ntx;
+    mbar_expect_tx(&bar[b], kPyrSW * kPyrSH);
+    tma_load_2d(raw + b * kPyrSrcBytes, &src_map, 2 * bx * kPyrTX - 16, 2 * (trow_begin + by * kPyrTH) - 2, &bar[b]);
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles && tid == 0) issue(tile, 0);
+  for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+    const int b = it & 1;
+    // buffer b ^ 1 was last read by the conversion of iteration it - 1, which every thread left through the
+    // barrier that follows it
+    if (tile + (int)gridDim.x < n_tiles && tid == 0) issue(tile + gridDim.x, b ^ 1);
+    mbar_wait(&bar[b], (it >> 1) & 1);
+    const uint8_t *rb = raw + b * kPyrSrcBytes;
+    for (int idx = tid; idx < kPyrSH * (kPyrSW / 16); idx += kPyrTX * kPyrTY) {
+      const int r = idx / (kPyrSW / 16), c16 = idx - r * (kPyrSW / 16);
+      const uint4 v = *reinterpret_cast<const uint4 *>(rb + r * kPyrSW + 16 * c16);
+      float4 *e = reinterpret_cast<float4 *>(&tE[r][8 * c16]), *o = reinterpret_cast<float4 *>(&tO[r][8 * c16]);
+      e[0] = make_float4(u8_to_float(v.x, 0), u8_to_float(v.x, 2), u8_to_float(v.y, 0), u8_to_float(v.y, 2));
+      o[0] = make_float4(u8_to_float(v.x, 1), u8_to_float(v.x, 3), u8_to_float(v.y, 1), u8_to_float(v.y, 3));
+      e[1] = make_float4(u8_to_float(v.z, 0), u8_to_float(v.z, 2), u8_to_float(v.w, 0), u8_to_float(v.w, 2));
+      o[1] = make_float4(u8_to_float(v.z, 1), u8_to_float(v.z, 3), u8_to_float(v.w, 1), u8_to_float(v.w, 3));
+    }
+    __syncthreads();
+    const int bx = tile % ntx, by = tile / ntx;
+    const int ti = bx * kPyrTX + tx, tj0 = trow_begin + by * kPyrTH + ty * kPyrK;
+    if (ti < dcols) {
+      float acc[kPyrK];
 #pragma unroll
-  for (int t = 0; t < kPyrK; ++t) acc[t] = 0.f;
-  // source column of tap di: 2 ti - 2 + di = sx0 + (2 tx + 14 + di): even di -> tE[tx + 7 + di/2], odd -> tO[tx + 7 + (di-1)/2]
+      for (int t = 0; t < kPyrK; ++t) acc[t] = 0.f;
+      // source column of tap di: 2 ti - 2 + di = window column 2 tx + 14 + di: even di -> tE[tx + 7 + di/2], odd -> tO[tx + 7 + (di-1)/2]
 #pragma unroll
-  for (int r = 0; r < 2 * kPyrK + 3; ++r) {
-    const float *rE = tE[2 * ty * kPyrK + r] + tx + 7, *rO = tO[2 * ty * kPyrK + r] + tx + 7;
-    const float s0 = rE[0], s1 = rO[0], s2 = rE[1], s3 = rO[1], s4 = rE[2];
+      for (int r = 0; r < 2 * kPyrK + 3; ++r) {
+        const float *rE = tE[2 * ty * kPyrK + r] + tx + 7, *rO = tO[2 * ty * kPyrK + r] + tx + 7;
+        const float s0 = rE[0], s1 = rO[0], s2 = rE[1], s3 = rO[1], s4 = rE[2];
 #pragma unroll
-    for (int t = 0; t < kPyrK; ++t) {
-      const int dj = r - 2 * t; // row of target t's window
-      if (dj >= 0 && dj < 5) {
-        acc[t] = __fadd_rn(acc[t], __fmul_rn(s0, kw.w[dj * 5 + 0]));
-        acc[t] = __fadd_rn(acc[t], __fmul_rn(s1, kw.w[dj * 5 + 1]));
-        acc[t] = __fadd_rn(acc[t], __fmul_rn(s2, kw.w[dj * 5 + 2]));
-        acc[t] = __fadd_rn(acc[t], __fmul_rn(s3, kw.w[dj * 5 + 3]));
-        acc[t] = __fadd_rn(acc[t], __fmul_rn(s4, kw.w[dj * 5 + 4]));
+        for (int t = 0; t < kPyrK; ++t) {
+          const int dj = r - 2 * t; // row of target t's window
+          if (dj >= 0 && dj < 5) {
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(s0, kw.w[dj * 5 + 0]));
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(s1, kw.w[dj * 5 + 1]));
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(s2, kw.w[dj * 5 + 2]));
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(s3, kw.w[dj * 5 + 3]));
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(s4, kw.w[dj * 5 + 4]));
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kPyrK; ++t) {
+        const int tj = tj0 + t;
+        if (tj >= drows || tj >= trow_end) break;
+        const bool interior = ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1;
+        dst[(size_t)tj * dpitch + ti] = interior ? (uint8_t)__float2uint_rz(acc[t]) : (uint8_t)0;
       }
     }
-  }
-#pragma unroll
-  for (int t = 0; t < kPyrK; ++t) {
-    const int tj = tj0 + t;
-    if (tj >= drows || tj >= trow_end) break;
-    const bool interior = ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1;
-    dst[(size_t)tj * dpitch + ti] = interior ? (uint8_t)__float2uint_rz(acc[t]) : (uint8_t)0;
+    __syncthreads(); // the fp32 tile is free for the next conversion
   }
 }
 

@@ -16,8 +16,6 @@
 // The moments are expanded to the full upper-triangular A, b with the lane's dx powers only when
 // the warp changes strip or the evaluation ends.
 #pragma once
-#include <cuda.h>
-
 #include "dic_kernels.cuh"
 
 namespace dic {
@@ -49,30 +47,6 @@ struct alignas(64) TileMaps {
   CUtensorMap def[kMaxLevels]; // deformed image, box kPatchW x kPatchH
   CUtensorMap und[kMaxLevels]; // reference image, box kUndW x kTileH
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// bounded: a transfer that never lands must end the launch with an error, not hang the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  unsigned int spins = 0;
-  while (!mbar_try_wait(bar, parity))
-    if (++spins > (1u << 24)) __trap();
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
 
 // A warp's staging state: buffer k & 1 serves the k-th staged unit, its mbarrier phase is (k >> 1) & 1.
 struct WarpStage {
