@@ -69,6 +69,8 @@ struct dic_engine {
   int num_sms = 0;
   cudaStream_t stream = nullptr, img_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_img = nullptr, ev_gn = nullptr, ev_copy = nullptr;
+  cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr; // around the whole GPU side of a correlate (copies included)
+  float last_step_ms = 0.f;
   PyramidSlot pyr[5];
   int role[5] = {0, 1, 2, 3, 4}; // role (0 und, 1 def, 2 nxt, 3 / 4 staged und / def of the next pair) -> slot
   int start = 0, step = 1, stop = 0;
@@ -767,6 +769,7 @@ dic_engine *dic_create(int device) {
             cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
+            cudaEventCreate(&e->ev_step0) == cudaSuccess && cudaEventCreate(&e->ev_step1) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_gn, cudaEventDisableTiming) == cudaSuccess;
   e->max_grid = e->num_sms * 8;
@@ -798,6 +801,8 @@ void dic_destroy(dic_engine *e) {
   if (e->h_guess) cudaFreeHost(e->h_guess);
   cudaFree(e->d_work); cudaFree(e->d_partials); cudaFree(e->d_scratch);
   cudaFree(e->d_counts); cudaFree(e->d_offsets); cudaFree(e->d_stage);
+  if (e->ev_step0) cudaEventDestroy(e->ev_step0);
+  if (e->ev_step1) cudaEventDestroy(e->ev_step1);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_img) cudaEventDestroy(e->ev_img);
@@ -1424,6 +1429,7 @@ static int enqueue_correlate(dic_engine *e, int first, int count, const float *g
     for (int k = 0; k < kMaxParams; ++k) g[k] = k < np ? guesses[(size_t)i * np + k] : 0.f;
     e->sectors[first + i].pending = true;
   }
+  CU_TRY(e, cudaEventRecord(e->ev_step0, e->stream));
   CU_TRY(e, cudaMemcpyAsync(e->d_guess + (size_t)first * kMaxParams, e->h_guess + (size_t)first * kMaxParams,
                             sizeof(float) * kMaxParams * count, cudaMemcpyHostToDevice, e->stream));
   CU_TRY(e, cudaEventRecord(e->ev0, e->stream));
@@ -1434,6 +1440,7 @@ static int enqueue_correlate(dic_engine *e, int first, int count, const float *g
   e->timing_pending = true;
   CU_TRY(e, cudaMemcpyAsync(e->h_results + first, e->d_results + first, sizeof(dic_result) * count,
                             cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaEventRecord(e->ev_step1, e->stream));
   return DIC_OK;
 }
 
@@ -1441,6 +1448,7 @@ static int collect(dic_engine *e, int first, int count, float *guesses_out, dic_
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   if (e->timing_pending) {
     cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+    cudaEventElapsedTime(&e->last_step_ms, e->ev_step0, e->ev_step1);
     e->timing_pending = false;
   }
   const int np = np_of(e);
@@ -1668,6 +1676,7 @@ int dic_get_cta_times(dic_engine *e, unsigned long long *out, int cap) {
   return n;
 }
 float dic_last_correlate_ms(dic_engine *e) { return e ? e->last_ms : 0.f; }
+float dic_last_step_ms(dic_engine *e) { return e ? e->last_step_ms : 0.f; }
 int64_t dic_kernel_launches(const dic_engine *e) { return e ? (int64_t)e->launches.load() : 0; }
 void *dic_correlation_stream(dic_engine *e) { return e ? (void *)e->stream : nullptr; }
 int dic_synchronize(dic_engine *e) {

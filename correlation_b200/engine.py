@@ -72,7 +72,7 @@ EXPORTS = [
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
-    "dic_last_correlate_ms", "dic_get_timeline", "dic_get_cta_times", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
+    "dic_last_correlate_ms", "dic_last_step_ms", "dic_get_timeline", "dic_get_cta_times", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
 ]
 
 
@@ -132,6 +132,7 @@ def load_library():
         "dic_evaluate": (I, [P, I, I, P, P, P, fp, C.POINTER(I)]),
         "dic_solve_step": (I, [P, P, P, F, F, P]),
         "dic_last_correlate_ms": (F, [P]),
+        "dic_last_step_ms": (F, [P]),
         "dic_get_timeline": (I, [P, P, I]),
         "dic_get_cta_times": (I, [P, P, I]),
         "dic_kernel_launches": (I64, [P]),
@@ -408,6 +409,9 @@ class CudaEngine:
 
     def last_correlate_ms(self):
         return float(self.lib.dic_last_correlate_ms(self.h))
+
+    def last_step_ms(self):
+        return float(self.lib.dic_last_step_ms(self.h))
 
     def timeline(self):
         m = np.zeros((129, 4), np.uint64)

@@ -15,7 +15,7 @@ import json, sys
 w, n = sys.argv[1], sys.argv[2]
 try:
     d = json.loads(open(f"gpurun_out/bench{n}_{w}.json").read().strip().splitlines()[-1])
-    print(f"{w} x{n}: value {d['value']/1e9:.1f} G  {d['ms_per_step']:.3f} ms/step  e2e {d['e2e']['value']/1e9:.1f} G ({d['e2e'].get('ms_per_step', 0):.3f} ms, h2d {d['e2e']['h2d_bytes_per_step']/1e6:.1f} MB)  kernel {d['roofline']['kernel_ms_per_step']:.3f} ms  clocks {d['clocks'].get('sm_mhz')}")
+    print(f"{w} x{n}: host {d.get('host_ms_per_step', 0):.3f} ms  value {d['value']/1e9:.1f} G  {d['ms_per_step']:.3f} ms/step  e2e {d['e2e']['value']/1e9:.1f} G ({d['e2e'].get('ms_per_step', 0):.3f} ms, h2d {d['e2e']['h2d_bytes_per_step']/1e6:.1f} MB)  kernel {d['roofline']['kernel_ms_per_step']:.3f} ms  clocks {d['clocks'].get('sm_mhz')}")
 except Exception as ex:
     print(w, n, "failed", ex)
 PY
