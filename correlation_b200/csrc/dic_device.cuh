@@ -70,7 +70,7 @@ struct GridWork {
   unsigned int slow_units; // units of the last launch that took the per-pixel (non-staged) path
   float pub_tot[96];       // row-split only: totals over all GPUs, published by CTA 0
   double acc[3][96];       // grid-wide sums of evaluations e % 3 (fp64 atomics)
-  // row-split of one domain over several GPUs: every rank's master adds its sums to
+  // row-split of one domain over several GPUs: CTA 0 of every rank adds the rank's sums to
   // every peer's mailbox over NVLink, then all ranks add the rows in rank order (bitwise identical)
   int rs_rank, rs_world;
   unsigned int rs_seq;             // evaluations exchanged so far (same on all ranks)

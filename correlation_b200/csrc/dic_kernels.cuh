@@ -242,7 +242,7 @@ __device__ __forceinline__ void evaluate_list(const SolveSettings &cfg, const Se
 //
 // One domain split by pixel rows over several GPUs: each evaluation ends with a sum of the
 // (n^2 + n)/2 + n + 2 normal-equation values over the ranks. Done here, inside the persistent
-// kernel, by the master CTA's warp 0: write this rank's sums into slot [parity][rank] of every
+// kernel, by warp 0 of CTA 0: write this rank's sums into slot [parity][rank] of every
 // peer's mailbox (plain stores to peer-mapped memory: NVLink), system fence, release-store the
 // sequence number; then wait for every peer's slot of this evaluation in the local mailbox and add
 // the rows IN RANK ORDER, so that every rank gets bitwise the same totals and takes the same LM
@@ -412,8 +412,8 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
   }
 }
 
-// Start of a sector: every CTA derives the first command locally; the owner of the LM state
-// (master CTA in grid mode, the CTA itself in batch mode) initialises it.
+// Start of a sector: every CTA derives the first command locally and initialises its own copy of the
+// LM state (grid mode: all CTAs keep identical copies; batch mode: the CTA owns the sector).
 template <int MODEL, bool GRID>
 __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &sh, const SolveSettings &cfg,
                                              const SectorDev *sec, const float *guess, GridWork *work,

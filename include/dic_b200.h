@@ -220,7 +220,7 @@ int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float la
 float dic_last_correlate_ms(dic_engine *e);
 /* the same over the whole GPU side of the call: guess upload, solve kernel(s), result download */
 float dic_last_step_ms(dic_engine *e);
-/* master-CTA timeline of the last single-sector correlate: per evaluation 4 device timestamps (ns):
+/* CTA 0's timeline of the last single-sector correlate: per evaluation 4 device timestamps (ns):
  * pass start, own pass done, all CTAs arrived, LM step published. Returns the evaluation count. */
 int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap);
 /* load-balance probe: per CTA of the last single-sector correlate, the device time (ns) at which its
