@@ -15,7 +15,7 @@
  *                            polygon_class.cpp (blob: ear clipping + scanline)
  *
  * It is pinned against the UNMODIFIED reference compiled into oracle/_ref/libdic_ref.so
- * (tests/test_oracle_vs_ref.py, bit-for-bit on parameters, chi, iterations, A, b, pyramid
+ * (tests/test_oracle.py, bit-for-bit on parameters, chi, iterations, A, b, pyramid
  * levels and point lists) and against the golden fixtures generated from that build
  * (tests/golden/). Deliberate differences, none of which changes an in-bounds result:
  *   - 64-bit indices and on-the-fly bicubic coefficients instead of the reference's lazy
