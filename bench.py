@@ -92,6 +92,14 @@ def subset_boxes(lo, hi, n):
     return boxes
 
 
+def upload_band(y_first, y_last, rows, pyramid_stop):
+    """Image rows [begin, end) a rank must hold to work on domain rows y_first..y_last: the domain plus a halo for
+    the workloads' displacement (<= 64 px), the 2-pixel bicubic support and 2^(level + 2) rows of pyramid support
+    at every cut (dic_stage_next_pair_rows)."""
+    halo = 64 + (8 << pyramid_stop)
+    return max(0, y_first - halo), min(rows, y_last + 1 + halo)
+
+
 # ------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
@@ -423,13 +431,10 @@ def main():
     # a rank that owns a band of the image (sharded subsets, row-split domain) transfers only its rows plus
     # a halo for displacement, bicubic support and pyramid support (dic_stage_next_pair_rows)
     band = None
-    if world > 1 and d[0] in ("rowsplit", "subsets"):
-        # displacement of the workload (<= 64 px) + bicubic halo + 2^(level + 2) rows of pyramid support per cut
-        halo = 64 + (8 << w["pyramid"][2])
-        if d[0] == "rowsplit":
-            band = (max(0, b0 - halo), min(rows, b1 + 1 + halo))
-        else:
-            band = (max(0, min(bx[1] for bx in boxes) - halo), min(rows, max(bx[3] for bx in boxes) + 1 + halo))
+    if world > 1 and d[0] == "rowsplit":
+        band = upload_band(b0, b1, rows, w["pyramid"][2])
+    elif world > 1 and d[0] == "subsets":
+        band = upload_band(min(bx[1] for bx in boxes), max(bx[3] for bx in boxes), rows, w["pyramid"][2])
     h2d_bytes = 2 * cols * ((band[1] - band[0]) if band else rows)
 
     def stage_pair():

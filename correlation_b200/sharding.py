@@ -3,8 +3,9 @@
 Two ways the path shards:
   * independent units -- subdivision subsets of a rectangle, annular sectors, separate polygon
     domains (the reference loops over them serially, manager_class.cpp:304-547): contiguous
-    blocks of sector ids per rank, images replicated, NO collective on the data path; one gather
-    of the (<= 168 B) result records at the end;
+    blocks of sector ids per rank (shard_range) or, for a grid of subsets, whole rows of subsets
+    per rank (shard_grid_rows: the rank then needs only a band of image rows), NO collective on
+    the data path; one gather of the (<= 176 B) result records at the end;
   * one huge domain -- pixel rows split into bands of equal pixel count; every evaluation ends
     with an all-reduce(sum) of the (n^2 + n)/2 + n + 2 normal-equation floats and every rank runs
     the identical LM state machine (see correlation_b200/rowsplit.py).

@@ -29,3 +29,17 @@ def test_subset_boxes_follow_manager_arithmetic():
     assert w == {125}                       # (8064 / 64 - 1) / 2 = 62 -> 2 * 62 + 1
     assert boxes[0][:2] == (65, 65) and boxes[1][0] == boxes[0][0]  # centre int(.5 + 64 + 62.5) = 127; sector = i * vs + j, j (y) fastest
     assert all(b[0] >= 64 and b[2] <= 8128 for b in boxes)
+
+
+def test_upload_band_covers_domain_plus_halo_and_stays_inside_the_image():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.upload_band(0, 100, 8192, 2) == (0, 100 + 1 + 64 + 32)
+    b = bench.upload_band(4000, 5000, 8192, 2)
+    assert b == (4000 - 96, 5001 + 96)
+    assert bench.upload_band(8000, 8191, 8192, 4) == (8000 - 192, 8192)
+    # every level's valid rows (two fewer per level at each cut) still cover the domain at that level
+    lo, hi = bench.upload_band(4000, 5000, 8192, 4)
+    for lv in range(1, 5):
+        lo, hi = (lo + 3) // 2, (hi - 3) // 2 + 1
+        assert lo <= (4000 >> lv) - 2 and hi >= (5000 >> lv) + 3
