@@ -62,19 +62,20 @@ struct Mailbox {
 // adds its sums to acc[e % 3] with fp64 atomics and bumps `arrive` (release); every CTA then waits for
 // the count, reads the same totals and runs the SAME LM step + solve on its own copy of the state in
 // shared memory -- bitwise identical decisions everywhere, no master, no publish / re-read hop.
-// The host zeroes `arrive` and `acc` before each launch; CTA 0 clears acc[(e + 2) % 3] after barrier e.
+// `arrive` and `acc` are zero between launches: CTA 0 clears acc[(e + 2) % 3] after barrier e and the last CTA to
+// leave the kernel clears the rest (see `departed`).
 struct GridWork {
   unsigned int arrive;     // CTAs that have delivered their sums, cumulative over the launch
-  unsigned int generation; // row-split only: bumped by CTA 0 after it has published the cross-GPU totals
+  unsigned int departed;   // CTAs that have left the kernel: the last one re-zeroes arrive / abort / acc,
+                           // so a launch needs no memset in front of it (nothing of a correlate touches a copy engine)
   int abort;               // set when a grid-barrier wait timed out (never expected)
   unsigned int slow_units; // units of the last launch that took the per-pixel (non-staged) path
-  float pub_tot[96];       // row-split only: totals over all GPUs, published by CTA 0
+  int img_error;           // set by the pyramid kernel when a TMA transfer never landed (sticky until read by the host)
   double acc[3][96];       // grid-wide sums of evaluations e % 3 (fp64 atomics)
   // row-split of one domain over several GPUs: CTA 0 of every rank adds the rank's sums to
   // every peer's mailbox over NVLink, then all ranks add the rows in rank order (bitwise identical)
   int rs_rank, rs_world;
-  unsigned int rs_seq;             // evaluations exchanged so far (same on all ranks)
-  int rs_error;                    // set when a peer did not answer in time
+  unsigned int rs_seq;             // evaluations exchanged so far (same on all ranks); carried from launch to launch
   struct Mailbox *rs_local;        // this rank's mailbox (peers write into it)
   struct Mailbox *rs_peer[kMaxRanks]; // peer-mapped mailboxes, index = rank
   // CTA 0's timeline of the last launch (ns, %globaltimer): per evaluation
@@ -136,11 +137,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded: a transfer that never lands must end the launch with an error, not hang the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// bounded by TIME (2 s on %globaltimer, looked at every 4096 polls): a transfer that never lands must end the
+// launch with an error code, not hang the GPU and not poison the context with a trap. Returns false on timeout;
+// the caller raises its kernel's error flag (DIC_ERROR_CUDA) and stops consuming staged data.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
   unsigned int spins = 0;
-  while (!mbar_try_wait(bar, parity))
-    if (++spins > (1u << 24)) __trap();
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffu) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) return false;
+    }
+  }
+  return true;
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -477,7 +493,10 @@ __device__ __forceinline__ void block_reduce(float *acc, float *red, float *out)
 // matrix row per lane, columns exchanged by warp shuffles (replaces the reference's cuSOLVER
 // potrf/potrs, cuda_solver.cu:119-149, and the CPU's Eigen QR). tot: packed upper A, then b
 // (shared memory). smem: NP*NP floats of scratch for the transposed back-substitution.
-// Returns false (warp-uniform) when a pivot is not positive.
+// A direction whose diagonal or pivot is not positive (textureless / saturated subset: A has an exactly zero
+// row) gets a ZERO step and is decoupled from the others -- what the rank-truncating column-pivoted QR of the CPU
+// engine returns (correlation_class.cpp:742-747): the LM loop then ends with error_none and unchanged parameters
+// in that direction instead of a solver error. Always returns true (kept bool for the call sites).
 template <int NP>
 __device__ bool warp_solve(const float *tot, float scaling, float lambda, float *smem, float *dp) {
   const int lane = threadIdx.x & 31;
@@ -494,8 +513,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
   float dii = 0.f;
 #pragma unroll
   for (int j = 0; j < NP; ++j) dii = (j == i) ? a[j] : dii;
-  if (__any_sync(full, lane < NP && !(dii > 0.f))) return false;
-  const float sc = 1.0f / sqrtf(dii);
+  const float sc = dii > 0.f ? 1.0f / sqrtf(dii) : 0.f; // zero row and column: the direction drops out
 #pragma unroll
   for (int j = 0; j < NP; ++j) a[j] *= sc * __shfl_sync(full, sc, j);
   rhs *= sc;
@@ -503,8 +521,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const float dk = __shfl_sync(full, a[k], k);
-    if (!(dk > 1e-12f)) return false;
-    const float inv = rsqrtf(dk); // 2 ulp is far below the fp32 conditioning noise of the system
+    const float inv = dk > 1e-12f ? rsqrtf(dk) : 0.f; // 2 ulp is far below the fp32 conditioning noise of the system
     const float lik = a[k] * inv;
     a[k] = lik;
 #pragma unroll
@@ -516,7 +533,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
   float lii = 1.f;
 #pragma unroll
   for (int j = 0; j < NP; ++j) lii = (j == i) ? a[j] : lii;
-  const float rinv = __frcp_rn(lii);
+  const float rinv = lii > 0.f ? __frcp_rn(lii) : 0.f;
   // forward substitution L y = rhs (column oriented)
   float y = rhs;
 #pragma unroll

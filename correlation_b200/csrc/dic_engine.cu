@@ -7,6 +7,7 @@
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only; ranges are free unless a profiler injects the NVTX library
 
 #include <algorithm>
 #include <atomic>
@@ -25,6 +26,13 @@
 using namespace dic;
 
 namespace {
+
+// NVTX ranges where the reference has them (cuda_class.cu:133-326 per level / solve / update, :497-554 image
+// reads, cuda_polygon.cuh:443, cuda_pyramid.cuh:58): one range per C-ABI call that enqueues device work.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 enum SectorKind { SK_NONE = 0, SK_RECT, SK_ANNULAR, SK_BLOB, SK_POINTS };
 
@@ -69,6 +77,7 @@ struct dic_engine {
   int num_sms = 0;
   cudaStream_t stream = nullptr, img_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_img = nullptr, ev_gn = nullptr, ev_copy = nullptr;
+  cudaEvent_t ev_rot = nullptr; // correlation-stream position at the last pyramid rotation (see dic_reset_next_pyramid)
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr; // around the whole GPU side of a correlate (copies included)
   float last_step_ms = 0.f;
   PyramidSlot pyr[5];
@@ -96,7 +105,12 @@ struct dic_engine {
   float *d_guess = nullptr;
   dic_result *d_results = nullptr;
   dic_result *h_results = nullptr; // pinned
-  float *h_guess = nullptr;        // pinned
+  float *h_guess = nullptr;        // pinned + mapped: batch kernels read their guesses from here (zero-copy)
+  float *h_guess_dev = nullptr;    // device-side address of h_guess
+  int cluster_mode = 0;            // batch launches: 0 auto, 1 one CTA per sector, 2 one CTA pair per sector
+  std::vector<void *> bulk_blocks; // device blocks shared by the sectors of a dic_reset_polygon_rect_grid call
+  void *grid_lists = nullptr, *grid_tiles = nullptr, *grid_desc = nullptr;
+  size_t cap_grid_lists = 0, cap_grid_tiles = 0, cap_grid_desc = 0;
   int cap_sectors = 0;
   GridWork *d_work = nullptr;
   float *d_partials = nullptr;
@@ -240,7 +254,7 @@ int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st, int r
       const int n_tiles = ((dst.cols + kPyrTX - 1) / kPyrTX) * ((te - tb + kPyrTH - 1) / kPyrTH);
       const int grid = std::max(1, std::min(n_tiles, e->num_sms * 5)); // persistent: 5 CTAs of 38 KB fit an SM
       pyramid_level_kernel<<<grid, block, kPyrSmem, st>>>(s.tm_pyr[l - 1], const_cast<uint8_t *>(dst.ptr), dst.rows,
-                                                          dst.cols, dst.pitch, kw, tb, te);
+                                                          dst.cols, dst.pitch, kw, tb, te, &e->d_work->img_error);
       e->launches++;
     }
     rb = tb; re = std::max(tb, te);
@@ -308,7 +322,7 @@ int ensure_sector_capacity(dic_engine *e, int n) {
   CU_TRY(e, cudaMemset(dt, 0, sizeof(SectorTiles) * cap));
   CU_TRY(e, cudaMalloc(&dr, sizeof(dic_result) * cap));
   CU_TRY(e, cudaMallocHost(&hr, sizeof(dic_result) * cap));
-  CU_TRY(e, cudaMallocHost(&hg, sizeof(float) * kMaxParams * cap));
+  CU_TRY(e, cudaHostAlloc(&hg, sizeof(float) * kMaxParams * cap, cudaHostAllocMapped | cudaHostAllocPortable));
   CU_TRY(e, cudaMallocHost(&hs, sizeof(SectorDev) * cap));
   CU_TRY(e, cudaMallocHost(&ht, sizeof(SectorTiles) * cap));
   memset(hs, 0, sizeof(SectorDev) * cap);
@@ -334,6 +348,12 @@ int ensure_sector_capacity(dic_engine *e, int n) {
   e->h_sectors = hs; e->h_sector_tiles = ht;
   e->d_sector_tiles = dt;
   e->d_sectors = ds; e->d_guess = dg; e->d_results = dr; e->h_results = hr; e->h_guess = hg;
+  void *hg_dev = nullptr;
+  CU_TRY(e, cudaHostGetDevicePointer(&hg_dev, hg, 0));
+  e->h_guess_dev = static_cast<float *>(hg_dev);
+  // the memsets / copies above ran on the legacy default stream, which the engine's non-blocking streams do
+  // not wait for: drain the device once (this path runs only when the sector table grows)
+  CU_TRY(e, cudaDeviceSynchronize());
   e->cap_sectors = cap;
   e->sectors.resize(cap);
   return DIC_OK;
@@ -581,16 +601,29 @@ int build_tiles(dic_engine *e, Sector &s, bool may_have_duplicates) {
   return DIC_OK;
 }
 
-template <int MODEL, int INTERP, int MODE>
-int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
+SolveSettings solve_settings(const dic_engine *e) {
   SolveSettings cfg;
   memset(&cfg, 0, sizeof(cfg));
   const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
   for (int l = 0; l < kMaxLevels; ++l) { cfg.und[l] = u.lev[l]; cfg.def[l] = d.lev[l]; }
   cfg.start = e->start; cfg.step = e->step; cfg.stop = e->stop;
   cfg.max_iters = e->max_iters; cfg.precision = e->precision;
+  return cfg;
+}
+
+// the guess of a single-sector launch rides in the kernel parameters (no copy-engine work per correlate)
+GuessParam guess_param(const dic_engine *e, int first) {
+  GuessParam g;
+  memcpy(g.v, e->h_guess + (size_t)first * kMaxParams, sizeof(g.v));
+  return g;
+}
+
+template <int MODEL, int INTERP, int MODE>
+int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
+  SolveSettings cfg = solve_settings(e);
   const SectorDev *sectors = e->d_sectors;
-  const float *guesses = e->d_guess;
+  const float *guesses = e->h_guess_dev;
+  GuessParam g0 = guess_param(e, first);
   dic_result *results = e->d_results;
   GridWork *work = e->d_work;
   if (grid_mode) {
@@ -604,8 +637,7 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
     int want = (int)std::min<long>((n0 + kThreads * 4 - 1) / (kThreads * 4), (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
-    CU_TRY(e, cudaMemsetAsync(work, 0, offsetof(GridWork, rs_rank), e->stream)); // arrive, abort, acc
-    void *args[] = {&cfg, &sectors, &guesses, &results, &first, &one, &work};
+    void *args[] = {&cfg, &sectors, &guesses, &g0, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, 0, e->stream));
   } else {
     auto kern = gn_solve_kernel<MODEL, INTERP, MODE, false>;
@@ -613,25 +645,28 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
     int &per_sm = per_sm_cached[e->device & 15];
     if (per_sm == 0) CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
     int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
-    kern<<<grid, kThreads, 0, e->stream>>>(cfg, sectors, guesses, results, first, count, work);
+    kern<<<grid, kThreads, 0, e->stream>>>(cfg, sectors, guesses, g0, results, first, count, work);
     CU_TRY(e, cudaGetLastError());
   }
   e->launches++;
   return DIC_OK;
 }
 
+// Wave efficiency of `units` equal work items on `slots` concurrent slots.
+double wave_efficiency(long units, long slots) {
+  if (units <= 0 || slots <= 0) return 1.0;
+  const double waves = (double)units / (double)slots;
+  return waves / std::ceil(waves);
+}
 
 template <int MODEL, int MODE>
 int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
-  SolveSettings cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  SolveSettings cfg = solve_settings(e);
   const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
-  for (int l = 0; l < kMaxLevels; ++l) { cfg.und[l] = u.lev[l]; cfg.def[l] = d.lev[l]; }
-  cfg.start = e->start; cfg.step = e->step; cfg.stop = e->stop;
-  cfg.max_iters = e->max_iters; cfg.precision = e->precision;
   const SectorDev *sectors = e->d_sectors;
   const SectorTiles *stiles = e->d_sector_tiles;
-  const float *guesses = e->d_guess;
+  const float *guesses = e->h_guess_dev;
+  GuessParam g0 = guess_param(e, first);
   dic_result *results = e->d_results;
   GridWork *work = e->d_work;
   TileMaps maps;
@@ -640,7 +675,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
   const size_t smem = tiles_dyn_smem(NACC);
   if (grid_mode) {
-    auto kern = gn_solve_tiles_kernel<MODEL, MODE, true>;
+    auto kern = gn_solve_tiles_kernel<MODEL, MODE, true, 1>;
     static int per_sm_cached[16] = {0}; // per device: attribute + occupancy queried once, not per launch
     int &per_sm = per_sm_cached[e->device & 15];
     if (per_sm == 0) {
@@ -653,19 +688,42 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     int want = (int)std::min<long>((nt + kWarpsPerCta - 1) / kWarpsPerCta, (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
-    CU_TRY(e, cudaMemsetAsync(work, 0, offsetof(GridWork, rs_rank), e->stream)); // arrive, abort, acc
-    void *args[] = {&cfg, &maps, &sectors, &stiles, &guesses, &results, &first, &one, &work};
+    void *args[] = {&cfg, &maps, &sectors, &stiles, &guesses, &g0, &results, &first, &one, &work};
     CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, smem, e->stream));
   } else {
-    auto kern = gn_solve_tiles_kernel<MODEL, MODE, false>;
+    auto kern1 = gn_solve_tiles_kernel<MODEL, MODE, false, 1>;
+    auto kern2 = gn_solve_tiles_kernel<MODEL, MODE, false, 2>;
     static int per_sm_cached[16] = {0};
     int &per_sm = per_sm_cached[e->device & 15];
     if (per_sm == 0) {
-      CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+      CU_TRY(e, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_TRY(e, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern1, kThreads, smem));
     }
-    int grid = std::max(1, std::min(count, std::max(1, per_sm) * e->num_sms));
-    kern<<<grid, kThreads, smem, e->stream>>>(cfg, maps, sectors, stiles, guesses, results, first, count, work);
+    const long slots = (long)std::max(1, per_sm) * e->num_sms;
+    // one CTA pair per sector halves the scheduling granule: worth it when the last wave of whole-sector CTAs
+    // would leave a good part of the GPU idle (a few hundred subsets per GPU; 4096 subsets fill 13.8 waves
+    // either way). 3 % is the measured price of the cluster barrier + the exchange per evaluation.
+    // The granule that matters is per SM (co-resident CTAs share the SM's issue slots, and a CTA alone on an SM in
+    // the last wave runs faster): 512 subsets on 148 SMs = 3.46 -> 4 rounds (86 %), 1024 halves = 6.92 -> 7 (99 %).
+    bool pair = e->cluster_mode == 2 ||
+                (e->cluster_mode == 0 && 0.97 * wave_efficiency(2L * count, e->num_sms) > wave_efficiency(count, e->num_sms) + 0.02);
+    if (pair) {
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3((unsigned)std::max(2L, std::min(2L * count, slots / 2 * 2)));
+      lc.blockDim = dim3(kThreads);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = e->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      CU_TRY(e, cudaLaunchKernelEx(&lc, kern2, cfg, maps, sectors, stiles, guesses, g0, results, first, count, work));
+    } else {
+      int grid = (int)std::max(1L, std::min((long)count, slots));
+      kern1<<<grid, kThreads, smem, e->stream>>>(cfg, maps, sectors, stiles, guesses, g0, results, first, count, work);
+    }
     CU_TRY(e, cudaGetLastError());
   }
   e->launches++;
@@ -714,11 +772,7 @@ int launch_solve_any(dic_engine *e, bool grid_mode, int first, int count) {
 
 template <int MODEL, int INTERP, int MODE>
 int launch_eval(dic_engine *e, int id, int level, const float *d_params, int grid) {
-  SolveSettings cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  const PyramidSlot &u = e->pyr[e->role[0]], &d = e->pyr[e->role[1]];
-  for (int l = 0; l < kMaxLevels; ++l) { cfg.und[l] = u.lev[l]; cfg.def[l] = d.lev[l]; }
-  cfg.start = e->start; cfg.step = e->step; cfg.stop = e->stop;
+  SolveSettings cfg = solve_settings(e);
   gn_eval_kernel<MODEL, INTERP, MODE><<<grid, kThreads, 0, e->stream>>>(cfg, e->d_sectors + id, level,
                                                                       d_params, e->d_partials);
   e->launches++;
@@ -771,7 +825,8 @@ dic_engine *dic_create(int device) {
             cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
             cudaEventCreate(&e->ev_step0) == cudaSuccess && cudaEventCreate(&e->ev_step1) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_gn, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&e->ev_gn, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_rot, cudaEventDisableTiming) == cudaSuccess;
   e->max_grid = e->num_sms * 8;
   ok = ok && cudaMalloc(&e->d_work, sizeof(GridWork)) == cudaSuccess &&
        cudaMemset(e->d_work, 0, sizeof(GridWork)) == cudaSuccess &&
@@ -792,6 +847,8 @@ void dic_destroy(dic_engine *e) {
     if (s.ebuf) cudaFree(s.ebuf);
   }
   for (char *c : e->arena_chunks) cudaFree(c);
+  for (void *b : e->bulk_blocks) cudaFree(b);
+  cudaFree(e->grid_lists); cudaFree(e->grid_tiles); cudaFree(e->grid_desc);
   if (e->h_sectors) cudaFreeHost(e->h_sectors);
   if (e->h_sector_tiles) cudaFreeHost(e->h_sector_tiles);
   cudaFree(e->d_sector_tiles); cudaFree(e->d_masks); cudaFree(e->d_mailbox);
@@ -807,6 +864,7 @@ void dic_destroy(dic_engine *e) {
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_img) cudaEventDestroy(e->ev_img);
   if (e->ev_gn) cudaEventDestroy(e->ev_gn);
+  if (e->ev_rot) cudaEventDestroy(e->ev_rot);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -882,6 +940,11 @@ int dic_reset_image_pyramids_device(dic_engine *e, const void *und, const void *
 int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols) {
   if (!e || !nxt) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
+  NvtxRange nvtx("dic_reset_next_pyramid");
+  // after a rotation the nxt slot is the previous und / def image, which solves enqueued BEFORE the rotation may
+  // still be reading: the upload waits for the correlation stream's position at that rotation (not for the
+  // current frame's solve, which is what this call is meant to overlap with)
+  CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_rot, 0));
   int rc = set_image(e, 2, nxt, rows, cols, cols, false, e->img_stream);
   if (rc) return rc;
   CU_TRY(e, cudaStreamSynchronize(e->img_stream));
@@ -890,6 +953,7 @@ int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols
 int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt, int rows, int cols, int pitch) {
   if (!e || !nxt) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
+  CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_rot, 0)); // see dic_reset_next_pyramid
   int rc = set_image(e, 2, nxt, rows, cols, pitch, true, e->img_stream);
   if (rc) return rc;
   CU_TRY(e, cudaEventRecord(e->ev_img, e->img_stream));
@@ -913,8 +977,10 @@ int dic_reset_def_pyramid_device(dic_engine *e, const void *def, int rows, int c
 int dic_make_und_pyramid_from_def(dic_engine *e) {
   if (!e) return DIC_ERROR_BAD_ARGUMENT;
   // pyramid_class.cpp:211-226: und takes def's images, def becomes empty
+  cudaSetDevice(e->device);
   std::swap(e->role[0], e->role[1]);
   e->pyr[e->role[1]].valid = false;
+  CU_TRY(e, cudaEventRecord(e->ev_rot, e->stream));
   return DIC_OK;
 }
 int dic_make_def_pyramid_from_nxt(dic_engine *e) {
@@ -925,6 +991,7 @@ int dic_make_def_pyramid_from_nxt(dic_engine *e) {
   CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_img, 0));
   std::swap(e->role[1], e->role[2]);
   e->pyr[e->role[2]].valid = false;
+  CU_TRY(e, cudaEventRecord(e->ev_rot, e->stream)); // everything that still reads the slot that is now `nxt`
   return DIC_OK;
 }
 
@@ -1154,6 +1221,129 @@ int dic_reset_polygon_rect(dic_engine *e, int id, int x0, int y0, int x1, int y1
 int dic_reset_polygon_rect_band(dic_engine *e, int id, int x0, int y0, int x1, int y1, int band_y0, int band_y1) {
   if (band_y1 < band_y0) return DIC_ERROR_BAD_ARGUMENT;
   return reset_rect_impl(e, id, x0, y0, x1, y1, std::max(y0, band_y0), std::min(y1, band_y1));
+}
+
+// A whole grid of rectangles in one go: what n calls of dic_reset_polygon_rect(first_id + k, boxes[4k..4k+3])
+// build (the subdivision loop of manager_class.cpp:274-336 issues exactly those calls on frame 0), with ONE list
+// kernel and ONE tile kernel over all sectors and levels, one descriptor upload and one upload of the sector
+// records -- 4096 subsets went from 3 launches + a sync each (138 ms) to a few launches in total.
+static int ensure_block(dic_engine *e, void **ptr, size_t *cap, size_t bytes) {
+  if (bytes <= *cap) return DIC_OK;
+  if (*ptr) CU_TRY(e, cudaFree(*ptr));
+  *ptr = nullptr; *cap = 0;
+  CU_TRY(e, cudaMalloc(ptr, bytes));
+  *cap = bytes;
+  return DIC_OK;
+}
+
+int dic_reset_polygon_rect_grid(dic_engine *e, int first_id, int n, const int *boxes) {
+  if (!e || !boxes || n <= 0 || first_id < 0 || first_id + n > (1 << 24)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  NvtxRange nvtx("dic_reset_polygon_rect_grid");
+  int rc = ensure_sector_capacity(e, first_id + n);
+  if (rc) return rc;
+  CU_TRY(e, cudaStreamSynchronize(e->stream)); // pinned mirrors / shared blocks of these sectors may be in flight
+  int lv_ids[kMaxLevels], nl = 0;
+  for (int l = 0; l <= e->stop; ++l)
+    if (level_used(e, l)) lv_ids[nl++] = l;
+  std::vector<RectDesc> desc((size_t)n * nl);
+  size_t total_px = 0, total_tiles = 0;
+  int worst = DIC_OK;
+  long max_n = 1, max_t = 1;
+  for (int k = 0; k < n; ++k) {
+    const int x0 = boxes[4 * k], y0 = boxes[4 * k + 1], x1 = boxes[4 * k + 2], y1 = boxes[4 * k + 3];
+    Sector &s = e->sectors[first_id + k];
+    if (s.buf && s.buf_owned) cudaFree(s.buf);
+    if (s.tbuf && s.tbuf_owned) cudaFree(s.tbuf);
+    s.buf = nullptr; s.cap = 0; s.buf_owned = false; s.tbuf = nullptr; s.tcap = 0; s.tbuf_owned = false;
+    s.kind = SK_NONE; s.pending = false; s.has_tiles = false;
+    clear_levels(s);
+    for (int l = 0; l < kMaxLevels; ++l) s.tl[l] = TileLevel{};
+    const bool bad = x1 < x0 || y1 < y0;
+    const size_t slice_begin = total_px;
+    for (int j = 0; j < nl; ++j) {
+      const int l = lv_ids[j], mag = 1 << l;
+      auto first_mult = [mag](int a) { int q = a / mag; if (q * mag < a) ++q; return q * mag; };
+      auto last_mult = [mag](int a) { int q = a / mag; if (q * mag > a) --q; return q * mag; };
+      RectDesc &d = desc[(size_t)k * nl + j];
+      memset(&d, 0, sizeof(d));
+      if (bad) continue;
+      const int xs = first_mult(x0), xe = last_mult(x1), ys = first_mult(y0), ye = last_mult(y1);
+      d.xs = xs; d.ys = ys; d.mag = mag;
+      d.nx = xe >= xs ? (xe - xs) / mag + 1 : 0;
+      d.ny = ye >= ys ? (ye - ys) / mag + 1 : 0;
+      if (d.nx == 0 || d.ny == 0) d.nx = d.ny = 0;
+      d.ntx = (d.nx + kTileW - 1) / kTileW; d.nty = (d.ny + kTileH - 1) / kTileH;
+      d.list_off = (long long)total_px; d.tile_off = (long long)total_tiles;
+      total_px += (size_t)d.nx * d.ny;
+      total_tiles += (size_t)d.ntx * d.nty;
+      max_n = std::max(max_n, (long)d.nx * d.ny);
+      max_t = std::max(max_t, (long)d.ntx * d.nty);
+    }
+    // a sector's levels are contiguous, with the slack the other builders reserve, so that a Lagrangian update
+    // (dic_update_polygon) can re-decimate in place instead of allocating
+    const size_t n0 = nl ? (size_t)desc[(size_t)k * nl].nx * desc[(size_t)k * nl].ny : 0;
+    total_px = std::max(total_px, slice_begin + n0 + n0 / 2 + 16);
+    s.cap = total_px - slice_begin;
+  }
+  if ((rc = ensure_block(e, &e->grid_lists, &e->cap_grid_lists, sizeof(float2) * std::max<size_t>(total_px, 1)))) return rc;
+  if ((rc = ensure_block(e, &e->grid_tiles, &e->cap_grid_tiles, sizeof(Tile) * std::max<size_t>(total_tiles, 1)))) return rc;
+  if ((rc = ensure_block(e, &e->grid_desc, &e->cap_grid_desc, sizeof(RectDesc) * desc.size()))) return rc;
+  float2 *lists = static_cast<float2 *>(e->grid_lists);
+  Tile *tiles = static_cast<Tile *>(e->grid_tiles);
+  CU_TRY(e, cudaMemcpyAsync(e->grid_desc, desc.data(), sizeof(RectDesc) * desc.size(), cudaMemcpyHostToDevice, e->stream));
+  const RectDesc *d_desc = static_cast<const RectDesc *>(e->grid_desc);
+  {
+    dim3 g1((unsigned)((max_n + 255) / 256), (unsigned)std::min<size_t>(desc.size(), 65535));
+    rect_grid_fill_kernel<<<g1, 256, 0, e->stream>>>(d_desc, (int)desc.size(), lists);
+    dim3 g2((unsigned)((max_t + 63) / 64), (unsigned)std::min<size_t>(desc.size(), 65535));
+    rect_grid_tiles_kernel<<<g2, 64, 0, e->stream>>>(d_desc, (int)desc.size(), tiles);
+    e->launches += 2;
+    CU_TRY(e, cudaGetLastError());
+  }
+  for (int k = 0; k < n; ++k) {
+    const int x0 = boxes[4 * k], y0 = boxes[4 * k + 1], x1 = boxes[4 * k + 2], y1 = boxes[4 * k + 3];
+    const int id = first_id + k;
+    Sector &s = e->sectors[id];
+    bool ok = !(x1 < x0 || y1 < y0);
+    for (int j = 0; j < nl && ok; ++j) {
+      const RectDesc &d = desc[(size_t)k * nl + j];
+      const int l = lv_ids[j];
+      s.xy[l] = lists + d.list_off;
+      s.n[l] = (long)d.nx * d.ny;
+      s.tl[l].tiles = tiles + d.tile_off;
+      s.tl[l].n_tiles = d.ntx * d.nty;
+    }
+    if (ok) {
+      s.buf = s.xy[0]; // level 0 first: the slice (s.cap elements) a Lagrangian update rewrites in place
+      s.cx = (float)(x0 + x1) * 0.5f; s.cy = (float)(y0 + y1) * 0.5f;
+      s.rx0 = x0; s.ry0 = y0; s.rx1 = x1; s.ry1 = y1;
+      s.integer_grid = true;
+      ok = check_levels_nonempty(e, s) == DIC_OK;
+    }
+    if (!ok) { clear_levels(s); if (worst == DIC_OK) worst = DIC_ERROR_BAD_DOMAIN; }
+    else { s.kind = SK_RECT; s.has_tiles = x0 >= 0 && y0 >= 0; }
+    // sector records: filled on the host, uploaded in one piece below
+    SectorDev &d = e->h_sectors[id];
+    memset(&d, 0, sizeof(d));
+    for (int l = 0; l < kMaxLevels; ++l) { d.xy[l] = s.xy[l]; d.n[l] = (int)s.n[l]; d.n_total[l] = (int)s.n[l]; }
+    d.cx = s.cx; d.cy = s.cy;
+    SectorTiles &t = e->h_sector_tiles[id];
+    memset(&t, 0, sizeof(t));
+    if (s.has_tiles)
+      for (int l = 0; l < kMaxLevels; ++l) t.lev[l] = s.tl[l];
+  }
+  CU_TRY(e, cudaMemcpyAsync(e->d_sectors + first_id, e->h_sectors + first_id, sizeof(SectorDev) * n, cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(e->d_sector_tiles + first_id, e->h_sector_tiles + first_id, sizeof(SectorTiles) * n,
+                            cudaMemcpyHostToDevice, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream)); // `desc` is pageable host memory
+  return worst;
+}
+
+int dic_set_cluster_mode(dic_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 2) return DIC_ERROR_BAD_ARGUMENT;
+  e->cluster_mode = mode;
+  return DIC_OK;
 }
 
 int dic_reset_polygon_annular(dic_engine *e, int id, float r, float dr, float a, float da, float cx,
@@ -1394,7 +1584,7 @@ int dic_rowsplit_connect(dic_engine *e, int rank, int world, const void *handles
   e->rs_rank = rank; e->rs_world = world;
   GridWork w;
   CU_TRY(e, cudaMemcpy(&w, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost));
-  w.rs_rank = rank; w.rs_world = world; w.rs_seq = 0; w.rs_error = 0;
+  w.rs_rank = rank; w.rs_world = world; w.rs_seq = 0;
   w.rs_local = e->d_mailbox;
   for (int r = 0; r < kMaxRanks; ++r) w.rs_peer[r] = static_cast<Mailbox *>(r < world ? e->peer_mailbox[r] : nullptr);
   CU_TRY(e, cudaMemcpy(e->d_work, &w, sizeof(GridWork), cudaMemcpyHostToDevice));
@@ -1411,7 +1601,7 @@ int dic_rowsplit_disconnect(dic_engine *e) {
   e->rs_rank = 0; e->rs_world = 1;
   GridWork w;
   CU_TRY(e, cudaMemcpy(&w, e->d_work, sizeof(GridWork), cudaMemcpyDeviceToHost));
-  w.rs_rank = 0; w.rs_world = 1; w.rs_local = nullptr; w.rs_error = 0;
+  w.rs_rank = 0; w.rs_world = 1; w.rs_local = nullptr; w.rs_seq = 0;
   for (auto &p : w.rs_peer) p = nullptr;
   CU_TRY(e, cudaMemcpy(e->d_work, &w, sizeof(GridWork), cudaMemcpyHostToDevice));
   return DIC_OK;
@@ -1423,15 +1613,22 @@ static int enqueue_correlate(dic_engine *e, int first, int count, const float *g
   int rc = images_ready(e);
   if (rc) return rc;
   const int np = np_of(e);
+  NvtxRange nvtx(grid_mode ? "dic_correlate" : "dic_correlate_batch");
+  bool in_flight = false;
   for (int i = 0; i < count; ++i) {
     if (!sector_ok(e, first + i)) { set_error(e, "unknown sector"); return DIC_ERROR_BAD_ARGUMENT; }
+    in_flight = in_flight || e->sectors[first + i].pending;
+  }
+  // The guesses do not travel by memcpy: a single sector's guess rides in the kernel parameters, a batch reads the
+  // pinned block below directly (zero-copy). Nothing of a correlate() queues on the H2D copy engine, so it cannot
+  // end up behind the next image pair's upload (which used to serialise upload and solve on the batch path).
+  if (in_flight) CU_TRY(e, cudaStreamSynchronize(e->stream)); // an un-waited async solve may still read the block
+  for (int i = 0; i < count; ++i) {
     float *g = e->h_guess + (size_t)(first + i) * kMaxParams;
     for (int k = 0; k < kMaxParams; ++k) g[k] = k < np ? guesses[(size_t)i * np + k] : 0.f;
     e->sectors[first + i].pending = true;
   }
   CU_TRY(e, cudaEventRecord(e->ev_step0, e->stream));
-  CU_TRY(e, cudaMemcpyAsync(e->d_guess + (size_t)first * kMaxParams, e->h_guess + (size_t)first * kMaxParams,
-                            sizeof(float) * kMaxParams * count, cudaMemcpyHostToDevice, e->stream));
   CU_TRY(e, cudaEventRecord(e->ev0, e->stream));
   rc = tiles_applicable(e, first, count) ? launch_solve_tiles_any(e, grid_mode, first, count)
                                          : launch_solve_any(e, grid_mode, first, count);
@@ -1455,7 +1652,10 @@ static int collect(dic_engine *e, int first, int count, float *guesses_out, dic_
   int worst = DIC_OK;
   bool aborted = false;
   for (int i = 0; i < count; ++i) aborted = aborted || e->h_results[first + i].errorCode == DIC_ERROR_CUDA;
-  if (aborted) set_error(e, "a grid-barrier wait inside gn_solve timed out (10 s)"); // scratch is re-zeroed per launch
+  if (aborted) {
+    set_error(e, "a bounded wait inside a kernel expired (grid barrier 10 s / TMA transfer 2 s)");
+    cudaMemsetAsync(&e->d_work->img_error, 0, sizeof(int), e->stream); // sticky flag of the pyramid kernel: reported once
+  }
   for (int i = 0; i < count; ++i) {
     const dic_result &r = e->h_results[first + i];
     e->sectors[first + i].pending = false;

@@ -37,6 +37,13 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
 
 // ------------------------------------------------------------------ LM state machine
 
+// scratch of warp_solve (NP * NP) followed by the step dp (NP): lm_step puts dp at kDpOffset
+template <int NP> struct SolveScratch {
+  static constexpr int kDpOffset = NP * (NP + 1);
+  static constexpr int kFloats = kDpOffset + NP + 4 < 16 ? 16 : kDpOffset + NP + 4; // >= kMaxParams: also stages the guess
+};
+
+
 // Executed by ONE full warp after every evaluation. tot = the evaluation's reduced sums.
 // Restates correlation_class.cpp:373-591 as "what to evaluate next"; parameter vectors are held
 // one element per lane.
@@ -61,7 +68,7 @@ __device__ void lm_step(LMState *s, const float *tot, const SolveSettings &cfg,
 
   const float chi = tot[L::kChi] * scaling;
   const bool oob = tot[L::kOob] > 0.5f;
-  float *dp = smem + NP * (NP + 1);
+  float *dp = smem + SolveScratch<NP>::kDpOffset;
   bool end_level = false, finish = false, begin_iter = false;
   __syncwarp();
 
@@ -241,13 +248,17 @@ __device__ __forceinline__ void evaluate_list(const SolveSettings &cfg, const Se
 // ------------------------------------------------------------------ row-split all-reduce
 //
 // One domain split by pixel rows over several GPUs: each evaluation ends with a sum of the
-// (n^2 + n)/2 + n + 2 normal-equation values over the ranks. Done here, inside the persistent
-// kernel, by warp 0 of CTA 0: write this rank's sums into slot [parity][rank] of every
-// peer's mailbox (plain stores to peer-mapped memory: NVLink), system fence, release-store the
-// sequence number; then wait for every peer's slot of this evaluation in the local mailbox and add
-// the rows IN RANK ORDER, so that every rank gets bitwise the same totals and takes the same LM
-// decisions without a broadcast. Two parities: a rank cannot be more than one evaluation ahead of
-// a peer, because it needs that peer's sums of the current evaluation to get there.
+// (n^2 + n)/2 + n + 2 normal-equation values over the ranks. Done here, inside the persistent kernel:
+//   send     CTA 0, after the rank's own grid all-reduce: warp w stores the rank's sums into slot
+//            [parity][rank] of peer w's mailbox (plain stores to peer-mapped memory: NVLink), system
+//            fence, release-store of the sequence number -- one warp per peer, all peers in parallel;
+//   receive  EVERY CTA polls the rank's own mailbox (local HBM, written by the peers) for all ranks'
+//            sequence numbers and adds the rows IN RANK ORDER itself: every CTA of every rank gets bitwise
+//            the same totals and takes the same LM decisions -- no broadcast, no publish / re-read hop
+//            through a master CTA.
+// Two parities: a rank cannot be more than one evaluation ahead of a peer, because it needs that
+// peer's sums of the current evaluation to get there, and a peer sends those only after all of its
+// CTAs have passed its grid barrier, i.e. have finished reading the previous evaluation's slots.
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -261,67 +272,100 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float *p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ull; // 20 s: a peer that never answers is an error, not a hang
 
+// CTA 0 only, all of its warps: warp w serves peers w, w + 8, ...
 template <int NACC>
-__device__ void rowsplit_allreduce(GridWork *work, float *tot) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void rowsplit_send(GridWork *work, const float *tot, unsigned int seq) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rank = work->rs_rank, world = work->rs_world;
-  const unsigned int seq = work->rs_seq;
   const int par = seq & 1;
-  for (int r = 0; r < world; ++r) {
+  for (int r = warp; r < world; r += kThreads / 32) {
     Mailbox *mb = work->rs_peer[r];
     for (int k = lane; k < NACC; k += 32) mb->sums[par][rank][k] = tot[k];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) st_release_sys_u32(&mb->seq[par][rank], seq + 1);
   }
-  __threadfence_system();
-  __syncwarp();
-  if (lane < world) st_release_sys_u32(&work->rs_peer[lane]->seq[par][rank], seq + 1);
-  // wait for all ranks (including our own loop-back write) -- bounded, never hang the GPU
-  bool ok = true;
-  if (lane < world) {
-    const unsigned int *flag = &work->rs_local->seq[par][lane];
-    const unsigned long long t0 = global_ns();
+}
+// every CTA, all threads. Returns false (CTA-uniform) when a peer did not answer in time.
+template <int NACC>
+__device__ __forceinline__ bool rowsplit_receive(GridWork *work, float *tot, unsigned int seq, int *s_flag) {
+  const int tid = threadIdx.x;
+  const int world = work->rs_world;
+  const int par = seq & 1;
+  const Mailbox *mb = work->rs_local;
+  if (tid == 0) *s_flag = 1;
+  __syncthreads();
+  if (tid < world) {
+    const unsigned int *flag = &mb->seq[par][tid];
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
     while (ld_acquire_sys_u32(flag) != seq + 1) {
-      if (global_ns() - t0 > 20000000000ull) { ok = false; break; } // 20 s
-      __nanosleep(100);
+      if ((++spins & 0x3ffu) == 0) {
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kPeerTimeoutNs) { *s_flag = 0; break; }
+      }
     }
   }
-  ok = __all_sync(0xffffffffu, ok);
-  if (!ok) {
-    if (lane == 0) work->rs_error = 1;
-  } else {
-    for (int k = lane; k < NACC; k += 32) {
-      double s = 0.0;
-      for (int r = 0; r < world; ++r) s += (double)ld_relaxed_sys_f32(&work->rs_local->sums[par][r][k]);
-      tot[k] = (float)s;
-    }
+  __syncthreads();
+  const bool ok = *s_flag != 0;
+  if (ok && tid < NACC) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += (double)ld_relaxed_sys_f32(&mb->sums[par][r][tid]);
+    tot[tid] = (float)s;
   }
-  __syncwarp();
-  if (lane == 0) work->rs_seq = seq + 1;
-  __syncwarp();
+  __syncthreads();
+  return ok;
+}
+
+// ------------------------------------------------------------------ thread-block cluster helpers
+// A subset solved by a PAIR of CTAs (cluster of 2, one CTA per SM): each CTA evaluates half of the
+// subset's units, stores its sums into BOTH CTAs' shared memory (its own and, through distributed
+// shared memory, the partner's), one cluster barrier, and both add the two rows in rank order --
+// bitwise identical totals, both run the same LM step. Halves the scheduling granule of a batch of
+// subsets (fills the tail wave when a GPU holds only a few hundred subsets).
+__device__ __forceinline__ unsigned int cluster_ctarank() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_dsmem_f32(const float *local_addr, unsigned int cta, float v) {
+  unsigned int remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(cta));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 
 // Shared-memory block common to both solve kernels.
 template <int NP> struct SolveShared {
   static constexpr int NACC = Acc<NP>::kN;
   float tot[NACC];
-  float solve[NP * NP + NP + 4];
+  float solve[SolveScratch<NP>::kFloats];
   float p[kMaxParams];
+  float xch[2][2][NACC]; // cluster pair: [evaluation parity][source CTA] partial sums
   int level, done;
   int rowsplit;  // this launch exchanges its sums with other GPUs (read once per sector, not per evaluation)
   int mark;      // next slot of CTA 0's timeline
   int timed_out; // a bounded wait expired
+  int rs_ok;     // row-split: scratch of rowsplit_receive
   unsigned int arrive_target; // value of GridWork::arrive that completes the current evaluation
-  unsigned int rs_gen;        // row-split: GridWork::generation before CTA 0's next publication
+  unsigned int rs_seq;        // row-split: evaluations exchanged so far (same on all CTAs of all ranks)
+  unsigned int xch_count;     // cluster pair: exchanges done by this CTA (parity of the xch buffer)
   LMState state;
 };
+static_assert(SolveScratch<12>::kDpOffset + 12 <= SolveScratch<12>::kFloats, "dp must lie inside SolveShared::solve");
 
 // After one evaluation pass: sh.tot holds this CTA's sums. Produces the next command in
 // sh.p / sh.level / sh.done for every CTA.
 //   GRID: all-reduce through GridWork (see there), then every CTA's warp 0 runs the LM step + solve
 //   on its own state; CTA 0 alone writes the result record and the timeline. With a row-split over
-//   GPUs, CTA 0 additionally exchanges the totals with the peers and publishes them to the others.
-//   Batch: the CTA owns the sector; only __syncthreads is needed.
-template <int MODEL, bool GRID>
+//   GPUs, CTA 0 additionally sends the rank's sums to the peers and every CTA adds all ranks' rows.
+//   Batch: the CTA (CL = 1) or the CTA pair (CL = 2) owns the sector.
+template <int MODEL, bool GRID, int CL = 1>
 __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)> &sh, bool active,
                                                 int n_active, const SolveSettings &cfg,
                                                 const SectorDev *sec, dic_result *result,
@@ -359,33 +403,17 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
     if (lead && tid < NACC) __stcg(&work->acc[(my_gen + 2u) % 3u][tid], 0.0);
     __syncthreads();
     if (sh.rowsplit) {
-      if (lead) {
-        if (warp == 0) {
-          rowsplit_allreduce<NACC>(work, sh.tot);
-          for (int k = lane; k < NACC; k += 32) __stcg(&work->pub_tot[k], sh.tot[k]);
-          __syncwarp(); // the other lanes' stores happen-before lane 0's release (cumulativity)
-          if (lane == 0) st_release_u32(&work->generation, sh.rs_gen + 1);
-        }
-      } else {
-        if (tid == 0) {
-          const unsigned long long t0 = global_ns();
-          unsigned int spins = 0;
-          while (ld_acquire_u32(&work->generation) == sh.rs_gen) {
-            __nanosleep(64);
-            if ((++spins & 0xfffu) == 0 && (global_ns() - t0 > 2 * kSpinTimeoutNs + 20000000000ull)) { sh.timed_out = 1; break; }
-          }
-        }
-        __syncthreads();
-        if (tid < NACC) sh.tot[tid] = __ldcg(&work->pub_tot[tid]);
-      }
-      if (tid == 0) sh.rs_gen += 1;
+      const unsigned int seq = sh.rs_seq;
+      if (lead) rowsplit_send<NACC>(work, sh.tot, seq);
+      if (!rowsplit_receive<NACC>(work, sh.tot, seq, &sh.rs_ok) && tid == 0) sh.timed_out = 2;
+      if (tid == 0) sh.rs_seq = seq + 1;
       __syncthreads();
     }
     if (warp == 0) {
       lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve, lead);
       if (lane == 0) {
-        if (sh.rowsplit && work->rs_error) { sh.state.done = 1; if (lead) result->errorCode = DIC_ERROR_MULTITHREAD; } // a peer never answered
-        if (sh.timed_out) { sh.state.done = 1; if (lead) result->errorCode = DIC_ERROR_CUDA; } // a CTA never arrived
+        if (sh.timed_out == 2) { sh.state.done = 1; if (lead) result->errorCode = DIC_ERROR_MULTITHREAD; } // a peer never answered
+        else if (sh.timed_out) { sh.state.done = 1; if (lead) result->errorCode = DIC_ERROR_CUDA; } // a CTA never arrived / a TMA copy never landed
       }
       __syncwarp();
       if (lane < NP) sh.p[lane] = sh.state.p[lane];
@@ -403,8 +431,26 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
     ++my_gen;
     __syncthreads();
   } else {
+    bool writer = true;
+    if (CL == 2) {
+      // exchange with the partner CTA through distributed shared memory
+      const unsigned int me = cluster_ctarank();
+      const int par = sh.xch_count & 1;
+      if (tid < NACC) {
+        const float v = sh.tot[tid];
+        sh.xch[par][me][tid] = v;
+        st_dsmem_f32(&sh.xch[par][me][tid], me ^ 1u, v);
+      }
+      cluster_sync_all(); // release / acquire at cluster scope: both rows are visible to both CTAs
+      if (tid < NACC) sh.tot[tid] = sh.xch[par][0][tid] + sh.xch[par][1][tid];
+      if (tid == 0) sh.xch_count += 1;
+      __syncthreads();
+      writer = me == 0;
+    }
     if (warp == 0) {
-      lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve);
+      lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve, writer);
+      if (lane == 0 && sh.timed_out) { sh.state.done = 1; if (writer) result->errorCode = DIC_ERROR_CUDA; }
+      __syncwarp();
       if (lane < NP) sh.p[lane] = sh.state.p[lane];
       if (lane == 0) { sh.level = sh.state.level; sh.done = sh.state.done; }
     }
@@ -412,25 +458,56 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
   }
 }
 
+// Initial guess of a single-sector (grid) launch: travels as a kernel parameter, so that a correlate() enqueues
+// nothing on a copy engine. Batch launches read their guesses straight from the caller-visible pinned block.
+struct GuessParam { float v[kMaxParams]; };
+
+__device__ __forceinline__ float ld_guess(const float *p) { // pinned host memory: never from a stale cache line
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Start of a sector: every CTA derives the first command locally and initialises its own copy of the
-// LM state (grid mode: all CTAs keep identical copies; batch mode: the CTA owns the sector).
+// LM state (grid mode: all CTAs keep identical copies; batch mode: the CTA or CTA pair owns the sector).
 template <int MODEL, bool GRID>
 __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &sh, const SolveSettings &cfg,
-                                             const SectorDev *sec, const float *guess, GridWork *work,
-                                             unsigned int &my_gen) {
+                                             const SectorDev *sec, const float *guess, const GuessParam &g0,
+                                             GridWork *work, unsigned int &my_gen) {
   constexpr int NP = model_nparams(MODEL);
   const int tid = threadIdx.x, warp = tid >> 5;
-  if (warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, guess); // grid mode: every CTA keeps its own copy
+  if (tid < kMaxParams) sh.solve[tid] = GRID ? g0.v[tid] : (tid < NP ? ld_guess(guess + tid) : 0.f);
+  __syncthreads();
+  if (warp == 0) lm_init<MODEL>(&sh.state, cfg, sec, sh.solve); // grid mode: every CTA keeps its own copy
   if (tid == 0) {
     sh.rowsplit = GRID && work->rs_local != nullptr;
-    sh.rs_gen = sh.rowsplit ? ld_acquire_u32(&work->generation) : 0u;
-    sh.mark = 0; sh.timed_out = 0; sh.arrive_target = 0;
+    sh.rs_seq = sh.rowsplit ? work->rs_seq : 0u;
+    sh.mark = 0; sh.arrive_target = 0;
+    if (work->img_error) sh.timed_out = 1; // a pyramid transfer failed earlier: finish at once with error_cuda
   }
   if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->slow_units = 0; work->marks[0][0] = global_ns(); }
-  if (tid < NP) sh.p[tid] = translate_param<MODEL>(guess[tid], tid, 0, cfg.stop);
+  if (tid < NP) sh.p[tid] = translate_param<MODEL>(sh.solve[tid], tid, 0, cfg.stop);
   if (tid == 0) { sh.level = cfg.stop; sh.done = 0; }
   __syncthreads();
   my_gen = 0u; // evaluations done by this launch
+}
+
+// End of a grid launch: the last CTA to leave puts GridWork back into its between-launch state.
+template <int NACC>
+__device__ __forceinline__ void grid_depart(GridWork *work, unsigned int rs_seq, bool rowsplit) {
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    if (rowsplit && blockIdx.x == 0) work->rs_seq = rs_seq;
+    __threadfence();
+    s_last = atomicAdd(&work->departed, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int k = threadIdx.x; k < 3 * 96; k += blockDim.x) (&work->acc[0][0])[k] = 0.0;
+    if (threadIdx.x == 0) { work->arrive = 0; work->abort = 0; work->departed = 0; }
+  }
 }
 
 // GRID = true : every CTA of a cooperative launch works on ONE sector (large domains).
@@ -438,20 +515,21 @@ __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &
 template <int MODEL, int INTERP, int MODE, bool GRID>
 __global__ void __launch_bounds__(kThreads)
 gn_solve_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
-                const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
+                const float *guesses, const GuessParam guess0, dic_result *__restrict__ results, int first_sector,
                 int n_sectors, GridWork *work) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   __shared__ float s_red[(kThreads / 32) * NACC];
   __shared__ SolveShared<NP> sh;
   const int tid = threadIdx.x;
+  if (tid == 0) { sh.timed_out = 0; sh.xch_count = 0; }
 
   for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
     const SectorDev *sec = sectors + first_sector + si;
     const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
     dic_result *result = results + first_sector + si;
     unsigned int my_gen;
-    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, work, my_gen);
+    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, guess0, work, my_gen);
     while (true) {
       const int level = sh.level;
       float p[NP];
@@ -479,6 +557,7 @@ gn_solve_kernel(const SolveSettings cfg, const SectorDev *__restrict__ sectors,
     }
     __syncthreads();
   }
+  if (GRID) grid_depart<NACC>(work, sh.rs_seq, sh.rowsplit != 0);
 }
 
 // ------------------------------------------------------------------ single evaluation (tests)
@@ -515,11 +594,11 @@ __global__ void sum_partials_kernel(const float *partials, int n_cta, int nacc, 
 template <int NP>
 __global__ void solve_step_kernel(const float *tot, float scaling, float lambda, float *dp_out,
                                   int *ok_out) {
-  __shared__ float smem[NP * (NP + 1) + NP + 4];
+  __shared__ float smem[SolveScratch<NP>::kFloats];
   __shared__ float s_tot[NP * (NP + 1) / 2 + NP + 2];
   for (int i = threadIdx.x; i < NP * (NP + 1) / 2 + NP; i += 32) s_tot[i] = tot[i];
   __syncwarp();
-  float *dp = smem + NP * (NP + 1);
+  float *dp = smem + SolveScratch<NP>::kDpOffset;
   bool ok = warp_solve<NP>(s_tot, scaling, lambda, smem, dp);
   if (threadIdx.x < NP) dp_out[threadIdx.x] = ok ? dp[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) *ok_out = ok ? 1 : 0;
@@ -548,7 +627,7 @@ struct PyrWeights { float w[25]; };
 
 __global__ void __launch_bounds__(kPyrTX *kPyrTY)
 pyramid_level_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t *__restrict__ dst, int drows, int dcols,
-                     int dpitch, PyrWeights kw, int trow_begin, int trow_end) {
+                     int dpitch, PyrWeights kw, int trow_begin, int trow_end, int *err_flag) {
   extern __shared__ __align__(128) uint8_t pyr_smem[];
   uint8_t *raw = pyr_smem;                                                        // [2][kPyrSrcBytes]
   float(*tE)[kPyrHalf] = reinterpret_cast<float(*)[kPyrHalf]>(pyr_smem + 2 * kPyrSrcBytes); // even source columns
@@ -578,7 +657,10 @@ pyramid_level_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t *__res
     // buffer b ^ 1 was last read by the conversion of iteration it - 1, which every thread left through the
     // barrier that follows it
     if (tile + (int)gridDim.x < n_tiles && tid == 0) issue(tile + gridDim.x, b ^ 1);
-    mbar_wait(&bar[b], (it >> 1) & 1);
+    if (!mbar_wait(&bar[b], (it >> 1) & 1)) { // the copy never landed: flag it (GridWork::img_error) and leave, all threads alike
+      if (tid == 0) atomicExch(err_flag, 1);
+      break;
+    }
     const uint8_t *rb = raw + b * kPyrSrcBytes;
     for (int idx = tid; idx < kPyrSH * (kPyrSW / 16); idx += kPyrTX * kPyrTY) {
       const int r = idx / (kPyrSW / 16), c16 = idx - r * (kPyrSW / 16);

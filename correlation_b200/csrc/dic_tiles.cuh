@@ -314,34 +314,41 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
   accumulate_moments<NP>(mom, V, wx, wy, Y);
 }
 
-// What a warp needs to know about a work unit before touching its pixels. A unit is `rpu` consecutive
-// rows of one tile (rpu = 16 >> split_log2).
+// What a warp needs to know about a work unit before touching its pixels. A unit is a run of consecutive
+// rows of one tile: rows [r0, r0 + nr) after trimming the rows no lane owns.
 struct UnitPlan {
   int x0, y0;       // level coordinates of the unit's first pixel
+  int nr;           // rows of the unit (0: nothing to do)
   uint32_t colmask; // this lane's column of the membership mask: bit r <=> pixel (x0 + lane, y0 + r)
   int px0, py0;     // origin of the staged deformed-image patch
-  bool full, empty, staged;
+  bool full, staged;
 };
 
-template <int NP>
-__device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int u, int split_log2, const float *p,
+// Rows [r0, r1) of tile `t`. GRAN = 4 keeps the trimmed range on multiples of four rows (fast mode walks four
+// pixels per trip), GRAN = 1 trims to the exact first / last owned row.
+template <int NP, int GRAN>
+__device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int t, int r0, int r1, const float *p,
                                               float ccx, float ccy, const LevelImage &def) {
   const int lane = threadIdx.x & 31;
-  const int rpu = kTileH >> split_log2;
   UnitPlan q;
-  const Tile *tp = tl.tiles + (u >> split_log2);
-  const int r0 = (u & ((1 << split_log2) - 1)) * rpu;
+  const Tile *tp = tl.tiles + t;
+  uint32_t col = ((uint32_t)__ldg(&tp->cols[lane]) >> r0) & ((1u << (r1 - r0)) - 1u);
+  const uint32_t any = __reduce_or_sync(0xffffffffu, col); // rows of the range some lane owns
+  if (any == 0u) { q.nr = 0; q.x0 = q.y0 = q.px0 = q.py0 = 0; q.colmask = 0; q.full = q.staged = false; return q; }
+  int lo = __ffs(any) - 1, hi = 32 - __clz(any);
+  if (GRAN > 1) { lo &= ~(GRAN - 1); hi = (hi + GRAN - 1) & ~(GRAN - 1); }
+  r0 += lo;
+  q.nr = hi - lo;
+  q.colmask = (col >> lo) & ((1u << q.nr) - 1u);
   q.x0 = __ldg(&tp->x0); q.y0 = __ldg(&tp->y0) + r0;
-  const uint32_t unit_rows = ((1u << rpu) - 1u) << r0;
-  q.colmask = ((uint32_t)__ldg(&tp->cols[lane]) & unit_rows) >> r0;
+  const uint32_t unit_rows = ((1u << q.nr) - 1u) << r0;
   q.full = (__ldg(&tp->full_rows) & unit_rows) == unit_rows;
-  q.empty = __all_sync(0xffffffffu, q.colmask == 0); // empty row chunk of a partial tile
   // footprint of the unit under the current parameters: one corner per lane (lanes 0-3), min / max by
   // shuffle, widened for the curvature of the quadratic model
   float bx0, bx1, by0, by1;
   {
     const float Xc = ((lane & 1) ? (float)(q.x0 + kTileW - 1) : (float)q.x0) - ccx;
-    const float Yc = ((lane & 2) ? (float)(q.y0 + rpu - 1) : (float)q.y0) - ccy;
+    const float Yc = ((lane & 2) ? (float)(q.y0 + q.nr - 1) : (float)q.y0) - ccy;
     float xd = Xc + ccx + p[0] + p[2] * Xc + p[3] * Yc;
     float yd = Yc + ccy + p[1] + p[4] * Xc + p[5] * Yc;
     if (NP == 12) {
@@ -372,7 +379,7 @@ __device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int u, int sp
 // lane 0 starts the two bulk tensor copies of a planned unit into the warp's next staging buffer
 __device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, const CUtensorMap *map_def,
                                            const CUtensorMap *map_und) {
-  if (!q.empty && q.staged) {
+  if (q.nr > 0 && q.staged) {
     if ((threadIdx.x & 31) == 0) {
       uint8_t *dst = st.buf + (st.issued & 1) * kStageBytes;
       uint64_t *bar = st.bar + (st.issued & 1);
@@ -384,23 +391,27 @@ __device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, con
   }
 }
 
-// ---- one evaluation over a range of work units of one level. Coarse levels and small subsets split
-// their tiles into row chunks so that every resident warp has work; units keep the column-major strip
-// order. The staging of unit u + 1 is in flight while unit u is being evaluated.
+// ---- one evaluation over a range of QUADS (4 consecutive rows of a tile; 4 quads per tile, tiles in column-major
+// strip order) of one level. The partition of a level over warps is in quads, so that every warp gets the same
+// number of pixel rows to within four -- a whole-tile granule left some warps with 8 tiles and others with 7
+// (12 % of a pass spent waiting at the barrier); coarse levels and small subsets spread the same way until every
+// warp has at least one quad. A warp walks its range tile by tile (first and last tile possibly partial); the
+// staging of the next unit is in flight while the current one is evaluated.
 template <int MODEL, int MODE>
 __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const TileMaps &maps, float cx0, float cy0,
                                                const TileLevel tl, int level, const float *p,
-                                               int unit_begin, int unit_end, int split_log2, WarpStage &st,
-                                               float *warp_acc, unsigned int *slow_counter) {
+                                               int quad_begin, int quad_end, WarpStage &st,
+                                               float *warp_acc, unsigned int *slow_counter, int *timeout_flag) {
   constexpr int NP = model_nparams(MODEL);
+  constexpr int GRAN = MODE == DIC_MODE_PARITY ? 1 : 4;
   using M = Mom<NP>;
   const int lane = threadIdx.x & 31;
+  if (__shfl_sync(0xffffffffu, *(volatile int *)timeout_flag, 0)) return; // a copy was lost earlier in this launch: the staging state is void (warp-uniform test)
   const LevelImage und = cfg.und[level];
   const LevelImage def = cfg.def[level];
   const CUtensorMap *map_def = &maps.def[level], *map_und = &maps.und[level];
   const float inv = 1.f / (float)(1 << level);
   const float ccx = cx0 * inv, ccy = cy0 * inv;
-  const int rpu = kTileH >> split_log2;
   float mom[M::kN];
 #pragma unroll
   for (int i = 0; i < M::kN; ++i) mom[i] = 0.f;
@@ -418,19 +429,30 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   LaneWarp<NP> lw;
   lw.set(p, 0.f, 0.f);
 
+  // rows [r0, r1) of tile t that belong to this warp's quad range
+  const int t_first = quad_begin >> 2, t_last = (quad_end - 1) >> 2;
+  auto rows_of = [&](int t, int &r0, int &r1) {
+    r0 = t == t_first ? (quad_begin & 3) * 4 : 0;
+    r1 = t == t_last ? ((quad_end - 1) & 3) * 4 + 4 : kTileH;
+  };
   UnitPlan nxt;
-  if (unit_begin < unit_end) {
-    nxt = plan_unit<NP>(tl, unit_begin, split_log2, p, ccx, ccy, def);
+  nxt.nr = 0;
+  if (quad_begin < quad_end) {
+    int r0, r1;
+    rows_of(t_first, r0, r1);
+    nxt = plan_unit<NP, GRAN>(tl, t_first, r0, r1, p, ccx, ccy, def);
     issue_unit(st, nxt, map_def, map_und);
   }
-  for (int u = unit_begin; u < unit_end; ++u) {
+  for (int t = t_first; quad_begin < quad_end && t <= t_last; ++t) {
     const UnitPlan q = nxt;
-    if (u + 1 < unit_end) {
-      nxt = plan_unit<NP>(tl, u + 1, split_log2, p, ccx, ccy, def);
+    if (t + 1 <= t_last) {
+      int r0, r1;
+      rows_of(t + 1, r0, r1);
+      nxt = plan_unit<NP, GRAN>(tl, t + 1, r0, r1, p, ccx, ccy, def);
       issue_unit(st, nxt, map_def, map_und);
     }
-    if (q.empty) continue;
-    const int x0 = q.x0, y0 = q.y0;
+    if (q.nr == 0) continue;
+    const int x0 = q.x0, y0 = q.y0, nr = q.nr;
     if (x0 != cur_x0) {
       if (cur_x0 != INT_MIN) flush_moments<NP>(mom, X, warp_acc);
       cur_x0 = x0;
@@ -442,8 +464,12 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
     if (q.staged) {
       const uint8_t *patch = st.buf + (st.consumed & 1) * kStageBytes;
       const uint8_t *ucol = patch + kPatchBytes + (x0 & 15) + lane; // reference pixels of this lane's column
-      mbar_wait(st.bar + (st.consumed & 1), (st.consumed >> 1) & 1);
+      const bool landed = mbar_wait(st.bar + (st.consumed & 1), (st.consumed >> 1) & 1);
       ++st.consumed;
+      if (!landed) { // never expected: end the launch with error_cuda instead of consuming garbage (or hanging)
+        if (lane == 0) atomicExch(timeout_flag, 1);
+        break;
+      }
       const int px0 = q.px0, py0 = q.py0;
       float cw[4][4];
       int wix = INT_MIN, wiy = INT_MIN; // no window yet: the first row rebuilds all four
@@ -459,17 +485,17 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
       if (MODE == DIC_MODE_PARITY) {
         if (q.full) {
 #pragma unroll 1
-          for (int r = 0; r < rpu; ++r) { DIC_STEP(true, 0, r); DIC_SHIFT(); }
+          for (int r = 0; r < nr; ++r) { DIC_STEP(true, 0, r); DIC_SHIFT(); }
         } else {
 #pragma unroll 1
-          for (int r = 0; r < rpu; ++r) { DIC_STEP(false, 0, r); DIC_SHIFT(); }
+          for (int r = 0; r < nr; ++r) { DIC_STEP(false, 0, r); DIC_SHIFT(); }
         }
       } else if (q.full) {
 #pragma unroll 1
-        for (int r = 0; r < rpu; r += 4) { DIC_STEP(true, 0, r); DIC_STEP(true, 1, r + 1); DIC_STEP(true, 2, r + 2); DIC_STEP(true, 3, r + 3); }
+        for (int r = 0; r < nr; r += 4) { DIC_STEP(true, 0, r); DIC_STEP(true, 1, r + 1); DIC_STEP(true, 2, r + 2); DIC_STEP(true, 3, r + 3); }
       } else {
 #pragma unroll 1
-        for (int r = 0; r < rpu; r += 4) { DIC_STEP(false, 0, r); DIC_STEP(false, 1, r + 1); DIC_STEP(false, 2, r + 2); DIC_STEP(false, 3, r + 3); }
+        for (int r = 0; r < nr; r += 4) { DIC_STEP(false, 0, r); DIC_STEP(false, 1, r + 1); DIC_STEP(false, 2, r + 2); DIC_STEP(false, 3, r + 3); }
       }
 #undef DIC_SHIFT
 #undef DIC_STEP
@@ -480,7 +506,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
       // own bounds test (error 2 + zero contribution, interpolation_class.cpp:129-137)
       const uint8_t *ucol = und.ptr + (size_t)y0 * und.pitch + x0 + lane;
 #pragma unroll 1
-      for (int r = 0; r < rpu; ++r) {
+      for (int r = 0; r < nr; ++r) {
         if (!((colmask >> r) & 1u)) continue;
         const float yf = (float)(y0 + r);
         float xd, yd, dxx, dyy, w, wx, wy;
@@ -526,14 +552,18 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float 
 }
 
 // ---- the solve kernel on tiles (same LM / barrier / solve machinery as gn_solve_kernel)
-template <int MODEL, int MODE, bool GRID>
+//   GRID         one sector, every CTA of a cooperative launch works on it (large domains)
+//   !GRID, CL=1  each CTA owns whole sectors (BASELINE config 4: thousands of small subsets)
+//   !GRID, CL=2  each CTA PAIR (thread-block cluster of 2) owns whole sectors
+template <int MODEL, int MODE, bool GRID, int CL>
 __global__ void __launch_bounds__(kThreads, tile_ctas_per_sm(MODEL))
 gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps maps,
                       const SectorDev *__restrict__ sectors, const SectorTiles *__restrict__ sector_tiles,
-                      const float *__restrict__ guesses, dic_result *__restrict__ results, int first_sector,
+                      const float *guesses, const GuessParam guess0, dic_result *__restrict__ results, int first_sector,
                       int n_sectors, GridWork *work) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
+  static_assert(!GRID || CL == 1, "clusters are a batch-mode feature");
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   uint8_t *s_stage = dyn_smem;                                                    // [warps][kWarpStageBytes]
   float *s_wacc = reinterpret_cast<float *>(dyn_smem + kWarpsPerCta * kWarpStageBytes); // [warps][NACC]
@@ -553,9 +583,13 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (tid == 0) { sh.xch_count = 0; sh.timed_out = 0; } // timed_out is sticky for the rest of the launch
   __syncwarp();
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  if (CL == 2) cluster_sync_all(); // the partner's shared memory exists from here on
+  const int group = GRID ? 0 : (int)blockIdx.x / CL, n_groups = GRID ? 1 : (int)gridDim.x / CL;
 
-  for (int si = GRID ? 0 : blockIdx.x; si < n_sectors; si += GRID ? n_sectors : gridDim.x) {
+  for (int si = group; si < n_sectors; si += GRID ? n_sectors : n_groups) {
     const SectorDev *sec = sectors + first_sector + si;
     const SectorTiles *stl = sector_tiles + first_sector + si;
     const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
@@ -563,31 +597,26 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
     unsigned int my_gen;
     if (tid < kMaxLevels) s_tiles.lev[tid] = stl->lev[tid];
     if (tid == kMaxLevels) { s_center[0] = sec->cx; s_center[1] = sec->cy; }
-    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, work, my_gen); // ends with a CTA barrier
+    begin_sector<MODEL, GRID>(sh, cfg, sec, guess, guess0, work, my_gen); // ends with a CTA barrier
     while (true) {
       const int level = sh.level;
       for (int k = lane; k < NACC; k += 32) warp_acc[k] = 0.f;
       __syncwarp();
       const TileLevel tl = s_tiles.lev[level];
-      // split tiles into row chunks until every warp that can take part has a unit (rpu >= 4)
-      const int warps_avail = GRID ? (int)gridDim.x * kWarpsPerCta : kWarpsPerCta;
-      int split_log2 = 0;
-      while (split_log2 < 2 && (tl.n_tiles << split_log2) < warps_avail) ++split_log2;
-      const int n_units = tl.n_tiles << split_log2;
-      int n_active = 1;
-      bool active = true;
-      if (GRID) {
-        n_active = max(1, min((n_units + kWarpsPerCta - 1) / kWarpsPerCta, (int)gridDim.x));
-        active = (int)blockIdx.x < n_active;
-      }
+      // quads of the level over the warps that take part: at least one quad per active warp
+      const int n_quads = tl.n_tiles * 4;
+      const int ctas = GRID ? (int)gridDim.x : CL;
+      const int n_active = max(1, min((n_quads + kWarpsPerCta - 1) / kWarpsPerCta, ctas));
+      const int cta = GRID ? (int)blockIdx.x : crank;
+      const bool active = cta < n_active;
       if (active) {
         const int nw = n_active * kWarpsPerCta;
-        const int wg = GRID ? blockIdx.x * kWarpsPerCta + warp : warp;
-        // balanced contiguous ranges: the first (n_units % nw) warps take one unit more
-        const int base = n_units / nw, rem = n_units - base * nw;
-        const int ub = wg * base + min(wg, rem), ue = ub + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, ub, ue, split_log2, st,
-                                    warp_acc, GRID ? &work->slow_units : nullptr);
+        const int wg = cta * kWarpsPerCta + warp;
+        // balanced contiguous ranges: the first (n_quads % nw) warps take one quad more
+        const int base = n_quads / nw, rem = n_quads - base * nw;
+        const int qb = wg * base + min(wg, rem), qe = qb + base + (wg < rem ? 1 : 0);
+        evaluate_tiles<MODEL, MODE>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, qb, qe, st,
+                                    warp_acc, GRID ? &work->slow_units : nullptr, &sh.timed_out);
         if (tl.n_extra > 0 && wg == 0)
           evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);
       }
@@ -599,11 +628,12 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
         sh.tot[k] = s;
       }
       __syncthreads();
-      reduce_and_step<MODEL, GRID>(sh, active, n_active, cfg, sec, result, work, my_gen);
+      reduce_and_step<MODEL, GRID, CL>(sh, active, n_active, cfg, sec, result, work, my_gen);
       if (sh.done) break;
     }
     __syncthreads();
   }
+  if (GRID) grid_depart<NACC>(work, sh.rs_seq, sh.rowsplit != 0);
 }
 
 constexpr size_t tiles_dyn_smem(int nacc) {
@@ -689,6 +719,40 @@ __global__ void rect_tiles_kernel(Tile *__restrict__ out, int ntx, int nty, int 
   for (int r = 0; r < kTileH; ++r) q.rows[r] = r < hrows ? m : 0u;
   tile_finish(q);
   out[t] = q;
+}
+
+// ---- a whole grid of rectangles at once (dic_reset_polygon_rect_grid): one descriptor per (sector, level)
+struct RectDesc {
+  int xs, ys, nx, ny, mag; // level-0 coordinates of the first kept pixel, kept pixels per row / column, 2^level
+  int ntx, nty;            // tiles across / down
+  long long list_off, tile_off; // offsets (elements) into the shared list / tile blocks
+};
+__global__ void rect_grid_fill_kernel(const RectDesc *__restrict__ desc, int n_desc, float2 *__restrict__ lists) {
+  for (int di = blockIdx.y; di < n_desc; di += gridDim.y) {
+    const RectDesc d = desc[di];
+    const long n = (long)d.nx * d.ny;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) continue;
+    const int row = (int)(i / d.nx), col = (int)(i % d.nx);
+    const float inv = 1.f / (float)d.mag;
+    lists[d.list_off + i] = make_float2((float)(d.xs + col * d.mag) * inv, (float)(d.ys + row * d.mag) * inv);
+  }
+}
+__global__ void rect_grid_tiles_kernel(const RectDesc *__restrict__ desc, int n_desc, Tile *__restrict__ tiles) {
+  for (int di = blockIdx.y; di < n_desc; di += gridDim.y) {
+    const RectDesc d = desc[di];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.ntx * d.nty) continue;
+    const int tx = t / d.nty, ty = t - tx * d.nty;
+    Tile q;
+    q.x0 = d.xs / d.mag + tx * kTileW; q.y0 = d.ys / d.mag + ty * kTileH;
+    const int wcols = min(kTileW, d.nx - tx * kTileW), hrows = min(kTileH, d.ny - ty * kTileH);
+    const uint32_t m = wcols >= 32 ? 0xffffffffu : ((1u << wcols) - 1u);
+#pragma unroll
+    for (int r = 0; r < kTileH; ++r) q.rows[r] = r < hrows ? m : 0u;
+    tile_finish(q);
+    tiles[d.tile_off + t] = q;
+  }
 }
 
 // integer bounding box of a list (for blob / point-list sectors)

@@ -67,7 +67,7 @@ EXPORTS = [
     "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_device",
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
-    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_points", "dic_set_polygon_center",
+    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_rect_grid", "dic_set_cluster_mode", "dic_reset_polygon_points", "dic_set_polygon_center",
     "dic_stage_next_pair", "dic_stage_next_pair_rows", "dic_advance_pair",
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
@@ -115,6 +115,8 @@ def load_library():
         "dic_reset_polygon_blob": (I, [P, I, P, I]),
         "dic_reset_polygon_points": (I, [P, I, P, I64, I, F, F]),
         "dic_reset_polygon_rect_band": (I, [P, I, I, I, I, I, I, I]),
+        "dic_reset_polygon_rect_grid": (I, [P, I, I, P]),
+        "dic_set_cluster_mode": (I, [P, I]),
         "dic_rowsplit_mailbox_handle": (I, [P, P, I]),
         "dic_rowsplit_connect": (I, [P, I, I, P, I]),
         "dic_rowsplit_disconnect": (I, [P]),
@@ -275,6 +277,14 @@ class CudaEngine:
     def resetPolygonRectBand(self, iSector, x0, y0, x1, y1, band_y0, band_y1):
         return self._ck(self.lib.dic_reset_polygon_rect_band(self.h, iSector, int(x0), int(y0), int(x1), int(y1),
                                                              int(band_y0), int(band_y1)), soft=(4,))
+
+    def resetPolygonRectGrid(self, first_sector, boxes):
+        """boxes: (n, 4) int array of x0, y0, x1, y1 -- n rectangles in one go (dic_reset_polygon_rect_grid)."""
+        b = np.ascontiguousarray(boxes, np.int32).reshape(-1, 4)
+        return self._ck(self.lib.dic_reset_polygon_rect_grid(self.h, int(first_sector), b.shape[0], _ptr(b)), soft=(4,))
+
+    def set_cluster_mode(self, mode):
+        self._ck(self.lib.dic_set_cluster_mode(self.h, int(mode)))
 
     def rowsplit_handle(self):
         buf = np.zeros(64, np.uint8)

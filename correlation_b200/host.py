@@ -20,19 +20,23 @@ class HostConfig(C.Structure):
                 ("model", C.c_int), ("interpolation", C.c_int), ("pyramid", C.c_int * 3),
                 ("precision", C.c_float), ("max_iters", C.c_int), ("deformation_description", C.c_int),
                 ("reference_image", C.c_int), ("global_initial_guess", C.c_float * 12),
-                ("arith_mode", C.c_int), ("batch_sectors", C.c_int), ("device", C.c_int)]
+                ("arith_mode", C.c_int), ("batch_sectors", C.c_int), ("device", C.c_int),
+                ("error_handling_mode", C.c_int)]
 
 
 ROW_DTYPE = np.dtype([("frame", np.int32), ("sector", np.int32), ("und_center_x", np.float32),
                       ("und_center_y", np.float32), ("def_center_x", np.float32), ("def_center_y", np.float32),
                       ("def_angle", np.float32), ("params", np.float32, (12,)), ("initial_guess", np.float32, (12,)),
                       ("chi", np.float32), ("number_of_points", np.int32), ("iterations", np.int32),
-                      ("error_code", np.int32)])
+                      ("error_code", np.int32), ("und_global_center_x", np.float32), ("und_global_center_y", np.float32),
+                      ("def_global_center_x", np.float32), ("def_global_center_y", np.float32),
+                      ("def_global_angle", np.float32), ("und_angle", np.float32)])
+ERROR_STOP_ALL, ERROR_STOP_FRAME, ERROR_CONTINUE = 0, 1, 2  # errorHandlingModeEnum, enums.hpp:80-85
 
 
 def run_sequence(frames, *, rect=None, subdivisions=(1, 1), annulus=None, contour=None, model=3,
                  interpolation=2, pyramid=(0, 1, 2), precision=1e-3, max_iters=50, deformation=2,
-                 reference=0, guess=None, arith_mode=0, batch=False, device=0):
+                 reference=0, guess=None, arith_mode=0, batch=False, device=0, on_error=ERROR_STOP_ALL):
     """frames: list of equally sized uint8 2-D arrays (host). Returns dict(csv, seconds, rows, error)."""
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} missing: run __graft_entry__.build()")
@@ -67,6 +71,7 @@ def run_sequence(frames, *, rect=None, subdivisions=(1, 1), annulus=None, contou
         g[:len(guess)] = guess
     c.global_initial_guess[:] = g.tolist()
     c.arith_mode, c.batch_sectors, c.device = int(arith_mode), int(bool(batch)), int(device)
+    c.error_handling_mode = int(on_error)
     ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
     n_sectors = int(subdivisions[0]) * int(subdivisions[1]) if contour is None else 1
     csv = C.create_string_buffer(max(1 << 16, 600 * n_sectors * len(frames)))

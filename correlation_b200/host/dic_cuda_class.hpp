@@ -11,6 +11,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -25,7 +26,9 @@ class CudaClass {
   int device_ = 0;
   int deviceCount = 0;
   int n_params_ = 6;
-  std::vector<CorrelationResult> results_; // engine-owned result records, one per sector (cuda_polygon.cuh:370-371)
+  // engine-owned result records, one per sector (cuda_polygon.cuh:370-371). A deque: growing it for a higher
+  // sector id never moves the records already handed out by correlate()
+  std::deque<CorrelationResult> results_;
 
   void need_engine() {
     if (!engine_) {
@@ -115,6 +118,11 @@ public:
     std::memcpy(&results_[iSector], &r, sizeof(r));
     if (rc >= DIC_ERROR_CUDA && r.errorCode == 0) results_[iSector].errorCode = (errorEnum)(rc > 7 ? error_cuda : rc);
     return &results_[iSector];
+  }
+  // extension: n rectangles at once (the subdivision loop's resetPolygon calls, manager_class.cpp:274-340)
+  errorEnum resetPolygonGrid(int firstSector, int nSectors, const int *boxes) {
+    need_engine();
+    return (errorEnum)dic_reset_polygon_rect_grid(engine_, firstSector, nSectors, boxes);
   }
   // extension: all subsets of a subdivided domain in one launch
   int correlateBatch(int firstSector, int nSectors, float *guesses, CorrelationResult *out) {

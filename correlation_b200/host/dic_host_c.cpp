@@ -30,6 +30,7 @@ struct dic_host_config {
   int arith_mode;
   int batch_sectors;
   int device;
+  int error_handling_mode;     // 0 stopAll (GUI default), 1 stopFrame, 2 continue (enums.hpp:80-85)
 };
 
 struct dic_host_row { // one CSV row, numerically
@@ -38,6 +39,7 @@ struct dic_host_row { // one CSV row, numerically
   float params[DIC_MAX_PARAMS], initial_guess[DIC_MAX_PARAMS];
   float chi;
   int number_of_points, iterations, error_code;
+  float und_global_center_x, und_global_center_y, def_global_center_x, def_global_center_y, def_global_angle, und_angle;
 };
 
 static dic_host::Config to_config(const dic_host_config *c) {
@@ -55,6 +57,7 @@ static dic_host::Config to_config(const dic_host_config *c) {
   k.referenceImage = (referenceImageEnum)c->reference_image;
   memcpy(k.global_initial_guess, c->global_initial_guess, sizeof(k.global_initial_guess));
   k.arith_mode = c->arith_mode; k.batch_sectors = c->batch_sectors != 0;
+  k.error_handling_mode = (errorHandlingModeEnum)c->error_handling_mode;
   return k;
 }
 
@@ -85,7 +88,10 @@ int dic_host_run(const dic_host_config *c, const uint8_t *const *frames, int n_f
       const auto &rs = m.results();
       for (size_t s = 0; s < rs.size() && w < rows_cap; ++s, ++w) {
         dic_host_row &o = out_rows[w];
-        o.frame = n_frames - 2; o.sector = (int)s;
+        o.frame = m.frames_done() - 1; o.sector = (int)s;
+        o.und_global_center_x = rs[s].und_global_center_x; o.und_global_center_y = rs[s].und_global_center_y;
+        o.def_global_center_x = rs[s].def_global_center_x; o.def_global_center_y = rs[s].def_global_center_y;
+        o.def_global_angle = rs[s].def_global_angle; o.und_angle = rs[s].und_angle;
         o.und_center_x = rs[s].und_center_x; o.und_center_y = rs[s].und_center_y;
         o.def_center_x = rs[s].def_center_x; o.def_center_y = rs[s].def_center_y; o.def_angle = rs[s].def_angle;
         memcpy(o.params, rs[s].resulting_parameters, sizeof(o.params));
@@ -152,6 +158,8 @@ int main(int argc, char **argv) {
     else if (a == "--previous") c.reference_image = 1;
     else if (a == "--fast") c.arith_mode = 1;
     else if (a == "--batch") c.batch_sectors = 1;
+    else if (a == "--on-error" && i + 1 < argc) { std::string m = argv[++i]; c.error_handling_mode = m == "stopFrame" ? 1 : m == "continue" ? 2 : 0; }
+    else if (a == "--strict-lagrangian") c.deformation_description = 0;
     else if (a == "--out") out = argv[++i];
     else files.push_back(a);
   }

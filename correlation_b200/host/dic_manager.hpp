@@ -40,6 +40,7 @@ struct Config {
   int max_iters = 50;
   deformationDescriptionEnum deformationDescription = def_Eulerian;
   referenceImageEnum referenceImage = refImage_First;
+  errorHandlingModeEnum error_handling_mode = errorMode_stopAll; // GUI default, mainapp.cpp:73
   float global_initial_guess[DIC_MAX_PARAMS] = {0};
   int arith_mode = DIC_MODE_PARITY;
   bool batch_sectors = false; // extension: all sectors of a frame in one launch
@@ -83,6 +84,13 @@ class HeadlessManager {
   int np_;
   std::vector<SectorState> results_;
   std::ostringstream report_;
+  // managerClass::error is ONE member overwritten by every sector's correlate (manager_class.cpp:443-452,
+  // 704-713, 1145-1154): at the end of a frame it holds the status of the LAST sector processed
+  bool error_ = false;
+  int frames_done_ = 0;
+  bool stops_frame() const { // :535-536, :795-796
+    return error_ && (cfg_.error_handling_mode == errorMode_stopAll || cfg_.error_handling_mode == errorMode_stopFrame);
+  }
   static constexpr float PI = 3.14159265359f; // parameters.hpp:23
 
   void distort(float x, float y, float cx, float cy, const float *p, float &xd, float &yd) const {
@@ -203,9 +211,11 @@ class HeadlessManager {
     const int xdim = (std::abs(x1 - x0) / hs - 1) / 2, ydim = (std::abs(y1 - y0) / vs - 1) / 2;
     const float fxdim = (std::fabs(cfg_.x_end - cfg_.x_begin) / (float)hs - 1.f) / 2.f;
     const float fydim = (std::fabs(cfg_.y_end - cfg_.y_begin) / (float)vs - 1.f) / 2.f;
-    bool error = false;
     std::vector<float> guesses((size_t)hs * vs * np_);
-    for (int i = 0; i < hs; ++i) {
+    std::vector<int> boxes; // batch mode: every subset's rectangle, built in one call
+    if (cfg_.batch_sectors && frame == 0) boxes.resize((size_t)hs * vs * 4);
+    bool stop = false;
+    for (int i = 0; i < hs && !stop; ++i) {
       int center_x = (int)(0.5f + cfg_.x_begin + fxdim + (2.f * fxdim + 1.f) * (float)i);
       for (int j = 0; j < vs; ++j) {
         const int iSector = i * vs + j;
@@ -223,36 +233,60 @@ class HeadlessManager {
         center_x = (int)(s.und_center_x + 0.5f);
         center_y = (int)(s.und_center_y + 0.5f);
         adjust_initial_guess(s, frame);
+        for (int p = 0; p < np_; ++p) guesses[(size_t)iSector * np_ + p] = s.initial_guess[p];
+        if (cfg_.batch_sectors) {
+          if (frame == 0) {
+            int *b = &boxes[(size_t)iSector * 4];
+            b[0] = center_x - xdim; b[1] = center_y - ydim; b[2] = center_x + xdim; b[3] = center_y + ydim;
+          } else if (cfg_.deformationDescription != def_Eulerian && !s.error_status) {
+            cuda_.updatePolygon(iSector, cfg_.deformationDescription);
+          }
+          continue;
+        }
         if (frame == 0) {
           if (cuda_.resetPolygon(iSector, center_x - xdim, center_y - ydim, center_x + xdim, center_y + ydim) != error_none) {
-            s.error_status = true; s.error_code = error_bad_domain; error = true; continue;
+            s.error_status = true; s.error_code = error_bad_domain; error_ = true;
+            if (stops_frame()) { stop = true; break; }
+            continue;
           }
         } else if (cfg_.deformationDescription != def_Eulerian) {
           cuda_.updatePolygon(iSector, cfg_.deformationDescription);
         }
-        for (int p = 0; p < np_; ++p) guesses[(size_t)iSector * np_ + p] = s.initial_guess[p];
-        if (!cfg_.batch_sectors) {
-          CorrelationResult *r = cuda_.correlate(iSector, &guesses[(size_t)iSector * np_]);
-          update_results(s, *r);
-          error = error || s.error_status;
-        }
+        CorrelationResult *r = cuda_.correlate(iSector, &guesses[(size_t)iSector * np_]);
+        update_results(s, *r);
+        error_ = s.error_status; // :452
+        if (stops_frame()) { stop = true; break; }
       }
     }
     if (cfg_.batch_sectors) {
-      std::vector<CorrelationResult> rs((size_t)hs * vs);
-      cuda_.correlateBatch(0, hs * vs, guesses.data(), rs.data());
-      for (int k = 0; k < hs * vs; ++k) { update_results(results_[k], rs[k]); error = error || results_[k].error_status; }
+      // extension: every subset of the frame in one launch. There is no "first sector that failed" inside a
+      // launch, so stopFrame / stopAll act on the frame as a whole (error_ = any sector failed).
+      const int n = hs * vs;
+      bool bad_domain = false;
+      if (frame == 0 && cuda_.resetPolygonGrid(0, n, boxes.data()) != error_none) bad_domain = true;
+      std::vector<CorrelationResult> rs((size_t)n);
+      const int rc = cuda_.correlateBatch(0, n, guesses.data(), rs.data());
+      error_ = false;
+      for (int k = 0; k < n; ++k) {
+        if (rc == DIC_ERROR_BAD_ARGUMENT || rc == DIC_ERROR_CUDA) { // the launch itself failed: no record is valid
+          results_[k].error_status = true; results_[k].error_code = (errorEnum)(rc == DIC_ERROR_CUDA ? error_cuda : error_bad_domain);
+        } else {
+          update_results(results_[k], rs[k]);
+        }
+        error_ = error_ || results_[k].error_status;
+      }
+      error_ = error_ || bad_domain;
     }
     update_global_results();
-    return error;
+    return error_;
   }
 
   bool frame_annular(int frame) {
     const int rs = cfg_.radial_subdivisions, as = cfg_.angular_subdivisions;
     const float ri = cfg_.r_inside, ro = cfg_.r_outside;
     const float dr = (ro - ri) / (float)rs, da = 2.f * PI / (float)as;
-    bool error = false;
-    for (int i = 0; i < rs; ++i)
+    bool stop = false;
+    for (int i = 0; i < rs && !stop; ++i)
       for (int j = 0; j < as; ++j) {
         const int iSector = i * as + j;
         SectorState &s = results_[iSector];
@@ -276,7 +310,9 @@ class HeadlessManager {
         adjust_initial_guess(s, frame);
         if (frame == 0) {
           if (cuda_.resetPolygon(iSector, r, dr, a, da, cx, cy, as) != error_none) {
-            s.error_status = true; s.error_code = error_bad_domain; error = true; continue;
+            s.error_status = true; s.error_code = error_bad_domain; error_ = true;
+            if (stops_frame()) { stop = true; break; }
+            continue;
           }
         } else if (cfg_.deformationDescription != def_Eulerian) {
           cuda_.updatePolygon(iSector, cfg_.deformationDescription);
@@ -284,15 +320,16 @@ class HeadlessManager {
         float guess[DIC_MAX_PARAMS];
         for (int p = 0; p < np_; ++p) guess[p] = s.initial_guess[p];
         update_results(s, *cuda_.correlate(iSector, guess));
-        error = error || s.error_status;
+        error_ = s.error_status; // :713
+        if (stops_frame()) { stop = true; break; } // :795-796
       }
     update_global_results();
-    return error;
+    return error_;
   }
 
   bool frame_blob(int frame) {
     SectorState &s = results_[0];
-    if (cfg_.xy_contour.size() < 3) { s.error_status = true; s.error_code = error_bad_domain; return true; }
+    if (cfg_.xy_contour.size() < 3) { s.error_status = true; s.error_code = error_bad_domain; error_ = true; return true; }
     if (frame == 0) { // adjust_blob_domain :2247-2262, centre = mean of the contour (parameters.cpp:35-53)
       float xc = 0, yc = 0;
       for (auto &q : cfg_.xy_contour) { xc += q.first; yc += q.second; }
@@ -306,7 +343,7 @@ class HeadlessManager {
     adjust_initial_guess(s, frame);
     if (frame == 0) {
       if (cuda_.resetPolygon(cfg_.xy_contour) != error_none) { // manager_class.cpp:1026-1030
-        s.error_status = true; s.error_code = error_bad_domain; return true;
+        s.error_status = true; s.error_code = error_bad_domain; error_ = true; return true;
       }
     } else if (cfg_.deformationDescription != def_Eulerian) {
       cuda_.updatePolygon(0, cfg_.deformationDescription);
@@ -314,8 +351,9 @@ class HeadlessManager {
     float guess[DIC_MAX_PARAMS];
     for (int p = 0; p < np_; ++p) guess[p] = s.initial_guess[p];
     update_results(s, *cuda_.correlate(0, guess));
+    error_ = s.error_status; // :1154
     update_global_results();
-    return s.error_status;
+    return error_;
   }
 
 public:
@@ -328,6 +366,7 @@ public:
     cuda_.set_arith_mode(cfg.arith_mode);
   }
   CudaClass &engine() { return cuda_; }
+  int frames_done() const { return frames_done_; } // frame pairs that reached the report (stopAll ends early)
   const std::vector<SectorState> &results() const { return results_; }
   std::string report() const { return report_.str(); }
 
@@ -337,6 +376,7 @@ public:
     const int n_sectors = cfg_.domain_type == domain_rectangular ? cfg_.horizontal_subdivisions * cfg_.vertical_subdivisions
                         : cfg_.domain_type == domain_annular ? cfg_.radial_subdivisions * cfg_.angular_subdivisions : 1;
     results_.assign(n_sectors, SectorState());
+    frames_done_ = 0;
     initializeReport();
     if (frames.size() < 2) return true;
     auto name = [&](size_t k) { return names && k < names->size() ? (*names)[k] : ("frame" + std::to_string(k)); };
@@ -344,6 +384,7 @@ public:
     cuda_.resetImagePyramids(frames[0], frames[1], frames.size() > 2 ? frames[2] : nullptr, rows, cols, color_monochrome,
                              cfg_.pyramid_start, cfg_.pyramid_step, cfg_.pyramid_stop);
     bool error = false;
+    error_ = false;
     const int total_frame_pairs = (int)frames.size() - 1;
     for (int frame = 0; frame < total_frame_pairs; ++frame) {
       if (frame > 0) {
@@ -359,8 +400,10 @@ public:
       case domain_annular: error = frame_annular(frame); break;
       default: error = frame_blob(frame); break;
       }
-      if (prefetch && loader.get() != error_none) error = true;
+      if (prefetch && loader.get() != error_none) error = error_ = true; // :1469-1474 (error_multiThread)
       addFrameToReport(frame, name(cfg_.referenceImage == refImage_First ? 0 : frame), name(frame + 1));
+      frames_done_ = frame + 1;
+      if (error && cfg_.error_handling_mode == errorMode_stopAll) break; // :1493
     }
     return error;
   }

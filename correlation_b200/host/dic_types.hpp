@@ -19,6 +19,7 @@ enum errorEnum {
 };
 enum colorEnum { color_monochrome, color_color, color_NUMBER_OF_ITEMS };
 enum deformationDescriptionEnum { def_strict_Lagrangian, def_Lagrangian, def_Eulerian, def_NUMBER_OF_ITEMS };
+enum errorHandlingModeEnum { errorMode_stopAll, errorMode_stopFrame, errorMode_continue, errorMode_NUMBER_OF_ITEMS };
 enum referenceImageEnum { refImage_First, refImage_Previous, refImage_NUMBER_OF_ITEMS };
 typedef std::vector<std::pair<float, float>> v_points;
 struct frame_results; // the manager's bookkeeping record; correlate() never reads it (cuda_class.cu:104-293)

@@ -158,6 +158,12 @@ int dic_reset_polygon_blob(dic_engine *e, int iSector, const float *contour_xy, 
  * centre, point counts and chi scaling stay those of the whole rectangle. Use with dic_rowsplit_*. */
 int dic_reset_polygon_rect_band(dic_engine *e, int iSector, int x0, int y0, int x1, int y1, int band_y0,
                                 int band_y1);
+/* extension (BASELINE config 4): n rectangles at once -- the result of n calls
+ * dic_reset_polygon_rect(first_sector + k, boxes[4k], boxes[4k+1], boxes[4k+2], boxes[4k+3]), which is what the
+ * subdivision loop of manager_class.cpp:274-336 issues on frame 0, built by one list kernel and one tile kernel
+ * over all sectors and levels. Returns DIC_ERROR_BAD_DOMAIN if any rectangle is empty at a used level (those
+ * sectors stay undefined, the others are valid). */
+int dic_reset_polygon_rect_grid(dic_engine *e, int first_sector, int n, const int *boxes);
 /* extension: an arbitrary point list (what CorrelationClass::Newton_Raphson(guess, N, xy) takes,
  * correlation_class.cpp:326-343). use_center: 0 = derive per the centre mode. */
 int dic_reset_polygon_points(dic_engine *e, int iSector, const float *xy, int64_t n,
@@ -178,6 +184,11 @@ int dic_correlate(dic_engine *e, int iSector, float *guess_inout, dic_result *ou
  * launch. guesses: n_sectors x n_params (row-major), overwritten; results: n_sectors entries. */
 int dic_correlate_batch(dic_engine *e, int first_sector, int n_sectors, float *guesses_inout,
                         dic_result *results);
+/* extension: how dic_correlate_batch maps sectors to thread blocks. 0 (default) = automatic: one CTA per
+ * sector, or one CTA PAIR per sector (thread-block cluster of 2, partial sums exchanged through distributed
+ * shared memory) when that fills the GPU's last wave better; 1 = always one CTA; 2 = always a pair.
+ * Results are identical to ~1 ulp of the sums (the two halves are added in a fixed order). */
+int dic_set_cluster_mode(dic_engine *e, int mode);
 /* extension: enqueue only (no host sync); dic_correlate_wait collects. Lets a caller overlap
  * the next upload with the solve, and lets bench.py time the device alone. */
 int dic_correlate_async(dic_engine *e, int iSector, const float *guess);
@@ -218,7 +229,8 @@ int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float la
 /* device-side time of the last correlate / correlate_batch launch in milliseconds (CUDA events
  * on the correlation stream) and how many kernels this engine has launched so far */
 float dic_last_correlate_ms(dic_engine *e);
-/* the same over the whole GPU side of the call: guess upload, solve kernel(s), result download */
+/* the same over the whole GPU side of the call: solve kernel(s) and result download (the guess travels in the
+ * kernel parameters / is read from pinned memory by the kernel: no upload) */
 float dic_last_step_ms(dic_engine *e);
 /* CTA 0's timeline of the last single-sector correlate: per evaluation 4 device timestamps (ns):
  * pass start, own pass done, all CTAs arrived, LM step published. Returns the evaluation count. */
