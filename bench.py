@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- domain pixel*GN-evaluations / s of the DIC hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1|c5|c3] [--impl ours|reference]
 
-A *step* is one correlate() of the workload's domain from the zero initial guess: every pyramid
-level, every LM iteration, reduction and solve (correlation_class.cpp:349-640 semantics), on image
-pyramids already resident in HBM.  Work per step = sum over levels of N_level x evaluations_level
-(SURVEY.md section 8d), reported by the engine itself.
+Default workload = BASELINE config 4 for EVERY N: the 8192^2 pair whose domain is subdivided into 64 x 64 = 4096
+subsets of 125^2 (affine model, pyramid 0/1/2), the subsets sharded over the N GPUs in whole rows of subsets
+(strong scaling, no data-path collective; manager_class.cpp:304-547 is the serial loop this replaces). It is the
+workload the north star's 1/2/4/8-GPU target is quoted on, it fits one GPU, and its CPU arm is the UNMODIFIED
+reference engine (oracle/_ref). A *step* is one pass of the hot path over the whole domain from the zero initial
+guess: every pyramid level, every LM iteration, reduction and solve of every subset
+(correlation_class.cpp:349-640 semantics). Work per step = sum over subsets and levels of N_level x
+evaluations_level, reported by the engine itself.
 
-  value     pixel*evaluations / s, device-resident inputs, all ranks (weak scaling: every rank
-            solves its own independent domain, no data-path collective)
-  e2e       same metric through the C-ABI with HOST (pinned) images: per step H2D of the image
-            pair, both pyramid builds, correlate, D2H of the result record
-  roofline  the fused GN kernel against the measured HBM copy bandwidth, with SURVEY 8d's
-            10 algorithmic bytes per pixel*evaluation
+  value     pixel*evaluations / s, device-resident inputs, all ranks (CUDA events, max over ranks)
+  e2e       same metric through the C-ABI with HOST (pinned) images: per step H2D of this rank's band of the
+            image pair, both pyramid builds, correlate, D2H of the result records
+  parity    results against the fp64-accumulator oracle on a stratified sample of subsets and, at N > 1, the
+            gathered records of all ranks bit-compared with rank 0's own single-GPU run of all 4096 subsets
+  roofline  the fused GN kernel against the measured HBM copy bandwidth, with SURVEY 8d's 10 algorithmic bytes
+            per pixel*evaluation
+  other_workloads   short runs of config 2 (one 9 M-pixel annulus, 12 parameters; N = 1) and config 5 (one 236 M
+            pixel domain row-split over the ranks with the in-kernel NVLink all-reduce; N > 1), each with its own
+            parity block
   cpu_baseline / --impl reference
-            the reference CPU algorithm on this box's host cores: oracle/_ref (unmodified
-            reference, 6-parameter workloads) or the oracle port (12-parameter workload, which the
-            reference does not have), all host threads.
+            the reference CPU algorithm on this box's host cores: oracle/_ref (unmodified reference, 6-parameter
+            workloads) or the oracle port (12-parameter workload, which the reference does not have).
 """
 from __future__ import annotations
 
@@ -35,6 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_PIXEL_EVAL = 10.0  # 8 B coordinates + 1 B und + 1 B def
+TOLERANCES = {"duv": 1e-4, "dgrad": 1e-6, "rel_dchi": 1e-5, "iterations": 1}  # BASELINE.json north_star
 
 
 # ------------------------------------------------------------------------------ workloads
@@ -42,28 +50,28 @@ ALGO_BYTES_PER_PIXEL_EVAL = 10.0  # 8 B coordinates + 1 B und + 1 
 def workload(name):
     two_pi = 2.0 * np.pi
     if name == "c1":  # BASELINE config 1 (the reference's CPU-runnable case)
-        return dict(name="c1: 1024^2 pair, 511x511 rect, affine 6-param, bicubic, pyramid 0/1/2",
+        return dict(key="c1", name="c1: 1024^2 pair, 511x511 rect, affine 6-param, bicubic, pyramid 0/1/2",
                     rows=1024, cols=1024, seed=1, model="affine", pyramid=(0, 1, 2),
                     truth=(1.75, -0.6, .004, -.003, .002, .005), center=(512.0, 512.0),
                     domain=("rect", 257, 257, 767, 767))
-    if name == "c2":  # BASELINE config 2: the configuration the metric is quoted on
-        return dict(name="c2: 4096^2 pair, annulus ri=600 ro=1800, quadratic 12-param, bicubic, pyramid 0..3",
+    if name == "c2":  # BASELINE config 2
+        return dict(key="c2", name="c2: 4096^2 pair, annulus ri=600 ro=1800, quadratic 12-param, bicubic, pyramid 0..3",
                     rows=4096, cols=4096, seed=2, model="quad", pyramid=(0, 1, 3),
                     truth=(2.5, -1.75, .002, -.0015, .001, .0025, 1e-6, -5e-7, 8e-7, -1e-6, 6e-7, 4e-7),
                     center=(2048.0, 2048.0), domain=("annulus", 600.0, 1200.0, 0.0, two_pi, 2048.0, 2048.0, 1))
-    if name == "c4":  # BASELINE config 4: 4096 subsets of 125^2
-        return dict(name="c4: 8192^2 pair, 64x64 subsets of 125^2, affine, pyramid 0/1/2",
+    if name == "c4":  # BASELINE config 4: 4096 subsets of 125^2 -- the default for every N
+        return dict(key="c4", name="c4: 8192^2 pair, 64x64 subsets of 125^2, affine, pyramid 0/1/2",
                     rows=8192, cols=8192, seed=4, model="affine", pyramid=(0, 1, 2),
                     truth=(1.25, -0.75, .0004, -.0003, .0002, .0005), center=(4096.0, 4096.0),
                     domain=("subsets", 64, 8128, 64))
     if name == "c3":  # BASELINE config 3: frames/s of a 100-frame sequence
-        return dict(name="c3: 100-frame 2048^2 sequence, 64-vertex star blob (mean radius 700), affine, pyramid 0/1/2, "
-                         "Eulerian + first-image reference, constant-velocity initial guess",
+        return dict(key="c3", name="c3: 100-frame 2048^2 sequence, 64-vertex star blob (mean radius 700), affine, pyramid 0/1/2, "
+                                   "Eulerian + first-image reference, constant-velocity initial guess",
                     rows=2048, cols=2048, seed=3, model="affine", pyramid=(0, 1, 2), frames=100,
                     rate=(0.8, -0.5, 0.0, -0.0005, 0.0005, 0.0), center=(1024.0, 1024.0),
                     truth=(0.8, -0.5, 0.0, -0.0005, 0.0005, 0.0), domain=("blob", 1024.0, 1024.0, 700.0, 64))
     if name == "c5":  # BASELINE config 5: one huge domain, row-split across GPUs
-        return dict(name="c5: 16384^2 pair, one 15361^2 rect domain, affine, pyramid 0..4, row-split + in-kernel all-reduce",
+        return dict(key="c5", name="c5: 16384^2 pair, one 15361^2 rect domain, affine, pyramid 0..4, row-split + in-kernel all-reduce",
                     rows=16384, cols=16384, seed=5, model="affine", pyramid=(0, 1, 4),
                     truth=(25.0, -15.0, .004, -.003, .002, .005), center=(8192.0, 8192.0),
                     domain=("rowsplit", 512, 512, 15872, 15872), spectrum=(5.0, 600.0), n_waves=64)
@@ -98,6 +106,29 @@ def upload_band(y_first, y_last, rows, pyramid_stop):
     at every cut (dic_stage_next_pair_rows)."""
     halo = 64 + (8 << pyramid_stop)
     return max(0, y_first - halo), min(rows, y_last + 1 + halo)
+
+
+def stratified_sample(n_units, n_sample):
+    """n_sample unit ids spread evenly over 0..n_units-1 (first and last included)."""
+    if n_sample >= n_units:
+        return list(range(n_units))
+    return sorted({int(round(k * (n_units - 1) / (n_sample - 1))) for k in range(n_sample)})
+
+
+def parity_block(gpu_params, gpu_chi, gpu_iters, want_params, want_chi, want_iters, n_grad_to=6):
+    """Worst deviations of GPU results from oracle results (arrays over the compared units) and the verdict."""
+    gp, wp = np.atleast_2d(np.asarray(gpu_params, np.float64)), np.atleast_2d(np.asarray(want_params, np.float64))
+    gc, wc = np.atleast_1d(np.asarray(gpu_chi, np.float64)), np.atleast_1d(np.asarray(want_chi, np.float64))
+    gi, wi = np.atleast_1d(np.asarray(gpu_iters)), np.atleast_1d(np.asarray(want_iters))
+    duv = float(np.abs(gp[:, :2] - wp[:, :2]).max())
+    dgrad = float(np.abs(gp[:, 2:n_grad_to] - wp[:, 2:n_grad_to]).max()) if gp.shape[1] > 2 else 0.0
+    rel = np.abs(gc - wc) / np.maximum(np.abs(wc), 1e-30)
+    dit = int(np.abs(gi.astype(np.int64) - wi.astype(np.int64)).max())
+    ok = duv < TOLERANCES["duv"] and dgrad < TOLERANCES["dgrad"] and float(rel.max()) <= TOLERANCES["rel_dchi"] and dit <= 1
+    return {"units_compared": int(gp.shape[0]), "max_abs_duv": duv, "max_abs_dgrad": dgrad,
+            "max_rel_dchi": float(rel.max()), "median_rel_dchi": float(np.median(rel)),
+            "units_with_rel_dchi_above_1e-5": int((rel > 1e-5).sum()), "max_abs_diterations": dit,
+            "tolerances": TOLERANCES, "within_tolerance": bool(ok)}
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -174,9 +205,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------ CPU reference arm
 
-def cpu_run(w, und, dfm, threads, sample_levels=None):
+def cpu_run(w, und, dfm, threads):
     """One 'step' of the reference CPU algorithm: both pyramid builds + Newton_Raphson (cold cache).
-    Returns (pixel_evaluations, seconds, kind, result)."""
+    Returns (pixel_evaluations, seconds, kind, result, sample, pyramid_seconds)."""
     import oracle
     use_ref = oracle.have_ref() and w["model"] == "affine" and w["rows"] <= 8192  # reference cache overflows int above ~11k^2
     pyr = w["pyramid"]
@@ -200,7 +231,8 @@ def cpu_run(w, und, dfm, threads, sample_levels=None):
     elif d[0] == "annulus":
         xy, center = oracle.annulus_points(*d[1:]), None
     else:  # subsets: a bounded sample of the 4096 subsets, run one after the other like the manager
-        boxes = subset_boxes(d[1], d[2], d[3])[:: max(1, (d[3] * d[3]) // 64)]
+        all_boxes = subset_boxes(d[1], d[2], d[3])
+        boxes = [all_boxes[i] for i in stratified_sample(len(all_boxes), 64)]
         xy, center = None, None
     n_par = 12 if w["model"] == "quad" else 6
     if counter is not None:
@@ -225,13 +257,14 @@ def cpu_run(w, und, dfm, threads, sample_levels=None):
             res = eng.correlate(np.zeros(n_par, np.float32), pts, center=c)
             secs += time.perf_counter() - t1
             work += res.get("pixel_evaluations") or counter.correlate(np.zeros(n_par, np.float32), pts, center=c)["pixel_evaluations"]
-        sample = f"{len(boxes)} of {d[3] * d[3]} subsets, one cold step"
+        sample = (f"{len(boxes)} of {d[3] * d[3]} subsets (stratified), one after the other as the manager does, one cold "
+                  f"step: both 8192^2 pyramid builds + Newton_Raphson per subset; {threads} threads per evaluation")
     return work, secs, ("reference" if use_ref else "port"), res, sample, t_pyr
 
 
 # ------------------------------------------------------------------------------ config 3: frames / s
 
-def run_c3(args, w):
+def run_c3(args, w, with_cpu=True):
     """The frame loop of the headless C++ host (correlation_b200/host/dic_manager.hpp) on pinned host
     frames: per frame H2D of the next image (second stream, overlapped), pyramid, rotation, GN."""
     import torch
@@ -255,7 +288,8 @@ def run_c3(args, w):
             r = host.run_sequence(frames, contour=contour, pyramid=w["pyramid"], arith_mode=mode)
             if i >= args.warmup:
                 runs.append(r)
-    secs = sum(r["seconds"] for r in runs) / len(runs)
+    secs_all = [r["seconds"] for r in runs]
+    secs = sum(secs_all) / len(runs)
     fps = (n - 1) / secs
     hdr, rows = host.parse_report(runs[-1]["csv"])
     last = runs[-1]["rows"][0]
@@ -265,34 +299,429 @@ def run_c3(args, w):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic analytic speckle sequence, constant velocity",
             "config": {"workload": w["name"], "arith_mode": args.mode, "frame_pairs": n - 1,
                        "points": int(last["number_of_points"]), "errors": int(sum(int(r["error_code"]) != 0 for r in rows)),
+                       "ms_per_frame": 1e3 * secs / (n - 1),
+                       "ms_per_frame_spread": [1e3 * min(secs_all) / (n - 1), 1e3 * max(secs_all) / (n - 1)],
                        "last_frame_params": [float(v) for v in last["params"][:6]],
                        "last_frame_truth": [float(v) for v in truth_last],
                        "step": "one step = the whole 99-pair sequence through dic_host_run (C++ host loop)"},
             "clocks": clk.summary(),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": n * w["rows"] * w["cols"],
                     "d2h_bytes_per_step": 176 * (n - 1)},
-            "gpu_launches": (n - 1) * 5,
+            "gpu_launches": (n - 1) * 4,
             "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "frames/s is a pipeline metric (upload + pyramid + GN per frame); see the c2 / c4 lines for the kernel roofline"}}
-    if not args.no_cpu_baseline:
+                         "note": "frames/s is a pipeline metric (upload + pyramid + GN per frame); see the c4 / c2 lines for the kernel roofline"}}
+    if with_cpu:
         import oracle
+        # the same bookkeeping on the CPU oracle (fp64 accumulators): first frames timed as the baseline, and the
+        # GPU's report rows of those frames checked against it
         t0 = time.perf_counter()
-        O = oracle.OracleEngine(n_threads=os.cpu_count() or 1, pyramid=w["pyramid"], real_threads=True)
+        O = oracle.OracleEngine(n_threads=os.cpu_count() or 1, pyramid=w["pyramid"], real_threads=True, accum_double=True)
         O.set_image("und", frames[0])
         xy = oracle.blob_points(contour)
         p = np.zeros(6, np.float32)
         p_prev = p.copy()
         nf = 4
+        want = []
         for k in range(nf):
             O.set_image("def", frames[k + 1])
             guess = p + (p - p_prev) if k else p
             p_prev = p
-            p = O.correlate(guess, xy)["params"]
+            r = O.correlate(guess, xy)
+            p = r["params"]
+            want.append(r)
         cs = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": nf / cs, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"first {nf} frame pairs of the sequence (pyramid + Newton_Raphson each)"}
-    print(json.dumps(line), flush=True)
-    return 0
+        gp = np.array([[rows[k][f"parameter_{q}"] for q in range(6)] for k in range(nf)])
+        line["parity"] = {"vs_oracle_first_frames": parity_block(
+            gp, [rows[k]["chi"] for k in range(nf)], [rows[k]["iterations"] for k in range(nf)],
+            [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want]),
+            "note": "GPU values are the 6-significant-digit CSV report rows of the first frames (constant-velocity guesses "
+                    "included); the oracle runs the same sequence with fp64 accumulators"}
+    return line
+
+
+# ------------------------------------------------------------------------------ one workload on the GPU(s)
+
+class Run:
+    """One workload set up on this rank's GPU: images resident and pinned, engine, domain(s) built."""
+
+    def __init__(self, args, w, dist, rank, world, local_rank):
+        import torch
+        from correlation_b200 import engine
+        self.args, self.w, self.dist, self.rank, self.world = args, w, dist, rank, world
+        self.torch, self.engine = torch, engine
+        self.dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(self.dev)
+        self.n_par = 12 if w["model"] == "quad" else 6
+        self.und_t, self.dfm_t = make_images(w, self.dev)
+        self.und_pin = torch.empty(self.und_t.shape, dtype=torch.uint8, pin_memory=True)
+        self.dfm_pin = torch.empty(self.dfm_t.shape, dtype=torch.uint8, pin_memory=True)
+        self.und_pin.copy_(self.und_t)
+        self.dfm_pin.copy_(self.dfm_t)
+        torch.cuda.synchronize()
+        self.mode = engine.MODE_PARITY if args.mode == "parity" else engine.MODE_FAST
+        self.eng = engine.CudaEngine(local_rank, fitting_model=engine.FM_QUADRATIC if w["model"] == "quad" else engine.FM_UVUxUyVxVy,
+                                     arith_mode=self.mode)
+        rows, cols = w["rows"], w["cols"]
+        self.eng.resetImagePyramidsDevice(self.und_t.data_ptr(), self.dfm_t.data_ptr(), None, rows, cols, cols, pyramid=w["pyramid"])
+        d = w["domain"]
+        self.scaling = "weak"
+        self.all_boxes = self.my_ids = None
+        self.band_rows = None
+        t_dom = time.perf_counter()
+        if d[0] in ("rect", "annulus"):
+            self.eng.resetPolygon(0, *d[1:])
+            self.n_sectors = 1
+        elif d[0] == "rowsplit":
+            # one domain, pixel rows in equal bands per rank, per-evaluation sum inside the kernel
+            from correlation_b200 import rowsplit
+            rowsplit.connect(self.eng, dist)
+            self.band_rows = rowsplit.equal_row_bands(d[2], d[4], world)[rank]
+            self.eng.resetPolygonRectBand(0, d[1], d[2], d[3], d[4], *self.band_rows)
+            self.n_sectors = 1
+            self.scaling = "strong"
+        else:
+            # independent subsets shard across ranks in whole rows of subsets (SURVEY 8e): each rank then needs
+            # only a band of image rows for the end-to-end path; no collective on the data path
+            from correlation_b200 import sharding
+            self.all_boxes = subset_boxes(d[1], d[2], d[3])
+            self.my_ids = sharding.shard_grid_rows(d[3], d[3], world, rank)
+            self.eng.resetPolygonRectGrid(0, np.array([self.all_boxes[i] for i in self.my_ids], np.int32))
+            self.n_sectors = len(self.my_ids)
+            self.scaling = "strong"
+        self.eng.synchronize()
+        self.domain_build_s = time.perf_counter() - t_dom
+        self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=self.dev)
+        self.res_buf = np.zeros(self.n_sectors, engine.RESULT_DTYPE)
+        self.guess_buf = np.zeros((self.n_sectors, self.n_par), np.float32)
+        self.one_guess = np.zeros(self.n_par, np.float32)
+        self.one_result = engine.DicResult()
+        # a rank that owns a band of the image (sharded subsets, row-split domain) transfers only its rows plus
+        # a halo for displacement, bicubic support and pyramid support (dic_stage_next_pair_rows)
+        self.band = None
+        if world > 1 and d[0] == "rowsplit":
+            self.band = upload_band(self.band_rows[0], self.band_rows[1], rows, w["pyramid"][2])
+        elif world > 1 and d[0] == "subsets":
+            mine = [self.all_boxes[i] for i in self.my_ids]
+            self.band = upload_band(min(bx[1] for bx in mine), max(bx[3] for bx in mine), rows, w["pyramid"][2])
+        self.h2d_bytes = 2 * cols * ((self.band[1] - self.band[0]) if self.band else rows)
+
+    # -- one step, inputs resident
+    def step_resident(self):
+        eng, engine = self.eng, self.engine
+        if self.n_sectors == 1:
+            self.one_guess[:] = 0.0
+            eng.correlate_raw(0, self.one_guess, self.one_result)
+            work = 0.0
+            for lv in range(engine.MAX_LEVELS):
+                work += float(self.one_result.evaluationsPerLevel[lv]) * float(self.one_result.pointsPerLevel[lv])
+            if self.w["domain"][0] == "rowsplit":
+                work /= self.world  # the record counts the whole domain; this rank evaluated its band of it
+            return work, eng.last_correlate_ms(), self.one_result
+        self.guess_buf[:] = 0.0
+        eng.lib.dic_correlate_batch(eng.h, 0, self.n_sectors, self.guess_buf.ctypes.data, self.res_buf.ctypes.data)
+        return eng.pixel_evaluations(self.res_buf), eng.last_correlate_ms(), self.res_buf
+
+    def stage_pair(self):
+        # this step's inputs: both images from pinned host memory, upload + pyramids on the copy / image streams
+        self.eng.stageNextPair(self.und_pin.data_ptr(), self.dfm_pin.data_ptr(), self.w["rows"], self.w["cols"], row_range=self.band)
+
+    def e2e_loop(self, n):
+        # double-buffered ingest (dic_stage_next_pair / dic_advance_pair): the PCIe transfer of pair k + 1
+        # overlaps the solve of pair k; every step copies its own pair and reads its own result record(s)
+        tot = 0.0
+        self.stage_pair()
+        for k in range(n):
+            self.eng.advancePair()
+            if k + 1 < n:
+                self.stage_pair()
+            wk, _, _ = self.step_resident()
+            tot += wk
+        return tot
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def last_record(self):
+        if self.n_sectors == 1:
+            return self.one_result.as_dict(self.n_par)
+        rs = self.res_buf
+        return dict(params=rs[0]["resultingParameters"][:self.n_par].copy(), chi=rs[0]["chi"],
+                    iterations=int(rs[0]["iterations"]), evaluations=rs[0]["evaluationsPerLevel"].tolist(),
+                    points_per_level=rs[0]["pointsPerLevel"].tolist(), errors=int((rs["errorCode"] != 0).sum()))
+
+    def measure(self, steps, warmup, with_other_mode=True):
+        """Timed resident steps, timed end-to-end steps, the other arithmetic mode. Returns a dict of reduced numbers
+        (identical on every rank for the reduced entries)."""
+        torch, eng, dist = self.torch, self.eng, self.dist
+        for _ in range(warmup):
+            self.step_resident()
+        launches0 = eng.kernel_launches()
+        self.barrier()
+        # Timed on the DEVICE: CUDA events on the correlation stream around the whole GPU side of each step (solve
+        # kernel, result download), summed over the K steps, max over ranks. The L2 flush between steps is outside
+        # the events. The host clock around the same calls is reported beside it (host_ms_per_step).
+        work = kern_ms = wall = host_wall = 0.0
+        with ClockSampler(self.dev.index, self.world) as clk:
+            for _ in range(steps):
+                self.flush.fill_(1)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                wk, ms, _ = self.step_resident()
+                host_wall += time.perf_counter() - t0
+                wall += 1e-3 * eng.last_step_ms()
+                work += wk
+                kern_ms += ms
+        self.barrier()
+        launches = eng.kernel_launches() - launches0
+        last = self.last_record()
+        resident_records = self.res_buf.copy() if self.n_sectors > 1 else None
+        # e2e: host buffers, copies inside the timed region
+        self.e2e_loop(2)
+        self.barrier()
+        t0 = time.perf_counter()
+        e2e_work = self.e2e_loop(steps)
+        self.barrier()
+        e2e_wall = time.perf_counter() - t0
+        o_val = None
+        if with_other_mode:  # the other arithmetic mode, same resident inputs, for the record
+            other = self.engine.MODE_PARITY if self.mode == self.engine.MODE_FAST else self.engine.MODE_FAST
+            eng.set_arith_mode(other)
+            for _ in range(2):
+                self.step_resident()
+            o_work = o_ms = 0.0
+            for _ in range(max(2, steps // 2)):
+                self.flush.fill_(1)
+                torch.cuda.synchronize()
+                wk, ms, _ = self.step_resident()
+                o_work += wk
+                o_ms += ms
+            eng.set_arith_mode(self.mode)
+            o_val = o_work / (o_ms * 1e-3) if o_ms > 0 else None
+        stats = torch.tensor([wall, e2e_wall, work, e2e_work, kern_ms, host_wall], dtype=torch.float64, device=self.dev)
+        my_work, my_kern_ms = work, kern_ms
+        if dist is not None:
+            mx = stats.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stats.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            wall, e2e_wall, host_wall = mx[0].item(), mx[1].item(), mx[5].item()
+            work, e2e_work = sm[2].item(), sm[3].item()
+        return dict(wall=wall, e2e_wall=e2e_wall, host_wall=host_wall, work=work, e2e_work=e2e_work, my_work=my_work,
+                    my_kern_ms=my_kern_ms, launches=launches, last=last, clocks=clk.summary(), other_mode_value=o_val,
+                    resident_records=resident_records)
+
+    # -- parity
+    def gather_records(self, local):
+        """All ranks' records in global sector order on rank 0 (None elsewhere). Collective."""
+        n_total = len(self.all_boxes)
+        if self.dist is None:
+            full = np.zeros(n_total, local.dtype)
+            full[self.my_ids] = local
+            return full
+        torch = self.torch
+        item = local.dtype.itemsize
+        per = -(-n_total // self.world) + 64
+        buf = torch.zeros(per * item, dtype=torch.uint8, device=self.dev)
+        raw = torch.from_numpy(np.frombuffer(local.tobytes(), np.uint8).copy())
+        buf[: raw.numel()] = raw.to(self.dev)
+        out = [torch.zeros_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(out, buf)
+        if self.rank != 0:
+            return None
+        from correlation_b200 import sharding
+        d = self.w["domain"]
+        full = np.zeros(n_total, local.dtype)
+        for r in range(self.world):
+            ids = sharding.shard_grid_rows(d[3], d[3], self.world, r)
+            full[ids] = np.frombuffer(out[r].cpu().numpy().tobytes()[: len(ids) * item], local.dtype)
+        return full
+
+    def parity_subsets(self, records, n_sample):
+        """records: all subsets in global order (rank 0). Oracle with fp64 accumulators on a stratified sample."""
+        import oracle
+        w = self.w
+        und, dfm = self.und_pin.numpy(), self.dfm_pin.numpy()
+        o = oracle.OracleEngine(model=oracle.FM_AFFINE, n_threads=os.cpu_count() or 1, pyramid=w["pyramid"],
+                                accum_double=True, real_threads=True)
+        o.set_image("und", und)
+        o.set_image("def", dfm)
+        ids = stratified_sample(len(self.all_boxes), n_sample)
+        want = []
+        for i in ids:
+            bx = self.all_boxes[i]
+            want.append(o.correlate(np.zeros(6, np.float32), oracle.rect_points(*bx), center=((bx[0] + bx[2]) / 2.0, (bx[1] + bx[3]) / 2.0)))
+        blk = parity_block(records["resultingParameters"][ids, :6], records["chi"][ids], records["iterations"][ids],
+                           [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want])
+        blk["errors"] = [int((records["errorCode"][ids] != 0).sum()), int(sum(r["error_code"] != 0 for r in want))]
+        blk["sample"] = f"{len(ids)} of {len(self.all_boxes)} subsets, stratified over the sector ids"
+        return blk
+
+    def close(self):
+        try:
+            if self.w["domain"][0] == "rowsplit":
+                self.eng.rowsplit_disconnect()
+        except Exception:
+            pass
+        self.eng.close()
+        del self.flush, self.und_t, self.dfm_t
+        self.torch.cuda.empty_cache()
+
+
+def roofline_block(args, w, m, peaks):
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gn_solve_tiles_kernel"].get(f"{w['key']} {args.mode}")
+        if tr:
+            traffic = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
+    except Exception:
+        pass
+    achieved = ALGO_BYTES_PER_PIXEL_EVAL * m["my_work"] / (m["my_kern_ms"] * 1e-3) / 1e9 if m["my_kern_ms"] > 0 else 0.0
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_note": "bytes per launch on ONE GPU at N = 1 (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json); "
+                            "algorithmic bytes per launch = 10 B x this rank's pixel_evaluations_per_step",
+            "kernel": "gn_solve_tiles_kernel", "kernel_ms_per_step": m["my_kern_ms"] / max(1, args.steps_used),
+            "rank_pixel_evaluations_per_step": m["my_work"] / max(1, args.steps_used),
+            "fp32_note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md 4.1): parity mode replays the reference's "
+                         "unfused fp32 operations per pixel; the level data stays L2-resident across evaluations. "
+                         "ncu summaries under profiles/",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+            "algorithmic_bytes_per_pixel_evaluation": ALGO_BYTES_PER_PIXEL_EVAL}
+
+
+def record_for(args, run, m, steps, peaks):
+    """The contract's JSON fields for one measured workload (rank 0)."""
+    w, world = run.w, run.world
+    d = w["domain"]
+    args.steps_used = steps
+    last = m["last"]
+    par = (f"one domain in {world} row band(s), per-evaluation all-reduce of the normal equations inside the kernel (NVLink peer mailboxes)"
+           if d[0] == "rowsplit" else
+           f"{d[3] * d[3]} subsets, whole rows of subsets per GPU, over {world} GPU(s), no collective"
+           if d[0] == "subsets" else f"{world} independent domain(s), one per GPU")
+    return {
+        "metric": "domain pixel*GN-evaluations/s", "value": m["work"] / m["wall"], "unit": "pixel*evaluations/s",
+        "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * m["wall"] / steps,
+        "host_ms_per_step": 1e3 * m["host_wall"] / steps,
+        "timing": "CUDA events on the correlation stream around each step's device work, summed over the steps, max over ranks",
+        "higher_is_better": True, "scaling": run.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic analytic speckle (SURVEY 8d), random phases seeded",
+        "config": {"workload": w["name"], "arith_mode": args.mode, "sectors_this_rank": run.n_sectors,
+                   "pixel_evaluations_per_step": m["work"] / steps,
+                   "evaluations_per_level": last["evaluations"][: w["pyramid"][2] + 1],
+                   "points_per_level": last["points_per_level"][: w["pyramid"][2] + 1],
+                   "l2": "flushed between steps (512 MiB write); evaluations inside a step re-read the domain by design",
+                   "domain_build_s": run.domain_build_s, "parallelism": par},
+        "clocks": m["clocks"],
+        "e2e": {"value": m["e2e_work"] / m["e2e_wall"], "unit": "pixel*evaluations/s",
+                "h2d_bytes_per_step": run.h2d_bytes, "d2h_bytes_per_step": 176 * run.n_sectors,
+                "ms_per_step": 1e3 * m["e2e_wall"] / steps,
+                "pipeline": "dic_stage_next_pair(k + 1) on the copy / image streams overlaps dic_correlate(k); H2D of both images every step"
+                            + ("" if run.band is None else f" (this rank's row band {run.band[0]}..{run.band[1]} of {w['rows']}; bytes are per rank)")},
+        "gpu_launches": m["launches"],
+        "other_arith_mode": {"arith_mode": "fast" if args.mode == "parity" else "parity",
+                             "kernel_value_this_rank": m["other_mode_value"],
+                             "unit": "pixel*evaluations/s (kernel time, one rank)"},
+        "roofline": roofline_block(args, w, m, peaks),
+    }
+
+
+def single_domain_parity(run, last, threads):
+    """c1 / c2: the whole domain against the fp64-accumulator oracle (and the fp32 CPU engine's own spread)."""
+    import oracle
+    w, d, n_par = run.w, run.w["domain"], run.n_par
+    und, dfm = run.und_pin.numpy(), run.dfm_pin.numpy()
+    od = oracle.OracleEngine(model=oracle.FM_QUAD if w["model"] == "quad" else oracle.FM_AFFINE, n_threads=threads,
+                             pyramid=w["pyramid"], accum_double=True, real_threads=True)
+    od.set_image("und", und)
+    od.set_image("def", dfm)
+    if d[0] == "rect":
+        dres = od.correlate(np.zeros(n_par, np.float32), oracle.rect_points(*d[1:]), center=((d[1] + d[3]) / 2.0, (d[2] + d[4]) / 2.0))
+    else:
+        dres = od.correlate(np.zeros(n_par, np.float32), oracle.annulus_points(*d[1:]))
+    blk = parity_block(last["params"], last["chi"], last["iterations"], dres["params"], dres["chi"], dres["iterations"])
+    blk["evaluations"] = [last["evaluations"][: w["pyramid"][2] + 1], dres["evaluations"][: w["pyramid"][2] + 1]]
+    return {"vs_oracle": blk}
+
+
+def other_workload_c2(args, peaks):
+    """Short run of config 2 on rank 0's GPU (N = 1 only)."""
+    sub = argparse.Namespace(**vars(args))
+    w = workload("c2")
+    run = Run(sub, w, None, 0, 1, 0)
+    steps = max(3, min(args.steps, 8))
+    m = run.measure(steps, 3, with_other_mode=True)
+    rec = record_for(sub, run, m, steps, peaks)
+    try:
+        rec["parity"] = single_domain_parity(run, m["last"], os.cpu_count() or 1)
+    except Exception as ex:
+        rec["parity"] = {"error": repr(ex)}
+    run.close()
+    return rec
+
+
+def other_workload_c5(args, dist, rank, world, local_rank, peaks):
+    """Short run of config 5 row-split over all ranks; rank 0 also solves the whole domain alone and a sample
+    region against the oracle. Collective."""
+    import torch
+    sub = argparse.Namespace(**vars(args))
+    w = workload("c5")
+    run, err = None, None
+    try:
+        run = Run(sub, w, dist, rank, world, local_rank)
+    except Exception as ex:  # one rank failing its set-up must not leave the others waiting in a collective
+        err = repr(ex)
+    ok = torch.tensor([0 if err else 1], device=torch.device("cuda", local_rank))
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        if run is not None:
+            run.close()
+        return {"error": err or "set-up failed on another rank"}
+    steps = max(3, min(args.steps, 5))
+    m = run.measure(steps, 3, with_other_mode=False)
+    split = m["last"]
+    rec = None
+    if rank == 0:
+        rec = record_for(sub, run, m, steps, peaks)
+    # parity_vs_single_gpu: the same domain on rank 0 alone (plain grid launch, no exchange)
+    run.barrier()
+    if rank == 0:
+        import oracle
+        d = w["domain"]
+        e1 = run.engine.CudaEngine(local_rank, fitting_model=run.engine.FM_UVUxUyVxVy, arith_mode=run.mode)
+        e1.resetImagePyramidsDevice(run.und_t.data_ptr(), run.dfm_t.data_ptr(), None, w["rows"], w["cols"], w["cols"], pyramid=w["pyramid"])
+        e1.resetPolygon(0, d[1], d[2], d[3], d[4])
+        one = e1.correlate(0, np.zeros(6, np.float32))
+        blk = parity_block(split["params"], split["chi"], split["iterations"], one["params"], one["chi"], one["iterations"])
+        blk["evaluations"] = [split["evaluations"][:5], one["evaluations"][:5]]
+        blk["bitwise_equal"] = bool(np.array_equal(split["params"], one["params"]) and split["chi"] == one["chi"])
+        rec["parity"] = {"vs_single_gpu": blk}
+        # sample region against the oracle (64-bit restatement; the reference's own cache index overflows at this size)
+        try:
+            cx, cy = (d[1] + d[3]) // 2, (d[2] + d[4]) // 2
+            hw = (d[3] - d[1]) // 16
+            box = (cx - hw, cy - hw, cx + hw, cy + hw)
+            e1.resetPolygon(1, *box)
+            g = e1.correlate(1, np.zeros(6, np.float32))
+            o = oracle.OracleEngine(model=oracle.FM_AFFINE, n_threads=os.cpu_count() or 1, pyramid=w["pyramid"], accum_double=True, real_threads=True)
+            o.set_image("und", run.und_pin.numpy())
+            o.set_image("def", run.dfm_pin.numpy())
+            want = o.correlate(np.zeros(6, np.float32), oracle.rect_points(*box), center=(float(cx), float(cy)))
+            sblk = parity_block(g["params"], g["chi"], g["iterations"], want["params"], want["chi"], want["iterations"])
+            sblk["region"] = f"central {2 * hw + 1}^2 px of the 16384^2 pair, 5 levels, one GPU vs the oracle with fp64 accumulators"
+            sblk["evaluations"] = [g["evaluations"][:5], want["evaluations"][:5]]
+            rec["parity"]["sample_region_vs_oracle"] = sblk
+        except Exception as ex:
+            rec["parity"]["sample_region_vs_oracle"] = {"error": repr(ex)}
+        e1.close()
+    run.barrier()
+    run.close()
+    return rec
 
 
 # ------------------------------------------------------------------------------ main
@@ -302,7 +731,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c4")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="parity", choices=["parity", "fast"],
                     help="arithmetic form of the per-pixel evaluation (include/dic_b200.h dic_arith_mode). 'parity' (default, "
@@ -311,6 +740,8 @@ def main():
                          "instructions, more accurate than the reference's own rounding noise, which is why its chi can sit "
                          "1e-5 away from the reference's); it is reported beside the headline, labelled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-records (c2 at N = 1, c5 at N > 1)")
+    ap.add_argument("--parity-sample", type=int, default=64, help="subsets compared with the oracle in the bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -318,11 +749,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = workload(args.workload)
-    n_par = 12 if w["model"] == "quad" else 6
     if args.workload == "c3" and args.impl == "ours":
         if rank != 0:
             return 0
-        return run_c3(args, w)
+        print(json.dumps(run_c3(args, w, with_cpu=not args.no_cpu_baseline)), flush=True)
+        return 0
 
     import torch
     dist = None
@@ -337,12 +768,12 @@ def main():
 
     if args.impl == "reference":
         dev = torch.device("cuda", 0) if torch.cuda.is_available() else None
-        und_t, dfm_t = make_images(w, dev) if dev is not None else (None, None)
         if dev is None:
             from correlation_b200 import synth
             und = synth.make_image(w["rows"], w["cols"], w["seed"], None, w["center"])
             dfm = synth.make_image(w["rows"], w["cols"], w["seed"], w["truth"], w["center"])
         else:
+            und_t, dfm_t = make_images(w, dev)
             und, dfm = und_t.cpu().numpy(), dfm_t.cpu().numpy()
         threads = os.cpu_count() or 1
         vals = []
@@ -354,7 +785,8 @@ def main():
         v = tot_w / tot_s
         line = {"impl": "reference", "metric": "domain pixel*GN-evaluations/s", "value": v,
                 "unit": "pixel*evaluations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True,
+                "scaling": "strong" if w["domain"][0] in ("subsets", "rowsplit") else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic analytic speckle (SURVEY 8d)",
                 "config": {"workload": w["name"]},
                 "cpu_baseline": {"value": v, "unit": "pixel*evaluations/s", "cores": threads, "kind": kind,
@@ -364,263 +796,92 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- our arm
-    from correlation_b200 import engine
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    und_t, dfm_t = make_images(w, dev)
-    und_pin = torch.empty(und_t.shape, dtype=torch.uint8, pin_memory=True)
-    dfm_pin = torch.empty(dfm_t.shape, dtype=torch.uint8, pin_memory=True)
-    und_pin.copy_(und_t)
-    dfm_pin.copy_(dfm_t)
-    torch.cuda.synchronize()
-    mode = engine.MODE_PARITY if args.mode == "parity" else engine.MODE_FAST
-    eng = engine.CudaEngine(local_rank, fitting_model=engine.FM_QUADRATIC if w["model"] == "quad" else engine.FM_UVUxUyVxVy,
-                            arith_mode=mode)
-    rows, cols = w["rows"], w["cols"]
-    eng.resetImagePyramidsDevice(und_t.data_ptr(), dfm_t.data_ptr(), None, rows, cols, cols, pyramid=w["pyramid"])
-    d = w["domain"]
-    scaling = "weak"
-    t_dom = time.perf_counter()
-    if d[0] == "rect":
-        eng.resetPolygon(0, *d[1:])
-        n_sectors = 1
-    elif d[0] == "annulus":
-        eng.resetPolygon(0, *d[1:])
-        n_sectors = 1
-    elif d[0] == "rowsplit":
-        # one domain, pixel rows in equal bands per rank, per-evaluation sum inside the kernel
-        from correlation_b200 import rowsplit
-        rowsplit.connect(eng, dist)
-        b0, b1 = rowsplit.equal_row_bands(d[2], d[4], world)[rank]
-        eng.resetPolygonRectBand(0, d[1], d[2], d[3], d[4], b0, b1)
-        n_sectors = 1
-        scaling = "strong"
-    else:
-        # independent subsets shard across ranks in contiguous blocks, images replicated
-        from correlation_b200 import sharding
-        boxes = subset_boxes(d[1], d[2], d[3])
-        # whole rows of subsets per rank: each rank then needs only a band of image rows (e2e upload)
-        boxes = [boxes[i] for i in sharding.shard_grid_rows(d[3], d[3], world, rank)]
-        for k, bx in enumerate(boxes):
-            eng.resetPolygon(k, *bx)
-        n_sectors = len(boxes)
-        scaling = "strong"
-    eng.synchronize()
-    t_dom = time.perf_counter() - t_dom
-    zero = np.zeros((n_sectors, n_par), np.float32)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-
-    res_buf = np.zeros(n_sectors, engine.RESULT_DTYPE)
-    guess_buf = np.zeros((n_sectors, n_par), np.float32)
-
-    one_guess = np.zeros(n_par, np.float32)
-    one_result = engine.DicResult()
-
-    def step_resident():
-        if n_sectors == 1:
-            one_guess[:] = 0.0
-            eng.correlate_raw(0, one_guess, one_result)
-            work = 0.0
-            for lv in range(engine.MAX_LEVELS):
-                work += float(one_result.evaluationsPerLevel[lv]) * float(one_result.pointsPerLevel[lv])
-            return work, eng.last_correlate_ms(), one_result
-        guess_buf[:] = 0.0
-        eng.lib.dic_correlate_batch(eng.h, 0, n_sectors, guess_buf.ctypes.data, res_buf.ctypes.data)
-        return None, eng.last_correlate_ms(), res_buf  # work is read from the records after the loop
-
-    # a rank that owns a band of the image (sharded subsets, row-split domain) transfers only its rows plus
-    # a halo for displacement, bicubic support and pyramid support (dic_stage_next_pair_rows)
-    band = None
-    if world > 1 and d[0] == "rowsplit":
-        band = upload_band(b0, b1, rows, w["pyramid"][2])
-    elif world > 1 and d[0] == "subsets":
-        band = upload_band(min(bx[1] for bx in boxes), max(bx[3] for bx in boxes), rows, w["pyramid"][2])
-    h2d_bytes = 2 * cols * ((band[1] - band[0]) if band else rows)
-
-    def stage_pair():
-        # this step's inputs: both images from pinned host memory, upload + pyramids on the image stream
-        eng.stageNextPair(und_pin.data_ptr(), dfm_pin.data_ptr(), rows, cols, row_range=band)
-
-    def e2e_loop(n):
-        # double-buffered ingest (dic_stage_next_pair / dic_advance_pair): the PCIe transfer of pair k + 1
-        # overlaps the solve of pair k; every step copies its own pair and reads its own result record
-        tot = 0.0
-        stage_pair()
-        for k in range(n):
-            eng.advancePair()
-            if k + 1 < n:
-                stage_pair()
-            wk, _, _ = step_resident()
-            tot += batch_work if wk is None else wk
-        return tot
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_resident()
-    launches0 = eng.kernel_launches()
-    barrier()
-    # Timed on the DEVICE: CUDA events on the correlation stream around the whole GPU side of each step (guess
-    # upload, solve, result download), summed over the K steps, max over ranks. The L2 flush between steps is
-    # outside the events. The host clock around the same calls is reported beside it (host_ms_per_step): it
-    # adds launch latency and the wake-up after the sync, and on a busy 8-rank box it jitters by 0.1 ms.
-    work = kern_ms = wall = host_wall = 0.0
-    with ClockSampler(local_rank, world) as clk:
-        for _ in range(args.steps):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            wk, ms, last = step_resident()
-            host_wall += time.perf_counter() - t0
-            wall += 1e-3 * eng.last_step_ms()
-            if wk is None:  # batch: identical inputs every step, count the work once per step from the records
-                wk = eng.pixel_evaluations(last)
-            work += wk
-            kern_ms += ms
-    barrier()
-    launches = eng.kernel_launches() - launches0
-    if n_sectors == 1:
-        last = last.as_dict(n_par)
-    else:
-        rs = last
-        last = dict(params=rs[0]["resultingParameters"][:n_par].copy(), chi=rs[0]["chi"],
-                    iterations=int(rs[0]["iterations"]), evaluations=rs[0]["evaluationsPerLevel"].tolist(),
-                    points_per_level=rs[0]["pointsPerLevel"].tolist(), errors=int((rs["errorCode"] != 0).sum()))
-    batch_work = eng.pixel_evaluations(res_buf) if n_sectors > 1 else None
-    # e2e: host buffers, copies inside the timed region
-    e2e_loop(2)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_work = e2e_loop(args.steps)
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-
-    # the other arithmetic mode, same resident inputs, for the record
-    other = engine.MODE_PARITY if mode == engine.MODE_FAST else engine.MODE_FAST
-    eng.set_arith_mode(other)
-    for _ in range(2):
-        step_resident()
-    o_work = o_ms = 0.0
-    for _ in range(max(2, args.steps // 2)):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        wk, ms, _o = step_resident()
-        o_work += eng.pixel_evaluations(_o) if wk is None else wk
-        o_ms += ms
-    eng.set_arith_mode(mode)
-
-    stats = torch.tensor([wall, e2e_wall, work, e2e_work, kern_ms, host_wall], dtype=torch.float64, device=dev)
-    if dist is not None:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        wall, e2e_wall, host_wall = mx[0].item(), mx[1].item(), mx[5].item()
-        work, e2e_work = sm[2].item(), sm[3].item()
-        if d[0] == "rowsplit":  # every rank's result record already counts the whole domain
-            work, e2e_work = mx[2].item(), mx[3].item()
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    try:  # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gn_solve_tiles_kernel"].get(f"{args.workload} {args.mode}")
-        if tr:
-            traffic = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
-    except Exception:
-        pass
-    my_work = stats[2].item()
-    achieved = ALGO_BYTES_PER_PIXEL_EVAL * my_work / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    value = work / wall
-    line = {
-        "metric": "domain pixel*GN-evaluations/s", "value": value, "unit": "pixel*evaluations/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-        "host_ms_per_step": 1e3 * host_wall / args.steps,
-        "timing": "CUDA events on the correlation stream around each step's device work, summed over the steps, max over ranks",
-        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic analytic speckle (SURVEY 8d), random phases seeded",
-        "config": {"workload": w["name"], "arith_mode": args.mode, "sectors": n_sectors,
-                   "pixel_evaluations_per_step": my_work / args.steps,
-                   "evaluations_per_level": last["evaluations"][: w["pyramid"][2] + 1],
-                   "points_per_level": last["points_per_level"][: w["pyramid"][2] + 1],
-                   "l2": "flushed between steps (512 MiB write); evaluations inside a step re-read the domain by design",
-                   "domain_build_s": t_dom,
-                   "parallelism": (f"one domain in {world} row band(s), per-evaluation all-reduce of the normal equations inside the kernel (NVLink peer mailboxes)"
-                                   if d[0] == "rowsplit" else
-                                   f"{d[3] * d[3]} subsets, whole rows of subsets per GPU, over {world} GPU(s), no collective"
-                                   if scaling == "strong" else f"{world} independent domain(s), one per GPU")},
-        "clocks": clk.summary(),
-        "e2e": {"value": e2e_work / e2e_wall, "unit": "pixel*evaluations/s",
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 176 * n_sectors,
-                "ms_per_step": 1e3 * e2e_wall / args.steps,
-                "pipeline": "dic_stage_next_pair(k + 1) on the copy / image streams overlaps dic_correlate(k); H2D of both images every step"
-                            + ("" if band is None else f" (this rank's row band {band[0]}..{band[1]} of {rows}; bytes are per rank)")},
-        "gpu_launches": launches,
-        "other_arith_mode": {"arith_mode": "parity" if other == engine.MODE_PARITY else "fast",
-                             "kernel_value_this_rank": o_work / (o_ms * 1e-3) if o_ms > 0 else None,
-                             "unit": "pixel*evaluations/s (kernel time, one rank)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
-                     "traffic_note": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json); "
-                                     "algorithmic bytes per launch = 10 B x pixel_evaluations_per_step",
-                     "kernel": "gn_solve_tiles_kernel" if n_sectors >= 1 else "gn_solve_kernel",
-                     "kernel_ms_per_step": kern_ms / args.steps,
-                     "fp32_note": "the kernel is FP32-issue bound, not HBM bound (DESIGN.md 4.1): parity mode replays the reference's "
-                                  "~270 unfused fp32 operations per pixel (369 issued instructions per pixel*evaluation over the whole "
-                                  "launch, FMA pipe 47 % of peak, issue slots 62 % incl. the per-evaluation grid all-reduce); the level "
-                                  "data stays L2-resident across evaluations (31 MB of DRAM reads for 369 MB of algorithmic traffic). "
-                                  "profiles/r1_c2_gn_solve_tiles_parity_ncu_full.txt, profiles/r1_l0_pass_ncu_full.txt",
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                     "algorithmic_bytes_per_pixel_evaluation": ALGO_BYTES_PER_PIXEL_EVAL},
-    }
-    if not args.no_cpu_baseline and world == 1:
+    if w["domain"][0] == "rowsplit" and world == 1 and not args.no_others:
+        args.no_others = True
+    run = Run(args, w, dist, rank, world, local_rank)
+    m = run.measure(args.steps, args.warmup)
+    line = record_for(args, run, m, args.steps, peaks) if rank == 0 else None
+    d = w["domain"]
+
+    # ---- parity (top level of the line)
+    parity = {}
+    if d[0] == "subsets":
+        full = run.gather_records(m["resident_records"])  # collective
+        if rank == 0:
+            try:
+                parity["vs_oracle"] = run.parity_subsets(full, args.parity_sample)
+            except Exception as ex:
+                parity["vs_oracle"] = {"error": repr(ex)}
+            if world > 1:
+                # rank 0 alone, all 4096 subsets, the same CTA mapping the ranks used: every subset's arithmetic is then
+                # the same instruction sequence on the same data, so the records must agree bit for bit
+                try:
+                    eng = run.eng
+                    pair_used = eng.last_cluster_size() == 2
+                    n_all = len(run.all_boxes)
+                    base = run.n_sectors
+                    eng.resetPolygonRectGrid(base, np.array(run.all_boxes, np.int32))
+                    eng.set_cluster_mode(2 if pair_used else 1)
+                    g = np.zeros((n_all, run.n_par), np.float32)
+                    one = np.zeros(n_all, run.engine.RESULT_DTYPE)
+                    eng.lib.dic_correlate_batch(eng.h, base, n_all, g.ctypes.data, one.ctypes.data)
+                    eng.set_cluster_mode(0)
+                    same = (one.tobytes() == full.tobytes())
+                    neq = int(sum(one[k].tobytes() != full[k].tobytes() for k in range(n_all)))
+                    parity["vs_single_gpu"] = {
+                        "records_compared": n_all, "records_bitwise_equal": n_all - neq, "bitwise_equal": bool(same),
+                        "ctas_per_subset": 2 if pair_used else 1,
+                        "max_abs_dparams": float(np.abs(one["resultingParameters"] - full["resultingParameters"]).max()),
+                        "max_rel_dchi": float((np.abs(one["chi"] - full["chi"]) / np.maximum(np.abs(one["chi"]), 1e-30)).max()),
+                        "note": "all ranks' result records gathered in sector order vs rank 0's own single-GPU batch of all subsets"}
+                except Exception as ex:
+                    parity["vs_single_gpu"] = {"error": repr(ex)}
+    elif d[0] in ("rect", "annulus") and rank == 0 and not args.no_cpu_baseline:
         try:
-            und, dfm = und_pin.numpy(), dfm_pin.numpy()
+            parity = single_domain_parity(run, m["last"], os.cpu_count() or 1)
+        except Exception as ex:
+            parity = {"vs_oracle": {"error": repr(ex)}}
+    if rank == 0:
+        line["parity"] = parity
+
+    # ---- CPU baseline (N = 1, rank 0): the reference's own engine on a bounded sample of the same workload
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        try:
             threads = os.cpu_count() or 1
-            cw, cs, kind, cres, sample, t_pyr = cpu_run(w, und, dfm, threads)
+            cw, cs, kind, cres, sample, t_pyr = cpu_run(w, run.und_pin.numpy(), run.dfm_pin.numpy(), threads)
             line["cpu_baseline"] = {"value": cw / cs, "unit": "pixel*evaluations/s", "cores": threads, "kind": kind,
                                     "sample": sample, "seconds": cs, "pyramid_seconds": t_pyr}
-            gp, cp = last["params"], cres["params"]
-            if d[0] in ("rect", "annulus") and w["rows"] <= 4096:
-                # the gate of BASELINE.json: against the oracle with fp64 accumulators (the CPU engine's own fp32
-                # accumulation moves chi by ~2e-4 with its thread count)
-                import oracle
-                od = oracle.OracleEngine(model=oracle.FM_QUAD if w["model"] == "quad" else oracle.FM_AFFINE, n_threads=threads,
-                                         pyramid=w["pyramid"], accum_double=True, real_threads=True)
-                od.set_image("und", und)
-                od.set_image("def", dfm)
-                if d[0] == "rect":
-                    dres = od.correlate(np.zeros(n_par, np.float32), oracle.rect_points(*d[1:]), center=((d[1] + d[3]) / 2.0, (d[2] + d[4]) / 2.0))
-                else:
-                    dres = od.correlate(np.zeros(n_par, np.float32), oracle.annulus_points(*d[1:]))
-                dp = dres["params"]
-                line["config"]["parity_vs_oracle_fp64_accumulators"] = {
-                    "max_abs_duv": float(np.abs(gp[:2] - dp[:2]).max()), "max_abs_dgrad": float(np.abs(gp[2:6] - dp[2:6]).max()),
-                    "rel_dchi": float(abs(last["chi"] - dres["chi"]) / max(abs(dres["chi"]), 1e-30)),
-                    "iterations": [int(last["iterations"]), int(dres["iterations"])],
-                    "tolerances": {"duv": 1e-4, "dgrad": 1e-6, "rel_dchi": 1e-5, "iterations": 1}}
-            if d[0] in ("rect", "annulus"):  # same domain on both sides
-              line["config"]["parity_vs_cpu"] = {
-                "max_abs_duv": float(np.abs(gp[:2] - cp[:2]).max()), "max_abs_dgrad": float(np.abs(gp[2:6] - cp[2:6]).max()),
-                "rel_dchi": float(abs(last["chi"] - cres["chi"]) / max(abs(cres["chi"]), 1e-30)),
-                "iterations": [int(last["iterations"]), int(cres["iterations"])],
-                "note": "CPU side accumulates in fp32 per thread (its chi moves ~2e-4 with the thread count, SURVEY H1)"}
         except Exception as ex:  # the baseline is reported, never allowed to sink the bench line
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    run.barrier()
+    run.close()
+
+    # ---- other workloads, short, for continuity with round 1 (each failure is recorded, never fatal)
+    if not args.no_others and d[0] == "subsets":
+        others = {}
+        if world == 1:
+            try:
+                others["c2"] = other_workload_c2(args, peaks)
+            except Exception as ex:
+                others["c2"] = {"error": repr(ex)}
+        else:
+            try:
+                rec = other_workload_c5(args, dist, rank, world, local_rank, peaks)
+                if rank == 0:
+                    others["c5"] = rec
+            except Exception as ex:
+                others["c5"] = {"error": repr(ex)}
+        if rank == 0:
+            line["other_workloads"] = others
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

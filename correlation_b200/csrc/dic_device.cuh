@@ -493,10 +493,15 @@ __device__ __forceinline__ void block_reduce(float *acc, float *red, float *out)
 // matrix row per lane, columns exchanged by warp shuffles (replaces the reference's cuSOLVER
 // potrf/potrs, cuda_solver.cu:119-149, and the CPU's Eigen QR). tot: packed upper A, then b
 // (shared memory). smem: NP*NP floats of scratch for the transposed back-substitution.
-// A direction whose diagonal or pivot is not positive (textureless / saturated subset: A has an exactly zero
-// row) gets a ZERO step and is decoupled from the others -- what the rank-truncating column-pivoted QR of the CPU
-// engine returns (correlation_class.cpp:742-747): the LM loop then ends with error_none and unchanged parameters
-// in that direction instead of a solver error. Always returns true (kept bool for the call sites).
+// Rank deficiency follows the CPU engine's column-pivoted QR (Eigen 3.4.0 ColPivHouseholderQR behind
+// correlation_class.cpp:742-747, restated in oracle/qr_colpiv.h):
+//   * a direction whose diagonal or pivot is not positive while others are (one zero row of A: no gradient along
+//     that parameter) is rank-truncated there -- it gets a ZERO step and the others are solved;
+//   * an identically zero matrix (textureless / saturated subset) is NOT truncated by Eigen (its threshold is
+//     relative to the largest column norm, 0 < 0 is false), the triangular solve divides 0 by 0 and the step is
+//     NaN: the next evaluation is out of the image and the pyramid ends with error 2 and NaN parameters. The same
+//     happens here (dp = NaN), so that the report matches the reference's even on such subsets.
+// Always returns true (kept bool for the call sites).
 template <int NP>
 __device__ bool warp_solve(const float *tot, float scaling, float lambda, float *smem, float *dp) {
   const int lane = threadIdx.x & 31;
@@ -513,6 +518,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
   float dii = 0.f;
 #pragma unroll
   for (int j = 0; j < NP; ++j) dii = (j == i) ? a[j] : dii;
+  const bool all_zero = __all_sync(full, lane >= NP || !(dii > 0.f));
   const float sc = dii > 0.f ? 1.0f / sqrtf(dii) : 0.f; // zero row and column: the direction drops out
 #pragma unroll
   for (int j = 0; j < NP; ++j) a[j] *= sc * __shfl_sync(full, sc, j);
@@ -554,7 +560,7 @@ __device__ bool warp_solve(const float *tot, float scaling, float lambda, float 
     const float lki = smem[k * NP + i]; // L[k][i], used by lanes i < k
     x = (i == k) ? xk : ((i < k) ? fmaf(-lki, xk, x) : x);
   }
-  if (lane < NP) dp[lane] = x * sc;
+  if (lane < NP) dp[lane] = all_zero ? __int_as_float(0x7fc00000) : x * sc;
   __syncwarp();
   return true;
 }

@@ -108,9 +108,11 @@ struct dic_engine {
   float *h_guess = nullptr;        // pinned + mapped: batch kernels read their guesses from here (zero-copy)
   float *h_guess_dev = nullptr;    // device-side address of h_guess
   int cluster_mode = 0;            // batch launches: 0 auto, 1 one CTA per sector, 2 one CTA pair per sector
-  std::vector<void *> bulk_blocks; // device blocks shared by the sectors of a dic_reset_polygon_rect_grid call
-  void *grid_lists = nullptr, *grid_tiles = nullptr, *grid_desc = nullptr;
-  size_t cap_grid_lists = 0, cap_grid_tiles = 0, cap_grid_desc = 0;
+  // device blocks shared by the sectors of one dic_reset_polygon_rect_grid call, keyed by its first sector id:
+  // rebuilding the same range reuses (or regrows) its blocks, another range gets its own
+  struct GridBlock { int first_id = 0; void *lists = nullptr, *tiles = nullptr, *desc = nullptr; size_t cap_lists = 0, cap_tiles = 0, cap_desc = 0; };
+  std::vector<GridBlock> grid_blocks;
+  int last_cluster = 1;            // CTAs per sector of the last batch launch (1 or 2)
   int cap_sectors = 0;
   GridWork *d_work = nullptr;
   float *d_partials = nullptr;
@@ -708,6 +710,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     // the last wave runs faster): 512 subsets on 148 SMs = 3.46 -> 4 rounds (86 %), 1024 halves = 6.92 -> 7 (99 %).
     bool pair = e->cluster_mode == 2 ||
                 (e->cluster_mode == 0 && 0.97 * wave_efficiency(2L * count, e->num_sms) > wave_efficiency(count, e->num_sms) + 0.02);
+    e->last_cluster = pair ? 2 : 1;
     if (pair) {
       cudaLaunchConfig_t lc;
       memset(&lc, 0, sizeof(lc));
@@ -847,8 +850,7 @@ void dic_destroy(dic_engine *e) {
     if (s.ebuf) cudaFree(s.ebuf);
   }
   for (char *c : e->arena_chunks) cudaFree(c);
-  for (void *b : e->bulk_blocks) cudaFree(b);
-  cudaFree(e->grid_lists); cudaFree(e->grid_tiles); cudaFree(e->grid_desc);
+  for (auto &g : e->grid_blocks) { cudaFree(g.lists); cudaFree(g.tiles); cudaFree(g.desc); }
   if (e->h_sectors) cudaFreeHost(e->h_sectors);
   if (e->h_sector_tiles) cudaFreeHost(e->h_sector_tiles);
   cudaFree(e->d_sector_tiles); cudaFree(e->d_masks); cudaFree(e->d_mailbox);
@@ -1286,13 +1288,17 @@ int dic_reset_polygon_rect_grid(dic_engine *e, int first_id, int n, const int *b
     total_px = std::max(total_px, slice_begin + n0 + n0 / 2 + 16);
     s.cap = total_px - slice_begin;
   }
-  if ((rc = ensure_block(e, &e->grid_lists, &e->cap_grid_lists, sizeof(float2) * std::max<size_t>(total_px, 1)))) return rc;
-  if ((rc = ensure_block(e, &e->grid_tiles, &e->cap_grid_tiles, sizeof(Tile) * std::max<size_t>(total_tiles, 1)))) return rc;
-  if ((rc = ensure_block(e, &e->grid_desc, &e->cap_grid_desc, sizeof(RectDesc) * desc.size()))) return rc;
-  float2 *lists = static_cast<float2 *>(e->grid_lists);
-  Tile *tiles = static_cast<Tile *>(e->grid_tiles);
-  CU_TRY(e, cudaMemcpyAsync(e->grid_desc, desc.data(), sizeof(RectDesc) * desc.size(), cudaMemcpyHostToDevice, e->stream));
-  const RectDesc *d_desc = static_cast<const RectDesc *>(e->grid_desc);
+  dic_engine::GridBlock *gb = nullptr;
+  for (auto &g : e->grid_blocks)
+    if (g.first_id == first_id) gb = &g;
+  if (!gb) { e->grid_blocks.emplace_back(); gb = &e->grid_blocks.back(); gb->first_id = first_id; }
+  if ((rc = ensure_block(e, &gb->lists, &gb->cap_lists, sizeof(float2) * std::max<size_t>(total_px, 1)))) return rc;
+  if ((rc = ensure_block(e, &gb->tiles, &gb->cap_tiles, sizeof(Tile) * std::max<size_t>(total_tiles, 1)))) return rc;
+  if ((rc = ensure_block(e, &gb->desc, &gb->cap_desc, sizeof(RectDesc) * desc.size()))) return rc;
+  float2 *lists = static_cast<float2 *>(gb->lists);
+  Tile *tiles = static_cast<Tile *>(gb->tiles);
+  CU_TRY(e, cudaMemcpyAsync(gb->desc, desc.data(), sizeof(RectDesc) * desc.size(), cudaMemcpyHostToDevice, e->stream));
+  const RectDesc *d_desc = static_cast<const RectDesc *>(gb->desc);
   {
     dim3 g1((unsigned)((max_n + 255) / 256), (unsigned)std::min<size_t>(desc.size(), 65535));
     rect_grid_fill_kernel<<<g1, 256, 0, e->stream>>>(d_desc, (int)desc.size(), lists);
@@ -1340,6 +1346,7 @@ int dic_reset_polygon_rect_grid(dic_engine *e, int first_id, int n, const int *b
   return worst;
 }
 
+int dic_last_cluster_size(const dic_engine *e) { return e ? e->last_cluster : 0; }
 int dic_set_cluster_mode(dic_engine *e, int mode) {
   if (!e || mode < 0 || mode > 2) return DIC_ERROR_BAD_ARGUMENT;
   e->cluster_mode = mode;

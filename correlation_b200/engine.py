@@ -67,7 +67,7 @@ EXPORTS = [
     "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_device",
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
-    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_rect_grid", "dic_set_cluster_mode", "dic_reset_polygon_points", "dic_set_polygon_center",
+    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_rect_grid", "dic_set_cluster_mode", "dic_last_cluster_size", "dic_reset_polygon_points", "dic_set_polygon_center",
     "dic_stage_next_pair", "dic_stage_next_pair_rows", "dic_advance_pair",
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
@@ -117,6 +117,7 @@ def load_library():
         "dic_reset_polygon_rect_band": (I, [P, I, I, I, I, I, I, I]),
         "dic_reset_polygon_rect_grid": (I, [P, I, I, P]),
         "dic_set_cluster_mode": (I, [P, I]),
+        "dic_last_cluster_size": (I, [P]),
         "dic_rowsplit_mailbox_handle": (I, [P, P, I]),
         "dic_rowsplit_connect": (I, [P, I, I, P, I]),
         "dic_rowsplit_disconnect": (I, [P]),
@@ -285,6 +286,9 @@ class CudaEngine:
 
     def set_cluster_mode(self, mode):
         self._ck(self.lib.dic_set_cluster_mode(self.h, int(mode)))
+
+    def last_cluster_size(self):
+        return int(self.lib.dic_last_cluster_size(self.h))
 
     def rowsplit_handle(self):
         buf = np.zeros(64, np.uint8)

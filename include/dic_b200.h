@@ -189,6 +189,8 @@ int dic_correlate_batch(dic_engine *e, int first_sector, int n_sectors, float *g
  * shared memory) when that fills the GPU's last wave better; 1 = always one CTA; 2 = always a pair.
  * Results are identical to ~1 ulp of the sums (the two halves are added in a fixed order). */
 int dic_set_cluster_mode(dic_engine *e, int mode);
+/* CTAs per sector the last dic_correlate_batch launch used (1 or 2) */
+int dic_last_cluster_size(const dic_engine *e);
 /* extension: enqueue only (no host sync); dic_correlate_wait collects. Lets a caller overlap
  * the next upload with the solve, and lets bench.py time the device alone. */
 int dic_correlate_async(dic_engine *e, int iSector, const float *guess);
