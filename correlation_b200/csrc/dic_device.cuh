@@ -83,6 +83,7 @@ struct GridWork {
   int n_marks;
   unsigned long long marks[kMaxMarks][4];
   unsigned long long cta_done[kMaxCtaMarks]; // per CTA: when its pass of the LAST evaluation ended (load-balance probe)
+  unsigned int cta_smid[kMaxCtaMarks];       // per CTA: the SM it runs on (same probe)
 };
 
 struct SolveSettings {
@@ -191,10 +192,11 @@ __device__ __forceinline__ void monomial_from_samples(float p0, float p1, float 
 // The 40 terms of interpolation_class.cpp:108-126 in the reference's order, unfused mul / add.
 // Exact shortcuts only: x * 1 is skipped, (2 a) * y == 2 (a * y) and acc + 2 t == fma(2, t, acc)
 // bit for bit (power-of-two scaling commutes with rounding), 3 a is exact (|a| < 2^20, quarter units).
-__device__ __forceinline__ void parity_eval(const float a[4][4], float xdef, float ydef, int ix, int iy,
-                                            float &w, float &wx, float &wy) {
-  const float dx = __fadd_rn(__fsub_rn(xdef, (float)ix), 1.f);
-  const float dy = __fadd_rn(__fsub_rn(ydef, (float)iy), 1.f);
+// fix, fiy = (float)ix, (float)iy (the caller may have them already: floor_magic returns exactly that value).
+__device__ __forceinline__ void parity_eval_f(const float a[4][4], float xdef, float ydef, float fix, float fiy,
+                                              float &w, float &wx, float &wy) {
+  const float dx = __fadd_rn(__fsub_rn(xdef, fix), 1.f);
+  const float dy = __fadd_rn(__fsub_rn(ydef, fiy), 1.f);
   float px[4], py[4];
   px[0] = 1.f; px[1] = dx; px[2] = __fmul_rn(dx, dx); px[3] = __fmul_rn(px[2], dx);
   py[0] = 1.f; py[1] = dy; py[2] = __fmul_rn(dy, dy); py[3] = __fmul_rn(py[2], dy);
@@ -228,6 +230,10 @@ __device__ __forceinline__ void parity_eval(const float a[4][4], float xdef, flo
   }
   w = rw; wx = rx; wy = ry;
 }
+__device__ __forceinline__ void parity_eval(const float a[4][4], float xdef, float ydef, int ix, int iy,
+                                            float &w, float &wx, float &wy) {
+  parity_eval_f(a, xdef, ydef, (float)ix, (float)iy, w, wx, wy);
+}
 
 // y pass of the separable coefficient stage: rows r0..r3 hold the x-direction monomial
 // coefficients (in s = 1 + t) of image rows iy-1 .. iy+2.
@@ -243,6 +249,19 @@ __device__ __forceinline__ void bicubic_parity_rows(const float *r0, const float
     for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
   }
   parity_eval(a, xdef, ydef, ix, iy, w, wx, wy);
+}
+__device__ __forceinline__ void bicubic_parity_rows_f(const float *r0, const float *r1, const float *r2,
+                                                      const float *r3, float xdef, float ydef, float fix, float fiy,
+                                                      float &w, float &wx, float &wy) {
+  float a[4][4];
+#pragma unroll
+  for (int ik = 0; ik < 4; ++ik) {
+    float c[4];
+    monomial_from_samples(r0[ik], r1[ik], r2[ik], r3[ik], c);
+#pragma unroll
+    for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
+  }
+  parity_eval_f(a, xdef, ydef, fix, fiy, w, wx, wy);
 }
 
 __device__ __forceinline__ void bicubic_parity(const float p[4][4], float xdef, float ydef, int ix,

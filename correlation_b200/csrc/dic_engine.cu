@@ -675,7 +675,8 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   memset(&maps, 0, sizeof(maps));
   for (int l = 0; l <= e->stop; ++l) { maps.def[l] = d.tm_patch[l]; maps.und[l] = u.tm_tile[l]; }
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
-  const size_t smem = tiles_dyn_smem(NACC);
+  const size_t smem = tiles_dyn_smem(NACC, grid_mode);
+  constexpr int NTB = tile_cta_threads(false); // threads per CTA of the batch form
   if (grid_mode) {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, true, 1>;
     static int per_sm_cached[16] = {0}; // per device: attribute + occupancy queried once, not per launch
@@ -700,7 +701,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     if (per_sm == 0) {
       CU_TRY(e, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU_TRY(e, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern1, kThreads, smem));
+      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern1, NTB, smem));
     }
     const long slots = (long)std::max(1, per_sm) * e->num_sms;
     // one CTA pair per sector halves the scheduling granule: worth it when the last wave of whole-sector CTAs
@@ -715,7 +716,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
       cudaLaunchConfig_t lc;
       memset(&lc, 0, sizeof(lc));
       lc.gridDim = dim3((unsigned)std::max(2L, std::min(2L * count, slots / 2 * 2)));
-      lc.blockDim = dim3(kThreads);
+      lc.blockDim = dim3(NTB);
       lc.dynamicSmemBytes = smem;
       lc.stream = e->stream;
       cudaLaunchAttribute at[1];
@@ -725,7 +726,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
       CU_TRY(e, cudaLaunchKernelEx(&lc, kern2, cfg, maps, sectors, stiles, guesses, g0, results, first, count, work));
     } else {
       int grid = (int)std::max(1L, std::min((long)count, slots));
-      kern1<<<grid, kThreads, smem, e->stream>>>(cfg, maps, sectors, stiles, guesses, g0, results, first, count, work);
+      kern1<<<grid, NTB, smem, e->stream>>>(cfg, maps, sectors, stiles, guesses, g0, results, first, count, work);
     }
     CU_TRY(e, cudaGetLastError());
   }
@@ -1879,6 +1880,14 @@ int dic_get_cta_times(dic_engine *e, unsigned long long *out, int cap) {
   cudaSetDevice(e->device);
   int n = std::min(cap, kMaxCtaMarks);
   if (cudaMemcpy(out, (const char *)e->d_work + offsetof(GridWork, cta_done), sizeof(unsigned long long) * n,
+                 cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return n;
+}
+int dic_get_cta_smids(dic_engine *e, unsigned int *out, int cap) {
+  if (!e || !out) return 0;
+  cudaSetDevice(e->device);
+  int n = std::min(cap, kMaxCtaMarks);
+  if (cudaMemcpy(out, (const char *)e->d_work + offsetof(GridWork, cta_smid), sizeof(unsigned int) * n,
                  cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return n;
 }

@@ -486,6 +486,11 @@ __device__ __forceinline__ void begin_sector(SolveShared<model_nparams(MODEL)> &
     if (work->img_error) sh.timed_out = 1; // a pyramid transfer failed earlier: finish at once with error_cuda
   }
   if (GRID && blockIdx.x == 0 && tid == 0) { work->n_marks = 0; work->slow_units = 0; work->marks[0][0] = global_ns(); }
+  if (GRID && tid == 0 && blockIdx.x < kMaxCtaMarks) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    work->cta_smid[blockIdx.x] = smid;
+  }
   if (tid < NP) sh.p[tid] = translate_param<MODEL>(sh.solve[tid], tid, 0, cfg.stop);
   if (tid == 0) { sh.level = cfg.stop; sh.done = 0; }
   __syncthreads();

@@ -26,7 +26,7 @@ namespace dic {
 #ifndef DIC_TILE_CTAS_AFFINE
 #define DIC_TILE_CTAS_AFFINE 2
 #endif
-constexpr int tile_ctas_per_sm(int model) { return model == DIC_FM_QUADRATIC ? 2 : DIC_TILE_CTAS_AFFINE; }
+__host__ __device__ constexpr int tile_ctas_per_sm(int model) { return model == DIC_FM_QUADRATIC ? 2 : DIC_TILE_CTAS_AFFINE; }
 constexpr int kTileW = 32, kTileH = 16;
 // Per-warp staging, filled by TMA (cp.async.bulk.tensor.2d) one unit ahead of the arithmetic:
 //   the deformed-image footprint of a unit as u8, kPatchW x kPatchH bytes,
@@ -314,6 +314,70 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
   accumulate_moments<NP>(mom, V, wx, wy, Y);
 }
 
+// ---- parity mode, second form of the inner loop (DIC_PARITY_LOOP == 2, the default).
+// The window state of a lane: cw = x-direction cubic coefficients of the four window rows in ROTATING slots,
+// (wix, wiy) = the window's pixel, wp = address of the aligned 32-bit word that holds the first byte of the window's
+// LAST row in the staged patch, wsh = bit shift of that byte inside the word (the same for every row of a window,
+// because the patch pitch is a multiple of four).
+//   parity_window_open   (cold: first row of a unit, or a lane's window did not simply move down one row)
+//                        positions the window ONE ROW ABOVE the pixel: rows 0..2 of the pixel's window go to slots
+//                        0..2, so that the very next slide step -- at the same pixel -- loads row 3 and evaluates;
+//   parity_slide_step<S> (hot) one pixel: warp, floor, "did every lane's window move down by exactly one row?"; if
+//                        not, returns false without side effects (the caller reopens the window at this pixel). Else
+//                        one row is read (wp += pitch: no address arithmetic from ix, iy), converted, and the pixel
+//                        is evaluated on slots (S, S+1, S+2, S+3) mod 4. Four steps with S = 0, 1, 2, 3 in a row
+//                        rotate the slots back: the window never moves between registers (the first form shifted
+//                        12 registers per pixel and paid ~7 more copies to merge its two branches).
+// The per-pixel results are bit-identical to the first form: same operations on the same values.
+template <int MODEL>
+__device__ __forceinline__ void parity_window_open(const float *pw, float xf, float yf, float ccx, float ccy,
+                                                   const uint8_t *patch, int px0, int py0, float (&cw)[4][4],
+                                                   int &wix, int &wiy, const uint8_t *&wp, int &wsh) {
+  float xd, yd, dxx, dyy;
+  warp_point<MODEL, DIC_MODE_PARITY>(pw, xf, yf, ccx, ccy, xd, yd, dxx, dyy);
+  int ix, iy;
+  floor_magic(xd, ix);
+  floor_magic(yd, iy);
+  const int o = (iy - 1 - py0) * kPatchW + (ix - 1 - px0); // byte offset of the window's first row
+  wsh = (o & 3) * 8;
+  const uint8_t *b = patch + (o & ~3);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(b + k * kPatchW);
+    row_coeffs_u8<DIC_MODE_PARITY>(__funnelshift_r(w[0], w[1], wsh), cw[k]);
+  }
+  wp = b + 2 * kPatchW;
+  wix = ix; wiy = iy - 1;
+}
+
+template <int MODEL, int S>
+__device__ __forceinline__ bool parity_slide_step(const float *pw, float xf, float yf, float ccx, float ccy,
+                                                  float (&cw)[4][4], int wix, int &wiy, const uint8_t *&wp, int wsh,
+                                                  float und_w, bool member, float *mom) {
+  constexpr int NP = model_nparams(MODEL);
+  float xd, yd, dxx, Y;
+  warp_point<MODEL, DIC_MODE_PARITY>(pw, xf, yf, ccx, ccy, xd, yd, dxx, Y);
+  int ix, iy;
+  const float fx = floor_magic(xd, ix), fy = floor_magic(yd, iy);
+  if (!__all_sync(0xffffffffu, ix == wix && iy == wiy + 1)) return false;
+  wp += kPatchW;
+  wiy = iy;
+  {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(wp);
+    row_coeffs_u8<DIC_MODE_PARITY>(__funnelshift_r(w[0], w[1], wsh), cw[(3 + S) & 3]);
+  }
+  float w, wx, wy;
+  bicubic_parity_rows_f(cw[(0 + S) & 3], cw[(1 + S) & 3], cw[(2 + S) & 3], cw[(3 + S) & 3], xd, yd, fx, fy, w, wx, wy);
+  float V = und_w - w;
+  V = member ? V : 0.f; wx = member ? wx : 0.f; wy = member ? wy : 0.f;
+  accumulate_moments<NP>(mom, V, wx, wy, Y);
+  return true;
+}
+
+#ifndef DIC_PARITY_LOOP
+#define DIC_PARITY_LOOP 2
+#endif
+
 // What a warp needs to know about a work unit before touching its pixels. A unit is a run of consecutive
 // rows of one tile: rows [r0, r0 + nr) after trimming the rows no lane owns.
 struct UnitPlan {
@@ -482,7 +546,25 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
       // 2.4x longer and the unrolled body overflowed the instruction cache (10 % no-instruction stalls).
 #define DIC_SHIFT()                                                                                  \
   _Pragma("unroll") for (int k_ = 0; k_ < 4; ++k_) { cw[0][k_] = cw[1][k_]; cw[1][k_] = cw[2][k_]; cw[2][k_] = cw[3][k_]; }
-      if (MODE == DIC_MODE_PARITY) {
+      if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 2) {
+        // one code path for full and partial units (three selects per pixel buy half the instruction footprint)
+        const uint8_t *wp = patch;
+        int wsh = 0;
+        float yf = (float)y0;       // exact: small integers; yf += 1 replaces an int -> float conversion per pixel
+        const uint8_t *up = ucol;   // reference pixel of the current row
+        uint32_t cm = q.full ? 0xffffffffu : colmask;
+        int r = 0;
+#define DIC_PSTEP(SV)                                                                                        \
+  if (!parity_slide_step<MODEL, SV>(pw, xf, yf, ccx, ccy, cw, wix, wiy, wp, wsh, (float)*up, (cm & 1u) != 0, mom)) break; \
+  yf += 1.f; up += kUndW; cm >>= 1; if (++r >= nr) break;
+#pragma unroll 1
+        while (r < nr) {
+          parity_window_open<MODEL>(pw, xf, yf, ccx, ccy, patch, px0, py0, cw, wix, wiy, wp, wsh);
+#pragma unroll 1
+          while (true) { DIC_PSTEP(0) DIC_PSTEP(1) DIC_PSTEP(2) DIC_PSTEP(3) }
+        }
+#undef DIC_PSTEP
+      } else if (MODE == DIC_MODE_PARITY) {
         if (q.full) {
 #pragma unroll 1
           for (int r = 0; r < nr; ++r) { DIC_STEP(true, 0, r); DIC_SHIFT(); }
@@ -555,8 +637,17 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float 
 //   GRID         one sector, every CTA of a cooperative launch works on it (large domains)
 //   !GRID, CL=1  each CTA owns whole sectors (BASELINE config 4: thousands of small subsets)
 //   !GRID, CL=2  each CTA PAIR (thread-block cluster of 2) owns whole sectors
+// Threads per CTA of the BATCH form (grid form: always kThreads). 128 = four warps per subset and four CTAs per SM:
+// while one subset's warp 0 runs its LM step + solve only three warps wait instead of seven, and the SM still
+// holds 16 warps (measured on c4: see DESIGN.md section 4.1).
+#ifndef DIC_BATCH_THREADS
+#define DIC_BATCH_THREADS 128
+#endif
+__host__ __device__ constexpr int tile_cta_threads(bool grid) { return grid ? kThreads : DIC_BATCH_THREADS; }
+__host__ __device__ constexpr int tile_ctas_for(int model, bool grid) { return tile_ctas_per_sm(model) * kThreads / tile_cta_threads(grid); }
+
 template <int MODEL, int MODE, bool GRID, int CL>
-__global__ void __launch_bounds__(kThreads, tile_ctas_per_sm(MODEL))
+__global__ void __launch_bounds__(tile_cta_threads(GRID), tile_ctas_for(MODEL, GRID))
 gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps maps,
                       const SectorDev *__restrict__ sectors, const SectorTiles *__restrict__ sector_tiles,
                       const float *guesses, const GuessParam guess0, dic_result *__restrict__ results, int first_sector,
@@ -564,11 +655,13 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   static_assert(!GRID || CL == 1, "clusters are a batch-mode feature");
+  constexpr int NT = tile_cta_threads(GRID), NW = NT / 32; // threads, warps of this CTA
+  static_assert(Acc<NP>::kN <= NT && kMaxParams <= NT, "one thread per accumulator / parameter");
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   uint8_t *s_stage = dyn_smem;                                                    // [warps][kWarpStageBytes]
-  float *s_wacc = reinterpret_cast<float *>(dyn_smem + kWarpsPerCta * kWarpStageBytes); // [warps][NACC]
+  float *s_wacc = reinterpret_cast<float *>(dyn_smem + NW * kWarpStageBytes);     // [warps][NACC]
   __shared__ SolveShared<NP> sh;
-  __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][2];
+  __shared__ __align__(8) uint64_t s_bar[NW][2];
   __shared__ SectorTiles s_tiles; // this sector's tile lists and centre: read once, not once per evaluation
   __shared__ float s_center[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -606,12 +699,12 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
       // quads of the level over the warps that take part: at least one quad per active warp
       const int n_quads = tl.n_tiles * 4;
       const int ctas = GRID ? (int)gridDim.x : CL;
-      const int n_active = max(1, min((n_quads + kWarpsPerCta - 1) / kWarpsPerCta, ctas));
+      const int n_active = max(1, min((n_quads + NW - 1) / NW, ctas));
       const int cta = GRID ? (int)blockIdx.x : crank;
       const bool active = cta < n_active;
       if (active) {
-        const int nw = n_active * kWarpsPerCta;
-        const int wg = cta * kWarpsPerCta + warp;
+        const int nw = n_active * NW;
+        const int wg = cta * NW + warp;
         // balanced contiguous ranges: the first (n_quads % nw) warps take one quad more
         const int base = n_quads / nw, rem = n_quads - base * nw;
         const int qb = wg * base + min(wg, rem), qe = qb + base + (wg < rem ? 1 : 0);
@@ -621,10 +714,10 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
           evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);
       }
       __syncthreads();
-      for (int k = tid; k < NACC; k += kThreads) {
+      for (int k = tid; k < NACC; k += NT) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) s += s_wacc[w * NACC + k];
+        for (int w = 0; w < NW; ++w) s += s_wacc[w * NACC + k];
         sh.tot[k] = s;
       }
       __syncthreads();
@@ -636,8 +729,8 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   if (GRID) grid_depart<NACC>(work, sh.rs_seq, sh.rowsplit != 0);
 }
 
-constexpr size_t tiles_dyn_smem(int nacc) {
-  return (size_t)kWarpsPerCta * kWarpStageBytes + sizeof(float) * (size_t)kWarpsPerCta * nacc;
+constexpr size_t tiles_dyn_smem(int nacc, bool grid) {
+  return (size_t)(tile_cta_threads(grid) / 32) * kWarpStageBytes + sizeof(float) * (size_t)(tile_cta_threads(grid) / 32) * nacc;
 }
 
 // ------------------------------------------------------------------ tile construction

@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdic_b200.so")
+# DIC_B200_LIB: an alternative build of the same library (A/B runs of kernel variants, tools/ab.sh)
+LIB_PATH = os.environ.get("DIC_B200_LIB") or os.path.join(HERE, "libdic_b200.so")
 
 MAX_PARAMS, MAX_LEVELS = 12, 8
 FM_U, FM_UV, FM_UVQ, FM_UVUxUyVxVy, FM_QUADRATIC = range(5)
@@ -72,7 +73,7 @@ EXPORTS = [
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
-    "dic_last_correlate_ms", "dic_last_step_ms", "dic_get_timeline", "dic_get_cta_times", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
+    "dic_last_correlate_ms", "dic_last_step_ms", "dic_get_timeline", "dic_get_cta_times", "dic_get_cta_smids", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
 ]
 
 
@@ -138,6 +139,7 @@ def load_library():
         "dic_last_step_ms": (F, [P]),
         "dic_get_timeline": (I, [P, P, I]),
         "dic_get_cta_times": (I, [P, P, I]),
+        "dic_get_cta_smids": (I, [P, P, I]),
         "dic_kernel_launches": (I64, [P]),
         "dic_correlation_stream": (P, [P]),
         "dic_synchronize": (I, [P]),
@@ -436,6 +438,11 @@ class CudaEngine:
     def cta_times(self, n=296):
         m = np.zeros(n, np.uint64)
         k = self.lib.dic_get_cta_times(self.h, _ptr(m), n)
+        return m[:k].astype(np.int64)
+
+    def cta_smids(self, n=296):
+        m = np.zeros(n, np.uint32)
+        k = self.lib.dic_get_cta_smids(self.h, _ptr(m), n)
         return m[:k].astype(np.int64)
 
     def kernel_launches(self):

@@ -240,6 +240,8 @@ int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap);
 /* load-balance probe: per CTA of the last single-sector correlate, the device time (ns) at which its
  * pass of the last evaluation ended. Returns the number of entries written (<= cap, <= 1024). */
 int dic_get_cta_times(dic_engine *e, unsigned long long *out, int cap);
+/* same probe: the SM each CTA of the last single-sector correlate ran on */
+int dic_get_cta_smids(dic_engine *e, unsigned int *out, int cap);
 int64_t dic_kernel_launches(const dic_engine *e);
 /* the CUDA stream handle (cudaStream_t as void*) the GN kernels run on, for event timing */
 void *dic_correlation_stream(dic_engine *e);

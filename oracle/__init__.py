@@ -216,7 +216,9 @@ class OracleEngine(_Base):
     Result = OrcResult
 
     def __init__(self, model=FM_AFFINE, interp=IM_BICUBIC, n_threads=20, precision=1e-3,
-                 max_iters=50, pyramid=(0, 1, 2), accum_double=False, real_threads=False):
+                 max_iters=50, pyramid=(0, 1, 2), accum_double=False, real_threads=False, solve_double=False):
+        """accum_double / solve_double: arbitration variants -- fp64 accumulators for A, b, chi and an fp64 solve of
+        the damped system, each the reference's algorithm with ONE source of fp32 rounding removed."""
         self.lib = C.CDLL(ORACLE_SO)
         self.n_params = N_PARAMS[model]
         P = C.c_void_p
@@ -231,6 +233,8 @@ class OracleEngine(_Base):
         self._level_pts = self._fn("level_points", None, P, C.c_int, _f32p)
         self.h = create(n_threads, interp, model, precision, max_iters, *pyramid,
                         int(accum_double), int(real_threads))
+        if solve_double:
+            self._fn("set_solve_double", None, P, C.c_int)(self.h, 1)
 
 
 # ---- free functions of the restatement (no engine needed) ---------------------------------

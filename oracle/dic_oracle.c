@@ -32,6 +32,10 @@
  *     ~1e12 larger than the translation columns at 4096^2).
  *   - the 6x6 solve restates Eigen 3.4.0 colPivHouseholderQr (oracle/qr_colpiv.h; parity
  *     unpinned at that boundary, shared with the _ref build so the two agree).
+ *   - optional fp64 solve of the same damped system (orc_set_solve_double) to arbitrate the solver the way
+ *     accum_double arbitrates the accumulators: the fp32 Householder QR of the UNEQUILIBRATED normal equations
+ *     (cond ~1e4..1e5 for a 125^2 subset) errs by ~cond * eps of the step, and the reported chi -- evaluated
+ *     at the point that step leads to -- moves by up to 2e-4 relative with it (tools/lm_trace.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.
@@ -82,6 +86,7 @@ typedef struct {
 
 typedef struct orc_engine {
   int n_threads, real_threads, accum_double;
+  int solve_double; /* arbitration variant: the damped system solved in fp64 instead of the fp32 column-pivoted QR */
   int interp, model, np;
   float precision;
   int max_iters;
@@ -528,6 +533,33 @@ static int evaluate(orc_engine *e, int level, const float *p) {
   return err;
 }
 
+/* fp64 Gaussian elimination with partial pivoting of the (float-valued) damped system */
+static void solve_fp64(const float *A, const float *b, float *x, int n) {
+  double M[ORC_MAXP][ORC_MAXP + 1];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) M[i][j] = A[i * n + j];
+    M[i][n] = b[i];
+  }
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(M[i][k]) > fabs(M[piv][k])) piv = i;
+    if (piv != k)
+      for (int j = 0; j <= n; ++j) { double t = M[k][j]; M[k][j] = M[piv][j]; M[piv][j] = t; }
+    for (int i = k + 1; i < n; ++i) {
+      double f = M[i][k] / M[k][k];
+      for (int j = k; j <= n; ++j) M[i][j] -= f * M[k][j];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double sacc = M[i][n];
+    for (int j = i + 1; j < n; ++j) sacc -= M[i][j] * (double)x[j];
+    x[i] = (float)(sacc / M[i][i]);
+  }
+}
+
+void orc_set_solve_double(orc_engine *e, int on) { e->solve_double = on; }
+
 /* correlation_class.cpp:642-688 + solve :719-768. p += dp in place. */
 static void compute_model_parameters(orc_engine *e, float *p, float lambda, float scaling) {
   const int np = e->np;
@@ -541,7 +573,9 @@ static void compute_model_parameters(orc_engine *e, float *p, float lambda, floa
     A[p1 * np + p1] *= (1.f + lambda);
   }
   float dp[ORC_MAXP];
-  if (e->model == FM_QUAD) {
+  if (e->solve_double) {
+    solve_fp64(A, b, dp, np);
+  } else if (e->model == FM_QUAD) {
     /* extension only: Jacobi equilibration S A S y = S b, dp = S y */
     float s[ORC_MAXP], As[ORC_MAXP * ORC_MAXP], bs[ORC_MAXP], y[ORC_MAXP];
     for (int i = 0; i < np; ++i) {

@@ -27,3 +27,12 @@ print("last pass: per-CTA end times (us): n", len(ct), "min %.1f p10 %.1f median
 print("  first 8 CTAs", np.round(ct[:8], 1), " last 8", np.round(ct[-8:], 1))
 order = np.argsort(ct)
 print("  slowest CTAs", order[-8:], np.round(ct[order[-8:]], 1))
+sm = eng.cta_smids(296)[: len(ct)]
+print("  CTA -> SM:", " ".join(f"{i}:{s}" for i, s in list(enumerate(sm))[:16]), "...")
+by_sm = {}
+for i, s in enumerate(sm):
+    by_sm.setdefault(int(s), []).append(i)
+print("  CTAs per SM histogram:", np.bincount([len(v) for v in by_sm.values()]))
+fast = [i for i in range(len(ct)) if ct[i] < np.median(ct) - 0.5 * (np.median(ct) - ct.min())]
+print("  fast CTAs:", fast[:40], "their SM mates:", [[j for j in by_sm[int(sm[i])] if j != i] for i in fast[:12]])
+print("  end time by SM (max over its CTAs) percentiles:", np.percentile([max(ct[j] for j in v) for v in by_sm.values()], [0, 10, 50, 90, 100]).round(1))
