@@ -25,8 +25,9 @@ constexpr int kMaxCtaMarks = 1024;
 // ------------------------------------------------------------------ descriptors
 
 struct LevelImage {
-  const uint8_t *ptr; // u8, row-major, `pitch` bytes per row (multiple of 128, >= cols + 16)
+  const uint8_t *ptr; // u8, row-major, `pitch` bytes per row (multiple of 128, >= cols * colors + 16)
   int rows, cols, pitch;
+  int colors;         // 1, or 3 interleaved channels (the reference's color_color mode, enums.hpp:37)
 };
 
 // Per-sector device record (one per domain / subdivision subset).
@@ -473,6 +474,91 @@ __device__ __forceinline__ void accumulate_pixel(const LevelImage &und, const Le
     for (int p2 = p1; p2 < NP; ++p2) {
       acc[k] = fmaf(H[p1], H[p2], acc[k]);
       ++k;
+    }
+  }
+}
+
+// ---- three-channel colour images (interpolation_class.cpp:712-750: the per-colour loop of one evaluation).
+// Column x of channel c sits at byte x * mult + add of its row. The reference's bicubic and bilinear coefficient
+// builders index the deformed image with `color = number_of_colors + color_in; index_ix = ix * color`
+// (interpolation_class.cpp:268-273, :356-359): mult = 3 + c, add = 0 -- right for channel 0 only, and what the CPU
+// engine EXECUTES for channels 1 and 2; parity means the same bytes here. Nearest uses ix * 3 + c (:391-398), and so
+// does the reference-image pixel (:701-704). Rows are padded and zero-filled, so the far reads of channel 2
+// (5 bytes per column) stay inside the level's allocation.
+template <int INTERP, int MODE>
+__device__ __forceinline__ bool sample_def_color(const LevelImage &img, float xdef, float ydef, int c, float &w,
+                                                 float &wx, float &wy) {
+  if (INTERP == DIC_IM_BICUBIC) {
+    if (!(xdef > 1.f && ydef > 1.f && xdef < (float)img.cols - 2.f && ydef < (float)img.rows - 2.f)) {
+      w = wx = wy = 0.f;
+      return false;
+    }
+    const int ix = (int)xdef, iy = (int)ydef, mult = 3 + c;
+    float p[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint8_t *row = img.ptr + (size_t)(iy - 1 + r) * img.pitch;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) p[r][k] = (float)__ldg(row + (ix - 1 + k) * mult);
+    }
+    if (MODE == DIC_MODE_PARITY) bicubic_parity(p, xdef, ydef, ix, iy, w, wx, wy);
+    else bicubic_fast(p, xdef - (float)ix, ydef - (float)iy, w, wx, wy);
+    return true;
+  }
+  if (!(xdef > 0.f && ydef > 0.f && xdef < (float)(img.cols - 1) && ydef < (float)(img.rows - 1))) {
+    w = wx = wy = 0.f;
+    return false;
+  }
+  if (INTERP == DIC_IM_BILINEAR) {
+    const int ix = (int)xdef, iy = (int)ydef, mult = 3 + c;
+    const uint8_t *r0 = img.ptr + (size_t)iy * img.pitch, *r1 = r0 + img.pitch;
+    const float w00 = (float)__ldg(r0 + ix * mult), w10 = (float)__ldg(r0 + (ix + 1) * mult);
+    const float w01 = (float)__ldg(r1 + ix * mult), w11 = (float)__ldg(r1 + (ix + 1) * mult);
+    const float a0 = w00, a1 = __fsub_rn(w10, w00), a2 = __fsub_rn(w01, w00);
+    const float a3 = __fadd_rn(__fsub_rn(__fsub_rn(w11, w10), w01), w00);
+    const float dx = __fsub_rn(xdef, (float)ix), dy = __fsub_rn(ydef, (float)iy);
+    float rw = a0;
+    rw = __fadd_rn(rw, __fmul_rn(a1, dx));
+    rw = __fadd_rn(rw, __fmul_rn(a2, dy));
+    rw = __fadd_rn(rw, __fmul_rn(__fmul_rn(a3, dy), dx));
+    w = rw; wx = __fadd_rn(a1, __fmul_rn(a3, dy)); wy = __fadd_rn(a2, __fmul_rn(a3, dx));
+    return true;
+  }
+  const int ix = (int)(xdef + 0.5f), iy = (int)(ydef + 0.5f);
+  const uint8_t *r0 = img.ptr + (size_t)iy * img.pitch + ix * 3 + c;
+  const float w00 = (float)__ldg(r0), w10 = (float)__ldg(r0 + 3), w01 = (float)__ldg(r0 + img.pitch);
+  w = w00; wx = __fsub_rn(w10, w00); wy = __fsub_rn(w01, w00);
+  return true;
+}
+
+template <int MODEL, int INTERP, int MODE>
+__device__ __forceinline__ void accumulate_pixel_color(const LevelImage &und, const LevelImage &def,
+                                                       const float *p, float cx, float cy, float x, float y,
+                                                       float *acc) {
+  constexpr int NP = model_nparams(MODEL);
+  using L = Acc<NP>;
+  float xd, yd, dx, dy;
+  warp_point<MODEL, MODE>(p, x, y, cx, cy, xd, yd, dx, dy);
+  const int uix = (int)(x + 0.5f), uiy = (int)(y + 0.5f);
+  const uint8_t *upx = und.ptr + (size_t)uiy * und.pitch + uix * 3;
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    float w, wx, wy;
+    const bool inside = sample_def_color<INTERP, MODE>(def, xd, yd, c, w, wx, wy);
+    const float V = (float)__ldg(upx + c) - w;
+    acc[L::kChi] = fmaf(V, V, acc[L::kChi]);
+    if (!inside) acc[L::kOob] += 1.f;
+    float H[NP];
+    descent_row<MODEL>(wx, wy, dx, dy, H);
+    int k = 0;
+#pragma unroll
+    for (int p1 = 0; p1 < NP; ++p1) {
+      acc[L::kB + p1] = fmaf(H[p1], V, acc[L::kB + p1]);
+#pragma unroll
+      for (int p2 = p1; p2 < NP; ++p2) {
+        acc[k] = fmaf(H[p1], H[p2], acc[k]);
+        ++k;
+      }
     }
   }
 }

@@ -87,6 +87,7 @@ struct dic_engine {
   float precision = 1e-3f;
   int model = DIC_FM_UVUxUyVxVy, interp = DIC_IM_BICUBIC, mode = DIC_MODE_PARITY;
   int center_mode = DIC_CENTER_REFERENCE;
+  int colors = 1; // channels of the images of the last dic_reset_image_pyramids (1, or 3 interleaved)
   std::vector<Sector> sectors;
   SectorDev *d_sectors = nullptr;
   SectorTiles *d_sector_tiles = nullptr;
@@ -194,7 +195,7 @@ int encode_level_map(dic_engine *e, CUtensorMap *map, const LevelImage &li, int 
 }
 
 // (Re)shape a pyramid slot for rows x cols, levels 0..stop.
-int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
+int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop, int colors = 1) {
   size_t total = 0;
   size_t off[kMaxLevels];
   int r = rows, c = cols;
@@ -203,9 +204,9 @@ int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
     // rows are 128-byte aligned; a row that is already a multiple of 128 stays tight so that the
     // level-0 upload is ONE linear PCIe copy (49 -> 55 GB/s measured against the pitched 2-D copy).
     // Loads past `cols` inside the pitch (or into the next row) are never used by an in-image sample.
-    int pitch = align_up(c, 128);
+    int pitch = align_up(c * colors, 128);
     off[l] = total;
-    lev[l].rows = r; lev[l].cols = c; lev[l].pitch = pitch;
+    lev[l].rows = r; lev[l].cols = c; lev[l].pitch = pitch; lev[l].colors = colors;
     total += (size_t)pitch * (r + 8);
     total = (total + 255) / 256 * 256;
     r /= 2; c /= 2;
@@ -216,12 +217,15 @@ int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop) {
     CU_TRY(e, cudaMalloc(&s.base, total));
     s.cap = total;
   }
+  // colour: the reference's coefficient builders read up to 5 bytes per column (see sample_def_color); padding
+  // and spare rows are zero so that those reads are deterministic
+  if (colors != 1) CU_TRY(e, cudaMemset(s.base, 0, total));
   for (int l = 0; l <= stop; ++l) {
     lev[l].ptr = s.base + off[l];
     const bool same = s.lev[l].ptr == lev[l].ptr && s.lev[l].rows == lev[l].rows && s.lev[l].cols == lev[l].cols &&
-                      s.lev[l].pitch == lev[l].pitch;
+                      s.lev[l].pitch == lev[l].pitch && s.lev[l].colors == lev[l].colors;
     s.lev[l] = lev[l];
-    if (!same && lev[l].rows > 0 && lev[l].cols > 0) {
+    if (colors == 1 && !same && lev[l].rows > 0 && lev[l].cols > 0) { // TMA descriptors: monochrome (tile kernel) only
       int rc = encode_level_map(e, &s.tm_patch[l], lev[l], kPatchW, kPatchH);
       if (!rc) rc = encode_level_map(e, &s.tm_tile[l], lev[l], kUndW, kTileH);
       if (!rc) rc = encode_level_map(e, &s.tm_pyr[l], lev[l], kPyrSW, kPyrSH);
@@ -243,6 +247,13 @@ int build_levels(dic_engine *e, PyramidSlot &s, int stop, cudaStream_t st, int r
     const LevelImage &src = s.lev[l - 1];
     const LevelImage &dst = s.lev[l];
     if (dst.rows <= 0 || dst.cols <= 0) break;
+    if (src.colors == 3) {
+      dim3 grid((dst.cols + 127) / 128, dst.rows);
+      pyramid_color_kernel<<<grid, 128, 0, st>>>(src.ptr, src.pitch, const_cast<uint8_t *>(dst.ptr), dst.rows, dst.cols,
+                                                 dst.pitch, kw);
+      e->launches++;
+      continue;
+    }
     // target row t reads source rows 2t-2 .. 2t+2
     const int tb = rb <= 0 ? 0 : (rb + 2 + 1) / 2;
     const int te = re >= src.rows ? dst.rows : std::min(dst.rows, (re - 1 - 2) / 2 + 1);
@@ -270,17 +281,18 @@ int upload_level0(dic_engine *e, PyramidSlot &s, const void *src, int rows, int 
                   bool src_on_device, cudaStream_t st) {
   uint8_t *dst = const_cast<uint8_t *>(s.lev[0].ptr);
   const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (spitch == cols && s.lev[0].pitch == cols)
-    CU_TRY(e, cudaMemcpyAsync(dst, src, (size_t)rows * cols, kind, st));
+  const int row_bytes = cols * s.lev[0].colors; // spitch: bytes per source row
+  if (spitch == row_bytes && s.lev[0].pitch == row_bytes)
+    CU_TRY(e, cudaMemcpyAsync(dst, src, (size_t)rows * row_bytes, kind, st));
   else
-    CU_TRY(e, cudaMemcpy2DAsync(dst, s.lev[0].pitch, src, spitch, cols, rows, kind, st));
+    CU_TRY(e, cudaMemcpy2DAsync(dst, s.lev[0].pitch, src, spitch, row_bytes, rows, kind, st));
   return DIC_OK;
 }
 
 int set_image(dic_engine *e, int role, const void *src, int rows, int cols, int spitch,
               bool on_device, cudaStream_t st) {
   PyramidSlot &s = e->pyr[e->role[role]];
-  int rc = shape_slot(e, s, rows, cols, e->stop);
+  int rc = shape_slot(e, s, rows, cols, e->stop, e->colors);
   if (rc) return rc;
   rc = upload_level0(e, s, src, rows, cols, spitch, on_device, st);
   if (rc) return rc;
@@ -654,13 +666,6 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
   return DIC_OK;
 }
 
-// Wave efficiency of `units` equal work items on `slots` concurrent slots.
-double wave_efficiency(long units, long slots) {
-  if (units <= 0 || slots <= 0) return 1.0;
-  const double waves = (double)units / (double)slots;
-  return waves / std::ceil(waves);
-}
-
 template <int MODEL, int MODE>
 int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   SolveSettings cfg = solve_settings(e);
@@ -704,13 +709,13 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
       CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern1, NTB, smem));
     }
     const long slots = (long)std::max(1, per_sm) * e->num_sms;
-    // one CTA pair per sector halves the scheduling granule: worth it when the last wave of whole-sector CTAs
-    // would leave a good part of the GPU idle (a few hundred subsets per GPU; 4096 subsets fill 13.8 waves
-    // either way). 3 % is the measured price of the cluster barrier + the exchange per evaluation.
-    // The granule that matters is per SM (co-resident CTAs share the SM's issue slots, and a CTA alone on an SM in
-    // the last wave runs faster): 512 subsets on 148 SMs = 3.46 -> 4 rounds (86 %), 1024 halves = 6.92 -> 7 (99 %).
-    bool pair = e->cluster_mode == 2 ||
-                (e->cluster_mode == 0 && 0.97 * wave_efficiency(2L * count, e->num_sms) > wave_efficiency(count, e->num_sms) + 0.02);
+    // One CTA pair per sector doubles the warps that work on a sector. Measured on c4 (B200, 128-thread CTAs, 4 per
+    // SM): a pair costs ~20 % per sector (cluster barrier + DSMEM exchange per evaluation, co-scheduling of the two
+    // CTAs inside one GPC), and a CTA does not run faster when its SM is only partly filled (a warp of this kernel
+    // is bound by its own dependent fp32 chains), so splitting sectors never shortens a launch that already fills
+    // the CTA slots once: 512 subsets per GPU take 0.43 ms as 1024 half-sector CTAs in 1.73 waves and 0.37 ms as
+    // 512 whole-sector CTAs in one wave. Pairs pay only when there are too few sectors to occupy the slots at all.
+    bool pair = e->cluster_mode == 2 || (e->cluster_mode == 0 && 2L * count <= slots);
     e->last_cluster = pair ? 2 : 1;
     if (pair) {
       cudaLaunchConfig_t lc;
@@ -736,6 +741,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
 
 bool tiles_applicable(const dic_engine *e, int first, int count) {
   if (e->kernel_variant == 1) return false;
+  if (e->colors != 1) return false; // colour images: generic pixel-list kernel
   if (e->interp != DIC_IM_BICUBIC) return false;
   if (e->model != DIC_FM_UVUxUyVxVy && e->model != DIC_FM_QUADRATIC) return false;
   for (int i = 0; i < count; ++i)
@@ -918,11 +924,19 @@ static int set_pyramid_range(dic_engine *e, int start, int step, int stop) {
 
 static int reset_pyramids_common(dic_engine *e, const void *und, const void *def, const void *nxt,
                                  int rows, int cols, int pitch, bool on_device, int start, int step,
-                                 int stop) {
+                                 int stop, int colors = 1) {
   if (!e || !und || !def || rows < 8 || cols < 8) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
+  NvtxRange nvtx("dic_reset_image_pyramids");
   int rc = set_pyramid_range(e, start, step, stop);
   if (rc) return rc;
+  if (colors == 3 && (cols % (1 << stop)) != 0) {
+    // pyramid_class.cpp:93-94 halves the BYTE step of a colour row (targetStep = sourceStep / 2): for an odd width
+    // that is not the width of the next level and the reference's own levels shear; refused instead of mimicked
+    set_error(e, "colour images need a width that stays even down to the coarsest pyramid level");
+    return DIC_ERROR_BAD_ARGUMENT;
+  }
+  e->colors = colors;
   if ((rc = set_image(e, 0, und, rows, cols, pitch, on_device, e->stream))) return rc;
   if ((rc = set_image(e, 1, def, rows, cols, pitch, on_device, e->stream))) return rc;
   if (nxt && (rc = set_image(e, 2, nxt, rows, cols, pitch, on_device, e->stream))) return rc;
@@ -932,8 +946,8 @@ static int reset_pyramids_common(dic_engine *e, const void *und, const void *def
 
 int dic_reset_image_pyramids(dic_engine *e, const uint8_t *und, const uint8_t *def, const uint8_t *nxt,
                              int rows, int cols, int channels, int start, int step, int stop) {
-  if (channels != 1) { if (e) set_error(e, "only monochrome images are implemented"); return DIC_ERROR_BAD_ARGUMENT; }
-  return reset_pyramids_common(e, und, def, nxt, rows, cols, cols, false, start, step, stop);
+  if (channels != 1 && channels != 3) { if (e) set_error(e, "images have 1 or 3 interleaved 8-bit channels"); return DIC_ERROR_BAD_ARGUMENT; }
+  return reset_pyramids_common(e, und, def, nxt, rows, cols, cols * channels, false, start, step, stop, channels);
 }
 int dic_reset_image_pyramids_device(dic_engine *e, const void *und, const void *def, const void *nxt,
                                     int rows, int cols, int pitch, int start, int step, int stop) {
@@ -948,13 +962,13 @@ int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols
   // still be reading: the upload waits for the correlation stream's position at that rotation (not for the
   // current frame's solve, which is what this call is meant to overlap with)
   CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_rot, 0));
-  int rc = set_image(e, 2, nxt, rows, cols, cols, false, e->img_stream);
+  int rc = set_image(e, 2, nxt, rows, cols, cols * e->colors, false, e->img_stream);
   if (rc) return rc;
   CU_TRY(e, cudaStreamSynchronize(e->img_stream));
   return DIC_OK;
 }
 int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt, int rows, int cols, int pitch) {
-  if (!e || !nxt) return DIC_ERROR_BAD_ARGUMENT;
+  if (!e || !nxt || e->colors != 1) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
   CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_rot, 0)); // see dic_reset_next_pyramid
   int rc = set_image(e, 2, nxt, rows, cols, pitch, true, e->img_stream);
@@ -966,13 +980,13 @@ int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt, int rows, int 
 int dic_reset_def_pyramid(dic_engine *e, const uint8_t *def, int rows, int cols) {
   if (!e || !def) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
-  int rc = set_image(e, 1, def, rows, cols, cols, false, e->stream);
+  int rc = set_image(e, 1, def, rows, cols, cols * e->colors, false, e->stream);
   if (rc) return rc;
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   return DIC_OK;
 }
 int dic_reset_def_pyramid_device(dic_engine *e, const void *def, int rows, int cols, int pitch) {
-  if (!e || !def) return DIC_ERROR_BAD_ARGUMENT;
+  if (!e || !def || e->colors != 1) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
   return set_image(e, 1, def, rows, cols, pitch, true, e->stream);
 }
@@ -1003,6 +1017,8 @@ int dic_make_def_pyramid_from_nxt(dic_engine *e) {
 static int stage_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols,
                            int row_begin, int row_end) {
   if (!e || !und || !def || rows < 8 || cols < 8) return DIC_ERROR_BAD_ARGUMENT;
+  if (e->colors != 1) { set_error(e, "staged image pairs are monochrome"); return DIC_ERROR_BAD_ARGUMENT; }
+  NvtxRange nvtx("dic_stage_next_pair");
   row_begin = std::max(0, row_begin); row_end = std::min(rows, row_end);
   if (row_end <= row_begin) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
@@ -1187,32 +1203,62 @@ static AnnulusGeom annulus_geom(float r, float dr, float a, float da, float cx, 
   return g;
 }
 
-// The sequential fp32 centre of the CPU engine for an annulus: its list order is x outer,
-// y inner (manager_class.cpp:902-919), so walk the box that way with the same predicate.
+// The sequential fp32 centre of the CPU engine for an annulus: its list order is x outer, y inner
+// (manager_class.cpp:902-919) and the centre is the running fp32 sum of that list divided by its length
+// (pyramid_class.cpp:325-347) -- inherently sequential, so it is replayed on the host. The membership test is not:
+// for a full ring (as == 1) the fp32 value r2 = fl(fl(ax * ax) + fl(ay * ay)) is monotone in |ay|, so the members
+// of a column are at most two runs of rows whose ends four binary searches find with the reference's own
+// predicate; only the 2 x N dependent additions remain (a 9 M pixel ring: 28 ms -> ~10 ms). Annular SECTORS
+// (as > 1: the wedge test is not monotone in a column) keep the plain walk over their much smaller box.
+static inline float ring_r2(float ax2, float j, float cy) {
+  const float ay = j - cy;
+  const float ay2 = ay * ay;
+  return ax2 + ay2;
+}
 static void annulus_reference_center(const AnnulusGeom &g, float cx, float cy, int as, float &ocx,
                                      float &ocy, long &count) {
-  volatile float sx = 0.f, sy = 0.f;
+  float sx = 0.f, sy = 0.f;
   long n = 0;
-  for (float i = (float)g.x0; i < (float)g.x1; ++i)
-    for (int j = g.y0; j < g.y1; ++j) {
-      volatile float ax = i - cx, ay = (float)j - cy;
-      volatile float ax2 = ax * ax, ay2 = ay * ay;
-      float r2 = ax2 + ay2;
-      if (r2 > g.ri2 && r2 < g.ro2) {
-        bool in = true;
-        if (as != 1) {
-          volatile float a1 = g.c11x - i, b1 = g.c01y - g.c11y, a2 = g.c11y - (float)j, b2 = g.c01x - g.c11x;
-          volatile float m1 = a1 * b1, m2 = a2 * b2;
-          float cross1 = m1 - m2;
-          volatile float a3 = g.c00x - i, b3 = g.c10y - g.c00y, a4 = g.c00y - (float)j, b4 = g.c10x - g.c00x;
-          volatile float m3 = a3 * b3, m4 = a4 * b4;
-          float cross2 = m3 - m4;
-          volatile float pr = cross1 * cross2;
-          in = pr > 0.f;
-        }
-        if (in) { sx = sx + i; sy = sy + (float)j; ++n; }
-      }
+  if (as == 1) {
+    // rows j0 .. j1 - 1; r2 falls while j < jc and rises from jc on (jc = first row with j - cy >= 0)
+    const int j0 = g.y0, j1 = g.y1;
+    int jc = j0;
+    while (jc < j1 && (float)jc - cy < 0.f) ++jc;
+    for (float i = (float)g.x0; i < (float)g.x1; ++i) {
+      const float ax = i - cx;
+      const float ax2 = ax * ax;
+      // falling side [j0, jc): members are rows with ri2 < r2 < ro2 -> [first r2 < ro2, last r2 > ri2]
+      // rising side  [jc, j1): members are                          -> [first r2 > ri2, last r2 < ro2]
+      auto first_true = [&](int lo, int hi, auto pred) { // smallest j in [lo, hi) with pred(j), pred monotone false -> true
+        while (lo < hi) { int mid = lo + (hi - lo) / 2; if (pred(mid)) hi = mid; else lo = mid + 1; }
+        return lo;
+      };
+      const int a_lo = first_true(j0, jc, [&](int j) { return ring_r2(ax2, (float)j, cy) < g.ro2; });
+      const int a_hi = first_true(j0, jc, [&](int j) { return !(ring_r2(ax2, (float)j, cy) > g.ri2); }); // exclusive
+      const int b_lo = first_true(jc, j1, [&](int j) { return ring_r2(ax2, (float)j, cy) > g.ri2; });
+      const int b_hi = first_true(jc, j1, [&](int j) { return !(ring_r2(ax2, (float)j, cy) < g.ro2); }); // exclusive
+      for (int j = a_lo; j < a_hi; ++j) { sx = sx + i; sy = sy + (float)j; }
+      for (int j = b_lo; j < b_hi; ++j) { sx = sx + i; sy = sy + (float)j; }
+      n += std::max(0, a_hi - a_lo) + std::max(0, b_hi - b_lo);
     }
+  } else {
+    for (float i = (float)g.x0; i < (float)g.x1; ++i)
+      for (int j = g.y0; j < g.y1; ++j) {
+        const float ax = i - cx, ay = (float)j - cy;
+        const float ax2 = ax * ax, ay2 = ay * ay;
+        const float r2 = ax2 + ay2;
+        if (r2 > g.ri2 && r2 < g.ro2) {
+          const float a1 = g.c11x - i, b1 = g.c01y - g.c11y, a2 = g.c11y - (float)j, b2 = g.c01x - g.c11x;
+          const float m1 = a1 * b1, m2 = a2 * b2;
+          const float cross1 = m1 - m2;
+          const float a3 = g.c00x - i, b3 = g.c10y - g.c00y, a4 = g.c00y - (float)j, b4 = g.c10x - g.c00x;
+          const float m3 = a3 * b3, m4 = a4 * b4;
+          const float cross2 = m3 - m4;
+          const float pr = cross1 * cross2;
+          if (pr > 0.f) { sx = sx + i; sy = sy + (float)j; ++n; }
+        }
+      }
+  }
   count = n;
   ocx = n ? sx / (float)n : cx;
   ocy = n ? sy / (float)n : cy;
@@ -1794,7 +1840,8 @@ int dic_get_pyramid_level(dic_engine *e, int which, int level, uint8_t *out, int
   if (cols) *cols = li.cols;
   if (!out) return DIC_OK;
   cudaStream_t st = which == 2 ? e->img_stream : e->stream;
-  CU_TRY(e, cudaMemcpy2DAsync(out, li.cols, li.ptr, li.pitch, li.cols, li.rows, cudaMemcpyDeviceToHost, st));
+  CU_TRY(e, cudaMemcpy2DAsync(out, (size_t)li.cols * li.colors, li.ptr, li.pitch, (size_t)li.cols * li.colors, li.rows,
+                              cudaMemcpyDeviceToHost, st));
   CU_TRY(e, cudaStreamSynchronize(st));
   return DIC_OK;
 }

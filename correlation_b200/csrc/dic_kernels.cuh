@@ -239,6 +239,13 @@ __device__ __forceinline__ void evaluate_list(const SolveSettings &cfg, const Se
   const long n = sec->n[level];
   const float inv = 1.f / (float)(1 << level); // pyramid_class.cpp:357-361
   const float cx = sec->cx * inv, cy = sec->cy * inv;
+  if (MODE == DIC_MODE_PARITY && und.colors == 3) { // colour images: generic path only, reference arithmetic only
+    for (long i = first; i < n; i += stride) {
+      float2 q = __ldg(xy + i);
+      accumulate_pixel_color<MODEL, INTERP, MODE>(und, def, p, cx, cy, q.x, q.y, acc);
+    }
+    return;
+  }
   for (long i = first; i < n; i += stride) {
     float2 q = __ldg(xy + i);
     accumulate_pixel<MODEL, INTERP, MODE>(und, def, p, cx, cy, q.x, q.y, acc);
@@ -709,6 +716,28 @@ pyramid_level_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t *__res
       }
     }
     __syncthreads(); // the fp32 tile is free for the next conversion
+  }
+}
+
+// pyramid_class.cpp:52-134 for three interleaved channels (the reference GPU's k_pyramid_color, kernels.cu:841-918,
+// is what this replaces; the arithmetic is the CPU engine's): per target pixel and channel the same 25 sequential
+// fp32 multiply-adds in dj-outer / di-inner order, truncation, zero border. Not a hot kernel (colour images take
+// the generic pixel-list path): one thread per target pixel, plain loads.
+__global__ void pyramid_color_kernel(const uint8_t *__restrict__ src, int spitch, uint8_t *__restrict__ dst, int drows,
+                                     int dcols, int dpitch, PyrWeights kw) {
+  const int ti = blockIdx.x * blockDim.x + threadIdx.x, tj = blockIdx.y;
+  if (ti >= dcols || tj >= drows) return;
+  const bool interior = ti >= 1 && tj >= 1 && ti < dcols - 1 && tj < drows - 1;
+  for (int c = 0; c < 3; ++c) {
+    float addition = 0.f;
+    if (interior) {
+      for (int dj = -2; dj <= 2; ++dj)
+        for (int di = -2; di <= 2; ++di) {
+          const float sv = (float)__ldg(src + (size_t)(2 * tj + dj) * spitch + (2 * ti + di) * 3 + c);
+          addition = __fadd_rn(addition, __fmul_rn(sv, kw.w[(2 + dj) * 5 + (2 + di)]));
+        }
+    }
+    dst[(size_t)tj * dpitch + ti * 3 + c] = interior ? (uint8_t)__float2uint_rz(addition) : (uint8_t)0;
   }
 }
 

@@ -823,10 +823,10 @@ struct RectDesc {
 __global__ void rect_grid_fill_kernel(const RectDesc *__restrict__ desc, int n_desc, float2 *__restrict__ lists) {
   for (int di = blockIdx.y; di < n_desc; di += gridDim.y) {
     const RectDesc d = desc[di];
-    const long n = (long)d.nx * d.ny;
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = d.nx * d.ny; // one rectangle at one level: far below 2^31 pixels
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) continue;
-    const int row = (int)(i / d.nx), col = (int)(i % d.nx);
+    const int row = i / d.nx, col = i - row * d.nx;
     const float inv = 1.f / (float)d.mag;
     lists[d.list_off + i] = make_float2((float)(d.xs + col * d.mag) * inv, (float)(d.ys + row * d.mag) * inv);
   }

@@ -224,17 +224,19 @@ class CudaEngine:
     @staticmethod
     def _img(a):
         a = np.ascontiguousarray(a, np.uint8)
-        assert a.ndim == 2
+        assert a.ndim == 2 or (a.ndim == 3 and a.shape[2] == 3), "rows x cols (monochrome) or rows x cols x 3 (colour)"
         return a
 
     def resetImagePyramids(self, und, dfm, nxt=None, pyramid=(0, 1, 2)):
         und, dfm = self._img(und), self._img(dfm)
         nx = self._img(nxt) if nxt is not None else None
+        self.channels = 3 if und.ndim == 3 else 1
         self._ck(self.lib.dic_reset_image_pyramids(
             self.h, _ptr(und), _ptr(dfm), _ptr(nx) if nx is not None else None,
-            und.shape[0], und.shape[1], 1, *pyramid))
+            und.shape[0], und.shape[1], self.channels, *pyramid))
 
     def resetImagePyramidsDevice(self, und_ptr, def_ptr, nxt_ptr, rows, cols, pitch, pyramid=(0, 1, 2)):
+        self.channels = 1
         self._ck(self.lib.dic_reset_image_pyramids_device(self.h, und_ptr, def_ptr, nxt_ptr, rows, cols,
                                                           pitch, *pyramid))
 
@@ -401,7 +403,8 @@ class CudaEngine:
     def pyramid_level(self, which, level):
         r, c = C.c_int(), C.c_int()
         self._ck(self.lib.dic_get_pyramid_level(self.h, which, level, None, C.byref(r), C.byref(c)))
-        out = np.zeros((r.value, c.value), np.uint8)
+        ch = getattr(self, "channels", 1)
+        out = np.zeros((r.value, c.value) if ch == 1 else (r.value, c.value, 3), np.uint8)
         self._ck(self.lib.dic_get_pyramid_level(self.h, which, level, _ptr(out), C.byref(r), C.byref(c)))
         return out
 

@@ -108,8 +108,13 @@ int dic_set_center_mode(dic_engine *e, int center_mode);
 int dic_set_kernel_variant(dic_engine *e, int variant);
 
 /* ---- CudaClass::resetImagePyramids(undPath, defPath, nxtPath, color, start, step, stop)
- *      (cuda_class.cu:512-572): host u8 images (row-major, `channels` interleaved; only
- *      channels == 1 is implemented), builds all three pyramids. nxt may be NULL. */
+ *      (cuda_class.cu:512-572): host u8 images (row-major, `channels` interleaved: 1 = monochrome,
+ *      3 = the reference's color_color mode), builds all three pyramids. nxt may be NULL.
+ *      Colour follows the CPU engine as executed: per-channel pyramid (pyramid_class.cpp:52-134), per-colour loop
+ *      of the evaluation (interpolation_class.cpp:712-750) INCLUDING the column indexing of its bicubic / bilinear
+ *      coefficient builders (ix * (3 + channel), :268-273, :356-359). Colour images take the generic pixel-list
+ *      kernel, need a width that stays even down to the coarsest level, and later next / def images passed to
+ *      dic_reset_next_pyramid / dic_reset_def_pyramid have the same channel count. */
 int dic_reset_image_pyramids(dic_engine *e, const uint8_t *und, const uint8_t *def,
                              const uint8_t *nxt, int rows, int cols, int channels,
                              int pyramid_start, int pyramid_step, int pyramid_stop);
@@ -186,7 +191,7 @@ int dic_correlate_batch(dic_engine *e, int first_sector, int n_sectors, float *g
                         dic_result *results);
 /* extension: how dic_correlate_batch maps sectors to thread blocks. 0 (default) = automatic: one CTA per
  * sector, or one CTA PAIR per sector (thread-block cluster of 2, partial sums exchanged through distributed
- * shared memory) when that fills the GPU's last wave better; 1 = always one CTA; 2 = always a pair.
+ * shared memory) when there are too few sectors to occupy the GPU's CTA slots at all; 1 = always one CTA; 2 = always a pair.
  * Results are identical to ~1 ulp of the sums (the two halves are added in a fixed order). */
 int dic_set_cluster_mode(dic_engine *e, int mode);
 /* CTAs per sector the last dic_correlate_batch launch used (1 or 2) */

@@ -98,7 +98,8 @@ class _Base:
     # -- images
     def set_image(self, which, img):
         img = np.ascontiguousarray(img, np.uint8)
-        self._set_img[which](self.h, img, img.shape[0], img.shape[1])
+        assert (img.ndim == 3 and img.shape[2] == 3) == (self.colors == 3), "image channels must match the engine's colours"
+        self._set_img[which](self.h, img.reshape(img.shape[0], -1), img.shape[0], img.shape[1])
 
     def und_from_def(self):
         self._und_from_def(self.h)
@@ -144,7 +145,7 @@ class _Base:
     def pyramid_level(self, which, level):
         r, c = C.c_int(), C.c_int()
         self._pyr(self.h, which, level, None, C.byref(r), C.byref(c))
-        out = np.empty((r.value, c.value), np.uint8)
+        out = np.empty((r.value, c.value) if self.colors == 1 else (r.value, c.value, 3), np.uint8)
         self._pyr(self.h, which, level, out.ctypes.data_as(C.c_void_p), C.byref(r), C.byref(c))
         return out
 
@@ -182,14 +183,15 @@ class RefEngine(_Base):
     Result = RefResult
 
     def __init__(self, model=FM_AFFINE, interp=IM_BICUBIC, n_threads=20, precision=1e-3,
-                 max_iters=50, pyramid=(0, 1, 2)):
+                 max_iters=50, pyramid=(0, 1, 2), colors=1):
         if model == FM_QUAD:
             raise ValueError("the reference has no 12-parameter model (SURVEY fact 2)")
         self.lib = C.CDLL(REF_SO)
         self.n_params = N_PARAMS[model]
+        self.colors = 3 if colors == 3 else 1
         P = C.c_void_p
-        create = self._fn("create", P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
-                          C.c_int, C.c_int, C.c_int)
+        create = self._fn("create_color", P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                          C.c_int, C.c_int, C.c_int, C.c_int)
         self._common()
         self._correlate = self._fn("correlate", C.c_int, P, _f32p, _f32p, C.c_int, C.c_int,
                                    C.c_float, C.c_float, C.POINTER(RefResult))
@@ -197,7 +199,7 @@ class RefEngine(_Base):
                                     C.c_float, C.c_float)
         self._level_n = self._fn("level_num_points", C.c_int, P, C.c_int)
         self._level_pts = self._fn("level_points", None, P, C.c_int, _f32p)
-        self.h = create(n_threads, interp, model, precision, max_iters, *pyramid)
+        self.h = create(n_threads, interp, model, precision, max_iters, *pyramid, self.colors)
 
     def blob_points(self, contour):
         contour = np.ascontiguousarray(contour, np.float32).reshape(-1, 2)
@@ -216,11 +218,12 @@ class OracleEngine(_Base):
     Result = OrcResult
 
     def __init__(self, model=FM_AFFINE, interp=IM_BICUBIC, n_threads=20, precision=1e-3,
-                 max_iters=50, pyramid=(0, 1, 2), accum_double=False, real_threads=False, solve_double=False):
+                 max_iters=50, pyramid=(0, 1, 2), accum_double=False, real_threads=False, solve_double=False, colors=1):
         """accum_double / solve_double: arbitration variants -- fp64 accumulators for A, b, chi and an fp64 solve of
         the damped system, each the reference's algorithm with ONE source of fp32 rounding removed."""
         self.lib = C.CDLL(ORACLE_SO)
         self.n_params = N_PARAMS[model]
+        self.colors = 3 if colors == 3 else 1
         P = C.c_void_p
         create = self._fn("create", P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
@@ -235,6 +238,8 @@ class OracleEngine(_Base):
                         int(accum_double), int(real_threads))
         if solve_double:
             self._fn("set_solve_double", None, P, C.c_int)(self.h, 1)
+        if self.colors == 3:
+            self._fn("set_colors", None, P, C.c_int)(self.h, 3)
 
 
 # ---- free functions of the restatement (no engine needed) ---------------------------------

@@ -86,6 +86,7 @@ typedef struct {
 
 typedef struct orc_engine {
   int n_threads, real_threads, accum_double;
+  int colors;       /* 1 (monochrome) or 3 (interleaved colour image), set before the images (orc_set_colors) */
   int solve_double; /* arbitration variant: the damped system solved in fp64 instead of the fp32 column-pivoted QR */
   int interp, model, np;
   float precision;
@@ -124,34 +125,35 @@ static void pyr_free(orc_pyr *p) {
 /* pyramid_class.cpp:52-134: 5x5 kernel [.05 .25 .4 .25 .05]^2, weights formed as fp32
  * products at run time (:83-90), 25 sequential mul+add in dj-outer/di-inner order (:109-117),
  * truncation to u8 (:118-119), 1-px zero border (zero-initialised target, loops 1..n-2). */
-static void pyr_build(orc_pyr *p, const uint8_t *img, int rows, int cols, int stop) {
+static void pyr_build(orc_pyr *p, const uint8_t *img, int rows, int cols, int stop, int colors) {
   pyr_free(p);
   p->rows = rows; p->cols = cols; p->n = stop + 1;
-  p->lev[0] = (uint8_t *)malloc((size_t)rows * cols);
-  memcpy(p->lev[0], img, (size_t)rows * cols);
+  p->lev[0] = (uint8_t *)malloc((size_t)rows * cols * colors);
+  memcpy(p->lev[0], img, (size_t)rows * cols * colors);
   const float km[5] = {0.05f, 0.25f, 0.4f, 0.25f, 0.05f};
   float kernel[25];
   for (int i = 0; i < 5; ++i)
     for (int j = 0; j < 5; ++j) kernel[5 * j + i] = km[i] * km[j];
   int sc = cols, sr = rows;
   for (int l = 1; l <= stop; ++l) {
-    long sstep = sc;
+    long sstep = (long)sc * colors;      /* :93 */
     int tc = sc / 2, tr = sr / 2;
-    long tstep = sstep / 2;
-    uint8_t *dst = (uint8_t *)calloc((size_t)tc * tr + 1, 1);
+    long tstep = sstep / 2;              /* :94 (== tc * colors for the even widths the colour path is used with) */
+    uint8_t *dst = (uint8_t *)calloc((size_t)tc * tr * colors + colors, 1);
     const uint8_t *src = p->lev[l - 1];
     for (int tj = 1; tj < tr - 1; ++tj)
-      for (int ti = 1; ti < tc - 1; ++ti) {
-        int si = ti * 2, sj = tj * 2;
-        float addition = 0.f;
-        for (int dj = -2; dj <= 2; ++dj)
-          for (int di = -2; di <= 2; ++di) {
-            uint8_t s = src[sstep * (sj + dj) + (si + di)];
-            float ker = kernel[(2 + dj) * 5 + (2 + di)];
-            addition += (float)s * ker;
-          }
-        dst[tstep * tj + ti] = (uint8_t)addition;
-      }
+      for (int ti = 1; ti < tc - 1; ++ti)
+        for (int c = 0; c < colors; ++c) {
+          int si = ti * 2, sj = tj * 2;
+          float addition = 0.f;
+          for (int dj = -2; dj <= 2; ++dj)
+            for (int di = -2; di <= 2; ++di) {
+              uint8_t s = src[sstep * (sj + dj) + (long)(si + di) * colors + c];
+              float ker = kernel[(2 + dj) * 5 + (2 + di)];
+              addition += (float)s * ker;
+            }
+          dst[tstep * tj + (long)ti * colors + c] = (uint8_t)addition;
+        }
     p->lev[l] = dst;
     sr = tr; sc = tc;
   }
@@ -168,8 +170,12 @@ orc_engine *orc_create(int n_threads, int interp, int model, float precision, in
   e->interp = interp; e->model = model; e->np = model_nparams(model);
   e->precision = precision; e->max_iters = max_iters;
   e->start = start; e->step = step < 1 ? 1 : step; e->stop = stop;
+  e->colors = 1;
   return e;
 }
+
+/* number_of_colors of the reference (manager_class.cpp:99-109): 3 for interleaved colour images */
+void orc_set_colors(orc_engine *e, int colors) { e->colors = colors == 3 ? 3 : 1; }
 
 static void free_points(orc_engine *e) {
   for (int i = 0; i < ORC_MAXLEV; ++i) { free(e->xy[i]); e->xy[i] = NULL; e->npts[i] = 0; }
@@ -183,13 +189,13 @@ void orc_destroy(orc_engine *e) {
 }
 
 void orc_set_und_image(orc_engine *e, const uint8_t *img, int rows, int cols) {
-  pyr_build(&e->und, img, rows, cols, e->stop);
+  pyr_build(&e->und, img, rows, cols, e->stop, e->colors);
 }
 void orc_set_def_image(orc_engine *e, const uint8_t *img, int rows, int cols) {
-  pyr_build(&e->def, img, rows, cols, e->stop);
+  pyr_build(&e->def, img, rows, cols, e->stop, e->colors);
 }
 void orc_set_nxt_image(orc_engine *e, const uint8_t *img, int rows, int cols) {
-  pyr_build(&e->nxt, img, rows, cols, e->stop);
+  pyr_build(&e->nxt, img, rows, cols, e->stop, e->colors);
 }
 /* pyramid_class.cpp:211-258: pointer rotation */
 void orc_und_from_def(orc_engine *e) {
@@ -249,7 +255,7 @@ void orc_pyramid_level(orc_engine *e, int which, int level, uint8_t *out, int *r
   orc_pyr *p = which == 0 ? &e->und : (which == 1 ? &e->def : &e->nxt);
   int r = p->rows / (1 << level), c = p->cols / (1 << level);
   *rows = r; *cols = c;
-  if (out) memcpy(out, p->lev[level], (size_t)r * c);
+  if (out) memcpy(out, p->lev[level], (size_t)r * c * e->colors);
 }
 
 /* pyramid_class.cpp:260-287: only u, v scale; the quadratic extension scales the
@@ -292,11 +298,14 @@ static const float BICUBIC_M[256] = {
 
 const float *orc_bicubic_matrix(void) { return BICUBIC_M; }
 
-/* interpolation_class.cpp:243-336 (monochrome) */
-static void bicubic_coeffs(const uint8_t *img, long step, int x, int y, float *a) {
+/* interpolation_class.cpp:243-336. Column x of colour channel c lives at byte x * mult (+ add) of its row:
+ * monochrome mult = 1; for colour images the reference's bicubic and bilinear coefficient builders index with
+ * `color = number_of_colors + color_in; index_ix = ix * color` (:268-273, :356-359), i.e. mult = 3 + c, add = 0 --
+ * correct for channel 0 only; restated as executed. Nearest uses ix * number_of_colors + color_in (:391-398). */
+static void bicubic_coeffs(const uint8_t *img, long step, int x, int y, int mult, float *a) {
   const uint8_t *r0 = img + step * (y - 1), *r1 = img + step * y, *r2 = img + step * (y + 1),
                 *r3 = img + step * (y + 2);
-  int x0 = x - 1, x1 = x, x2 = x + 1, x3 = x + 2;
+  int x0 = (x - 1) * mult, x1 = x * mult, x2 = (x + 1) * mult, x3 = (x + 2) * mult;
   float w00 = r0[x0], w01 = r1[x0], w02 = r2[x0], w03 = r3[x0];
   float w10 = r0[x1], w11 = r1[x1], w12 = r2[x1], w13 = r3[x1];
   float w20 = r0[x2], w21 = r1[x2], w22 = r2[x2], w23 = r3[x2];
@@ -317,13 +326,13 @@ static void bicubic_coeffs(const uint8_t *img, long step, int x, int y, float *a
 }
 
 /* returns 0 when in bounds, else ERR_INTERP_OOB (w = wx = wy = 0) */
-static int interp_bicubic(const uint8_t *img, int rows, int cols, long step, float xdef,
+static int interp_bicubic(const uint8_t *img, int rows, int cols, long step, int mult, float xdef,
                           float ydef, float *w, float *wx, float *wy) {
   /* interpolation_class.cpp:82-83 */
   if (xdef > 1.f && ydef > 1.f && xdef < cols - 2.f && ydef < rows - 2.f) {
     int ix = (int)xdef, iy = (int)ydef;
     float a[16];
-    bicubic_coeffs(img, step, ix, iy, a);
+    bicubic_coeffs(img, step, ix, iy, mult, a);
     float dx = xdef - ix + 1.f;
     float dy = ydef - iy + 1.f;
     float px[4] = {1.f, dx, dx * dx, dx * dx * dx};
@@ -344,12 +353,12 @@ static int interp_bicubic(const uint8_t *img, int rows, int cols, long step, flo
 }
 
 /* interpolation_class.cpp:140-195 + :338-374 */
-static int interp_bilinear(const uint8_t *img, int rows, int cols, long step, float xdef,
+static int interp_bilinear(const uint8_t *img, int rows, int cols, long step, int mult, float xdef,
                            float ydef, float *w, float *wx, float *wy) {
   if (xdef > 0 && ydef > 0 && xdef < cols - 1 && ydef < rows - 1) {
     int ix = (int)xdef, iy = (int)ydef;
-    float w00 = img[step * iy + ix], w01 = img[step * (iy + 1) + ix];
-    float w10 = img[step * iy + ix + 1], w11 = img[step * (iy + 1) + ix + 1];
+    float w00 = img[step * iy + ix * mult], w01 = img[step * (iy + 1) + ix * mult];
+    float w10 = img[step * iy + (ix + 1) * mult], w11 = img[step * (iy + 1) + (ix + 1) * mult];
     float a[4] = {w00, w10 - w00, w01 - w00, w11 - w10 - w01 + w00};
     float dx = xdef - ix, dy = ydef - iy;
     float px[2] = {1.f, dx}, py[2] = {1.f, dy};
@@ -369,12 +378,12 @@ static int interp_bilinear(const uint8_t *img, int rows, int cols, long step, fl
 }
 
 /* interpolation_class.cpp:197-226 + :376-406 */
-static int interp_nearest(const uint8_t *img, int rows, int cols, long step, float xdef,
+static int interp_nearest(const uint8_t *img, int rows, int cols, long step, int mult, int add, float xdef,
                           float ydef, float *w, float *wx, float *wy) {
   if (xdef > 0 && ydef > 0 && xdef < cols - 1 && ydef < rows - 1) {
     int ix = (int)(xdef + 0.5f), iy = (int)(ydef + 0.5f);
-    float w00 = img[step * iy + ix], w01 = img[step * (iy + 1) + ix];
-    float w10 = img[step * iy + ix + 1];
+    float w00 = img[step * iy + ix * mult + add], w01 = img[step * (iy + 1) + ix * mult + add];
+    float w10 = img[step * iy + (ix + 1) * mult + add];
     *w = w00; *wx = w10 - w00; *wy = w01 - w00;
     return 0;
   }
@@ -443,9 +452,10 @@ static void *chunk_run(void *arg) {
   const orc_engine *e = c->e;
   const int np = e->np, L = c->level;
   const uint8_t *und = e->und.lev[L], *def = e->def.lev[L];
-  const long ustep = e->und.cols / (1 << L);
+  const int nc = e->colors;
+  const long ustep = (long)(e->und.cols / (1 << L)) * nc;
   const int drows = e->def.rows / (1 << L), dcols = e->def.cols / (1 << L);
-  const long dstep = e->def.cols / (1 << L);
+  const long dstep = (long)(e->def.cols / (1 << L)) * nc;
   const float *xy = e->xy[L] + 2 * c->first;
   const float cx = e->cx[L], cy = e->cy[L];
   float dTx[ORC_MAXP], dTy[ORC_MAXP], H[ORC_MAXP];
@@ -457,25 +467,28 @@ static void *chunk_run(void *arg) {
     float xd, yd, w, wx, wy;
     model_point(e->model, c->p, x, y, cx, cy, &xd, &yd, dTx, dTy);
     int und_ix = (int)(x + 0.5f), und_iy = (int)(y + 0.5f);
-    int err;
-    if (e->interp == IM_BICUBIC) err = interp_bicubic(def, drows, dcols, dstep, xd, yd, &w, &wx, &wy);
-    else if (e->interp == IM_BILINEAR) err = interp_bilinear(def, drows, dcols, dstep, xd, yd, &w, &wx, &wy);
-    else err = interp_nearest(def, drows, dcols, dstep, xd, yd, &w, &wx, &wy);
-    if (err) c->error = err;
-    float und_w = (float)und[ustep * und_iy + und_ix];
-    float V = und_w - w;
-    for (int p = 0; p < np; ++p) H[p] = wx * dTx[p] + wy * dTy[p];
-    if (!e->accum_double) {
-      c->chi += V * V;
-      for (int p1 = 0; p1 < np; ++p1) {
-        c->b[p1] += H[p1] * V;
-        for (int p2 = p1; p2 < np; ++p2) c->A[p1 * np + p2] += H[p1] * H[p2];
-      }
-    } else {
-      c->chid += (double)(V * V);
-      for (int p1 = 0; p1 < np; ++p1) {
-        c->bd[p1] += (double)(H[p1] * V);
-        for (int p2 = p1; p2 < np; ++p2) c->Ad[p1 * np + p2] += (double)(H[p1] * H[p2]);
+    for (int col = 0; col < nc; ++col) { /* interpolation_class.cpp:712-750: per-colour loop */
+      int err;
+      const int mult = nc == 1 ? 1 : nc + col;
+      if (e->interp == IM_BICUBIC) err = interp_bicubic(def, drows, dcols, dstep, mult, xd, yd, &w, &wx, &wy);
+      else if (e->interp == IM_BILINEAR) err = interp_bilinear(def, drows, dcols, dstep, mult, xd, yd, &w, &wx, &wy);
+      else err = interp_nearest(def, drows, dcols, dstep, nc, col, xd, yd, &w, &wx, &wy);
+      if (err) c->error = err;
+      float und_w = (float)und[ustep * und_iy + (long)und_ix * nc + col];
+      float V = und_w - w;
+      for (int p = 0; p < np; ++p) H[p] = wx * dTx[p] + wy * dTy[p];
+      if (!e->accum_double) {
+        c->chi += V * V;
+        for (int p1 = 0; p1 < np; ++p1) {
+          c->b[p1] += H[p1] * V;
+          for (int p2 = p1; p2 < np; ++p2) c->A[p1 * np + p2] += H[p1] * H[p2];
+        }
+      } else {
+        c->chid += (double)(V * V);
+        for (int p1 = 0; p1 < np; ++p1) {
+          c->bd[p1] += (double)(H[p1] * V);
+          for (int p2 = p1; p2 < np; ++p2) c->Ad[p1 * np + p2] += (double)(H[p1] * H[p2]);
+        }
       }
     }
   }

@@ -70,6 +70,7 @@ struct ref_engine {
   cv::Mat und, def, nxt;
   std::vector<float> xy; // level-0 list: owned here, borrowed by the pyramid
   int n_params{0};
+  int colors{1};
 };
 
 ref_engine *ref_create(int n_threads, int interpolation_model, int fitting_model,
@@ -87,6 +88,18 @@ ref_engine *ref_create(int n_threads, int interpolation_model, int fitting_model
   return e;
 }
 
+// colour images: number_of_colors = 3 (manager_class.cpp:99-109), interleaved 8-bit channels
+ref_engine *ref_create_color(int n_threads, int interpolation_model, int fitting_model, float precision,
+                             int max_iters, int pyr_start, int pyr_step, int pyr_stop, int colors) {
+  ref_engine *e = new ref_engine;
+  e->colors = colors == 3 ? 3 : 1;
+  e->corr = new CorrelationClass(1, e->colors, (interpolationModelEnum)interpolation_model,
+                                 (fittingModelEnum)fitting_model, n_threads, precision, max_iters, pyr_start,
+                                 pyr_step, pyr_stop);
+  e->n_params = ModelClass::get_number_of_model_parameters((fittingModelEnum)fitting_model);
+  return e;
+}
+
 void ref_destroy(ref_engine *e) {
   if (!e) return;
   // CorrelationClass / Pyramid_class destructors free levels >= 1 only.
@@ -95,22 +108,22 @@ void ref_destroy(ref_engine *e) {
   delete e;
 }
 
-static cv::Mat make_mat(const uint8_t *img, int rows, int cols) {
-  cv::Mat m(rows, cols, CV_8U);
-  std::memcpy(m.data, img, (size_t)rows * cols);
+static cv::Mat make_mat(const uint8_t *img, int rows, int cols, int colors = 1) {
+  cv::Mat m(rows, cols, colors == 3 ? CV_8UC3 : CV_8U);
+  std::memcpy(m.data, img, (size_t)rows * cols * colors);
   return m;
 }
 
 void ref_set_und_image(ref_engine *e, const uint8_t *img, int rows, int cols) {
-  e->und = make_mat(img, rows, cols);
+  e->und = make_mat(img, rows, cols, e->colors);
   e->corr->set_undeformed_image(e->und);
 }
 void ref_set_def_image(ref_engine *e, const uint8_t *img, int rows, int cols) {
-  e->def = make_mat(img, rows, cols);
+  e->def = make_mat(img, rows, cols, e->colors);
   e->corr->set_deformed_image(e->def);
 }
 void ref_set_nxt_image(ref_engine *e, const uint8_t *img, int rows, int cols) {
-  e->nxt = make_mat(img, rows, cols);
+  e->nxt = make_mat(img, rows, cols, e->colors);
   e->corr->set_next_image(e->nxt);
 }
 void ref_und_from_def(ref_engine *e) {
@@ -203,7 +216,7 @@ void ref_pyramid_level(ref_engine *e, int which, int level, uint8_t *out,
   *cols = c;
   if (out)
     std::memcpy(out, which == 0 ? p.get_und_ptr(level) : p.get_def_ptr(level),
-                (size_t)r * c);
+                (size_t)r * c * e->colors);
 }
 
 // One evaluation (flush_A_B + apply_model_and_interpolate,

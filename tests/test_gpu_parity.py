@@ -823,3 +823,44 @@ def test_full_size_c4_256_subsets_vs_oracle(eng):
     assert (rel_gpu <= TOL_CHI).mean() >= 0.8
     assert rel_gpu.max() <= max(3e-4, 1.5 * rel_ref.max())
     assert (rel_ref > TOL_CHI).sum() >= 1  # the spread is the algorithm's, not the GPU's: the reference shows it against itself
+
+
+# ---------------------------------------------------------------- three-channel colour images
+
+@pytest.mark.parametrize("iname,interp", [("nearest", engine.IM_NEAREST), ("bilinear", engine.IM_BILINEAR), ("bicubic", engine.IM_BICUBIC)])
+def test_color_images_vs_reference_golden(eng, iname, interp):
+    """number_of_colors = 3 against the unmodified reference's outputs (tests/golden/golden_color_v1.npz, made by
+    make_golden_color.py from oracle/_ref): per-channel pyramid bit-exact, parameters / chi / iterations of the
+    per-colour evaluation loop with the column indexing the reference's coefficient builders execute."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_color_v1.npz"))
+    pyr = tuple(int(v) for v in g["pyramid"])
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_interpolation_model(interp)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramids(g["und"], g["def"], pyramid=pyr)
+    try:
+        assert np.array_equal(eng.pyramid_level(0, 1), g["pyr_und1"]) and np.array_equal(eng.pyramid_level(1, 1), g["pyr_def1"])
+        assert np.array_equal(eng.pyramid_level(1, 0), g["def"])
+        x0, y0, x1, y1 = (int(v) for v in g["rect"])
+        assert eng.resetPolygon(0, x0, y0, x1, y1) == 0
+        eng.setPolygonCenter(0, float(g["center"][0]), float(g["center"][1]))
+        got = eng.correlate(0, np.zeros(6, np.float32))
+        assert got["error_code"] == int(g[f"{iname}/error_code"]) and got["number_of_points"] == int(g[f"{iname}/number_of_points"])
+        d = np.abs(got["params"] - g[f"{iname}/params"])
+        # the bicubic / bilinear colour arithmetic of the reference reads channels 1 and 2 from the wrong columns:
+        # chi is ~7e3 and the fit is ill-posed by construction, so its LM path is as chaotic as nearest's
+        tol = (5e-2, 5e-4) if iname == "nearest" else (2e-3, 2e-5)
+        assert d[:2].max() < tol[0] and d[2:].max() < tol[1], (got["params"], g[f"{iname}/params"])
+        assert abs(got["chi"] - g[f"{iname}/chi"]) < 2e-3 * g[f"{iname}/chi"]
+        if iname == "bicubic":  # one evaluation: the sums themselves, before any LM decision
+            o_A, o_b, o_chi = g["bicubic/eval0/A"], g["bicubic/eval0/b"], g["bicubic/eval0/chi"]
+            A, b, chi, oob = eng.evaluate(0, 0, np.array([0.6, -0.35, 0.002, 0, 0, 0.003], np.float32))
+            assert oob == 0
+            assert np.allclose(np.triu(A), np.triu(o_A), rtol=2e-5, atol=2e-5 * np.abs(o_A).max())
+            assert np.allclose(b, o_b, rtol=2e-5, atol=2e-5 * np.abs(o_b).max())
+            assert abs(chi - o_chi) <= 2e-5 * o_chi
+    finally:
+        eng.set_interpolation_model(engine.IM_BICUBIC)
+        mono = g["und"][:, :, 0].copy()
+        eng.resetImagePyramids(mono, mono, pyramid=(0, 1, 2))  # back to monochrome for the tests that follow

@@ -1,6 +1,8 @@
 """CPU suite: the oracle restatement against the golden vectors of the unmodified reference
 (tests/golden/golden_v1.npz, made by tests/golden/make_golden.py from oracle/_ref) and, where the
 compiled reference is present, against the reference itself -- bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -222,3 +224,33 @@ def test_blob_points_equal_compiled_reference():
         contour = synth.star_polygon(200.0, 180.0, 120.0, n_vertices=40, seed=seed)
         ref = oracle.RefEngine().blob_points(contour)
         assert_bit_equal(oracle.blob_points(contour), ref)
+
+
+# ---------------------------------------------------------------- three-channel colour images
+
+@pytest.fixture(scope="module")
+def golden_color():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_color_v1.npz"))
+
+
+@pytest.mark.parametrize("iname,interp", [("nearest", oracle.IM_NEAREST), ("bilinear", oracle.IM_BILINEAR), ("bicubic", oracle.IM_BICUBIC)])
+def test_color_images_match_reference_golden(golden_color, iname, interp):
+    """number_of_colors = 3: per-channel pyramid and the per-colour loop of interpolation_class.cpp:712-750 with the
+    column indexing the reference's coefficient builders execute (tests/golden/make_golden_color.py)."""
+    g = golden_color
+    o = oracle.OracleEngine(n_threads=3, interp=interp, pyramid=tuple(int(v) for v in g["pyramid"]), colors=3)
+    o.set_image("und", g["und"])
+    o.set_image("def", g["def"])
+    r = o.correlate(np.zeros(6, np.float32), oracle.rect_points(*(int(v) for v in g["rect"])), center=tuple(float(v) for v in g["center"]))
+    assert_bit_equal(r["params"], g[f"{iname}/params"], iname)
+    assert np.float32(r["chi"]) == g[f"{iname}/chi"] and r["iterations"] == int(g[f"{iname}/iterations"])
+    assert r["error_code"] == int(g[f"{iname}/error_code"]) and r["number_of_points"] == int(g[f"{iname}/number_of_points"])
+    if iname == "bicubic":
+        assert np.array_equal(o.pyramid_level(0, 1), g["pyr_und1"]) and np.array_equal(o.pyramid_level(1, 1), g["pyr_def1"])
+        for lv in (1, 0):
+            p = np.array([0.6, -0.35, 0.002, 0, 0, 0.003], np.float32)
+            p[:2] *= np.float32(1.0 / (1 << lv))
+            A, b, chi, err = o.evaluate(lv, p)
+            assert_bit_equal(np.triu(A), np.triu(g[f"bicubic/eval{lv}/A"]))
+            assert_bit_equal(b, g[f"bicubic/eval{lv}/b"])
+            assert np.float32(chi) == g[f"bicubic/eval{lv}/chi"]
