@@ -195,7 +195,7 @@ int encode_level_map(dic_engine *e, CUtensorMap *map, const LevelImage &li, int 
 }
 
 // (Re)shape a pyramid slot for rows x cols, levels 0..stop.
-int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop, int colors = 1) {
+int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop, int colors = 1, cudaStream_t st = nullptr) {
   size_t total = 0;
   size_t off[kMaxLevels];
   int r = rows, c = cols;
@@ -218,8 +218,9 @@ int shape_slot(dic_engine *e, PyramidSlot &s, int rows, int cols, int stop, int 
     s.cap = total;
   }
   // colour: the reference's coefficient builders read up to 5 bytes per column (see sample_def_color); padding
-  // and spare rows are zero so that those reads are deterministic
-  if (colors != 1) CU_TRY(e, cudaMemset(s.base, 0, total));
+  // and spare rows are zero so that those reads are deterministic. Stream-ordered before the upload that follows
+  // on `st` (the legacy default stream is not ordered against the engine's non-blocking streams).
+  if (colors != 1) CU_TRY(e, cudaMemsetAsync(s.base, 0, total, st));
   for (int l = 0; l <= stop; ++l) {
     lev[l].ptr = s.base + off[l];
     const bool same = s.lev[l].ptr == lev[l].ptr && s.lev[l].rows == lev[l].rows && s.lev[l].cols == lev[l].cols &&
@@ -292,7 +293,7 @@ int upload_level0(dic_engine *e, PyramidSlot &s, const void *src, int rows, int 
 int set_image(dic_engine *e, int role, const void *src, int rows, int cols, int spitch,
               bool on_device, cudaStream_t st) {
   PyramidSlot &s = e->pyr[e->role[role]];
-  int rc = shape_slot(e, s, rows, cols, e->stop, e->colors);
+  int rc = shape_slot(e, s, rows, cols, e->stop, e->colors, st);
   if (rc) return rc;
   rc = upload_level0(e, s, src, rows, cols, spitch, on_device, st);
   if (rc) return rc;
@@ -681,23 +682,23 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   for (int l = 0; l <= e->stop; ++l) { maps.def[l] = d.tm_patch[l]; maps.und[l] = u.tm_tile[l]; }
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
   const size_t smem = tiles_dyn_smem(NACC, grid_mode);
-  constexpr int NTB = tile_cta_threads(false); // threads per CTA of the batch form
+  constexpr int NTB = tile_cta_threads(false), NTG = tile_cta_threads(true); // threads per CTA of the batch / grid form
   if (grid_mode) {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, true, 1>;
     static int per_sm_cached[16] = {0}; // per device: attribute + occupancy queried once, not per launch
     int &per_sm = per_sm_cached[e->device & 15];
     if (per_sm == 0) {
       CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+      CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTG, smem));
     }
     if (per_sm < 1) { set_error(e, "gn_solve_tiles_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }
     // one warp per ~2 finest-level tiles at most, never more CTAs than are co-resident
     long nt = e->sectors[first].tl[e->start].n_tiles;
-    int want = (int)std::min<long>((nt + kWarpsPerCta - 1) / kWarpsPerCta, (long)per_sm * e->num_sms);
+    int want = (int)std::min<long>((nt + NTG / 32 - 1) / (NTG / 32), (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;
     void *args[] = {&cfg, &maps, &sectors, &stiles, &guesses, &g0, &results, &first, &one, &work};
-    CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(kThreads), args, smem, e->stream));
+    CU_TRY(e, cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(NTG), args, smem, e->stream));
   } else {
     auto kern1 = gn_solve_tiles_kernel<MODEL, MODE, false, 1>;
     auto kern2 = gn_solve_tiles_kernel<MODEL, MODE, false, 2>;
@@ -951,6 +952,10 @@ int dic_reset_image_pyramids(dic_engine *e, const uint8_t *und, const uint8_t *d
 }
 int dic_reset_image_pyramids_device(dic_engine *e, const void *und, const void *def, const void *nxt,
                                     int rows, int cols, int pitch, int start, int step, int stop) {
+  // the source images were produced on streams this library knows nothing about (e.g. the framework's current
+  // stream) and the engine's own streams are non-blocking: drain the device once so that the copies below cannot
+  // overtake their producer. A set-up call, not a per-frame one.
+  if (e) { cudaSetDevice(e->device); cudaDeviceSynchronize(); }
   return reset_pyramids_common(e, und, def, nxt, rows, cols, pitch, true, start, step, stop);
 }
 
@@ -966,6 +971,17 @@ int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols
   if (rc) return rc;
   CU_TRY(e, cudaStreamSynchronize(e->img_stream));
   return DIC_OK;
+}
+// Enqueue-only form: the H2D copy and the pyramid build of the next image are queued on the image stream and the
+// call returns; dic_make_def_pyramid_from_nxt orders the correlation stream behind them. The caller keeps `nxt`
+// alive and unchanged until then (pinned memory makes the copy truly asynchronous). Lets a frame loop prefetch
+// frame k + 2 without a loader thread (the reference spawns one per frame, manager_class.cpp:1438-1447).
+int dic_reset_next_pyramid_async(dic_engine *e, const uint8_t *nxt, int rows, int cols) {
+  if (!e || !nxt) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  NvtxRange nvtx("dic_reset_next_pyramid_async");
+  CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_rot, 0)); // see dic_reset_next_pyramid
+  return set_image(e, 2, nxt, rows, cols, cols * e->colors, false, e->img_stream);
 }
 int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt, int rows, int cols, int pitch) {
   if (!e || !nxt || e->colors != 1) return DIC_ERROR_BAD_ARGUMENT;

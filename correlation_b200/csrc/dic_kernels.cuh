@@ -287,7 +287,7 @@ __device__ __forceinline__ void rowsplit_send(GridWork *work, const float *tot, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rank = work->rs_rank, world = work->rs_world;
   const int par = seq & 1;
-  for (int r = warp; r < world; r += kThreads / 32) {
+  for (int r = warp; r < world; r += (int)(blockDim.x >> 5)) {
     Mailbox *mb = work->rs_peer[r];
     for (int k = lane; k < NACC; k += 32) mb->sums[par][rank][k] = tot[k];
     __threadfence_system();

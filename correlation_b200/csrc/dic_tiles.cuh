@@ -17,6 +17,7 @@
 // the warp changes strip or the evaluation ends.
 #pragma once
 #include "dic_kernels.cuh"
+#include "dic_f32x2.cuh"
 
 namespace dic {
 
@@ -374,6 +375,110 @@ __device__ __forceinline__ bool parity_slide_step(const float *pw, float xf, flo
   return true;
 }
 
+// ---- parity mode, third form of the inner loop (DIC_PARITY_LOOP == 3, the default): TWO pixels per step in the two
+// halves of packed fp32 pairs (dic_f32x2.cuh). A unit of nr rows (nr even) is walked as two streams of nr / 2 rows,
+// stream A = rows [0, nr/2) in the lo halves, stream B = rows [nr/2, nr) in the hi halves; each stream has its own
+// sliding window (rotating slots, as in the second form), and one step
+//   warps both pixels, floors, tests "did every lane's two windows move down by exactly one row?", reads one new
+//   window row per stream, converts both with ONE set of packed operations, runs the y pass and the 40-term
+//   polynomial once on pairs, and adds both pixels to the lane's moments.
+// Per pixel the operations and their operands are those of the second form, so every w, dw/dx, dw/dy is bit-identical;
+// the issue slots per pixel fall from ~270 to ~140 and the loop becomes bound by the FMA pipe instead.
+template <int MODEL> struct PairWarp {
+  // the reference's left-to-right warp expression (model_class.cpp:150-202; warp_point<MODEL, PARITY>) with the
+  // prefix that does not depend on y evaluated once per strip
+  float kx, p3, q4, p1, p5, cy;
+  float qx, p7x, h8, qy, p10x, h11; // quadratic extension
+  __device__ __forceinline__ void set(const float *p, float xf, float ccx, float ccy) {
+    const float dx = __fsub_rn(xf, ccx);
+    kx = __fadd_rn(__fadd_rn(xf, p[0]), __fmul_rn(p[2], dx));
+    q4 = __fmul_rn(p[4], dx);
+    p1 = p[1]; p3 = p[3]; p5 = p[5]; cy = ccy;
+    if (MODEL == DIC_FM_QUADRATIC) {
+      qx = __fmul_rn(__fmul_rn(__fmul_rn(0.5f, p[6]), dx), dx); p7x = __fmul_rn(p[7], dx); h8 = __fmul_rn(0.5f, p[8]);
+      qy = __fmul_rn(__fmul_rn(__fmul_rn(0.5f, p[9]), dx), dx); p10x = __fmul_rn(p[10], dx); h11 = __fmul_rn(0.5f, p[11]);
+    } else {
+      qx = p7x = h8 = qy = p10x = h11 = 0.f;
+    }
+  }
+  __device__ __forceinline__ void point(f2 Y, f2 &XD, f2 &YD, f2 &DY) const {
+    static_assert(MODEL == DIC_FM_UVUxUyVxVy || MODEL == DIC_FM_QUADRATIC, "tile kernel models");
+    DY = sub2(Y, bc(cy));
+    f2 tx = add2(bc(kx), mul2(bc(p3), DY));
+    f2 ty = add2(add2(add2(Y, bc(p1)), bc(q4)), mul2(bc(p5), DY));
+    if (MODEL == DIC_FM_QUADRATIC) {
+      tx = add2(tx, bc(qx)); tx = add2(tx, mul2(bc(p7x), DY)); tx = add2(tx, mul2(mul2(bc(h8), DY), DY));
+      ty = add2(ty, bc(qy)); ty = add2(ty, mul2(bc(p10x), DY)); ty = add2(ty, mul2(mul2(bc(h11), DY), DY));
+    }
+    XD = tx; YD = ty;
+  }
+};
+
+// window state of the two streams
+struct PairWindow {
+  uint32_t mx_a, mx_b;     // bit patterns of 2^23 + ix of the windows' pixels (floor_magic)
+  uint32_t my_a, my_b;     // bit patterns of 2^23 + iy EXPECTED at the next step
+  const uint8_t *wp_a, *wp_b; // aligned word holding the first byte of the windows' last loaded row, at the trip's start
+  int sh_a, sh_b;          // bit shift of that byte inside the word
+};
+
+template <int MODEL>
+__device__ __forceinline__ void parity_pair_open(const PairWarp<MODEL> &pwp, f2 Y, const uint8_t *patch, int px0, int py0,
+                                                 f2 (&cw)[4][4], PairWindow &win) {
+  f2 XD, YD, DY;
+  pwp.point(Y, XD, YD, DY);
+  const f2 MX = add2_rd(XD, bc(8388608.0f)), MY = add2_rd(YD, bc(8388608.0f));
+  const int ixa = lo_bits(MX) & 0x7fffff, ixb = hi_bits(MX) & 0x7fffff;
+  const int iya = lo_bits(MY) & 0x7fffff, iyb = hi_bits(MY) & 0x7fffff;
+  const int oa = (iya - 1 - py0) * kPatchW + (ixa - 1 - px0), ob = (iyb - 1 - py0) * kPatchW + (ixb - 1 - px0);
+  win.sh_a = (oa & 3) * 8; win.sh_b = (ob & 3) * 8;
+  const uint8_t *ba = patch + (oa & ~3), *bb = patch + (ob & ~3);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t *wa = reinterpret_cast<const uint32_t *>(ba + k * kPatchW);
+    const uint32_t *wb = reinterpret_cast<const uint32_t *>(bb + k * kPatchW);
+    row_coeffs_u8_x2(__funnelshift_r(wa[0], wa[1], win.sh_a), __funnelshift_r(wb[0], wb[1], win.sh_b), cw[k]);
+  }
+  win.wp_a = ba + 2 * kPatchW; win.wp_b = bb + 2 * kPatchW;
+  win.mx_a = lo_bits(MX); win.mx_b = hi_bits(MX);
+  win.my_a = lo_bits(MY); win.my_b = hi_bits(MY); // the window sits one row above: the next step is at this same pixel
+}
+
+// U = reference pixels of the two rows, M = 1 / 0 membership of the two pixels
+template <int MODEL, int S>
+__device__ __forceinline__ bool parity_pair_step(const PairWarp<MODEL> &pwp, f2 Y, f2 (&cw)[4][4], PairWindow &win,
+                                                 f2 U, f2 M, float *mom) {
+  constexpr int NP = model_nparams(MODEL);
+  f2 XD, YD, DY;
+  pwp.point(Y, XD, YD, DY);
+  const f2 MX = add2_rd(XD, bc(8388608.0f)), MY = add2_rd(YD, bc(8388608.0f));
+  const bool slide = lo_bits(MX) == win.mx_a && hi_bits(MX) == win.mx_b && lo_bits(MY) == win.my_a && hi_bits(MY) == win.my_b;
+  if (!__all_sync(0xffffffffu, slide)) return false;
+  win.my_a = lo_bits(MY) + 1u; win.my_b = hi_bits(MY) + 1u;
+  {
+    const uint32_t *wa = reinterpret_cast<const uint32_t *>(win.wp_a + (S + 1) * kPatchW);
+    const uint32_t *wb = reinterpret_cast<const uint32_t *>(win.wp_b + (S + 1) * kPatchW);
+    row_coeffs_u8_x2(__funnelshift_r(wa[0], wa[1], win.sh_a), __funnelshift_r(wb[0], wb[1], win.sh_b), cw[(3 + S) & 3]);
+  }
+  f2 a[4][4];
+#pragma unroll
+  for (int ik = 0; ik < 4; ++ik) {
+    f2 c[4];
+    monomial_from_rows_x2(cw[(0 + S) & 3][ik], cw[(1 + S) & 3][ik], cw[(2 + S) & 3][ik], cw[(3 + S) & 3][ik], c);
+#pragma unroll
+    for (int jk = 0; jk < 4; ++jk) a[jk][ik] = c[jk];
+  }
+  const f2 FX = sub2(MX, bc(8388608.0f)), FY = sub2(MY, bc(8388608.0f));
+  const f2 dxf = add2(sub2(XD, FX), bc(1.f)), dyf = add2(sub2(YD, FY), bc(1.f));
+  f2 W, WX, WY;
+  parity_eval_x2(a, dxf, dyf, W, WX, WY);
+  const f2 V = mul2(sub2(U, W), M);
+  WX = mul2(WX, M); WY = mul2(WY, M);
+  accumulate_moments<NP>(mom, lo(V), lo(WX), lo(WY), lo(DY));
+  accumulate_moments<NP>(mom, hi(V), hi(WX), hi(WY), hi(DY));
+  return true;
+}
+
 #ifndef DIC_PARITY_LOOP
 #define DIC_PARITY_LOOP 2
 #endif
@@ -467,7 +572,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
                                                int quad_begin, int quad_end, WarpStage &st,
                                                float *warp_acc, unsigned int *slow_counter, int *timeout_flag) {
   constexpr int NP = model_nparams(MODEL);
-  constexpr int GRAN = MODE == DIC_MODE_PARITY ? 1 : 4;
+  constexpr int GRAN = MODE == DIC_MODE_PARITY ? (DIC_PARITY_LOOP == 3 ? 2 : 1) : 4;
   using M = Mom<NP>;
   const int lane = threadIdx.x & 31;
   if (__shfl_sync(0xffffffffu, *(volatile int *)timeout_flag, 0)) return; // a copy was lost earlier in this launch: the staging state is void (warp-uniform test)
@@ -492,6 +597,8 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   float X = 0.f, xf = 0.f;
   LaneWarp<NP> lw;
   lw.set(p, 0.f, 0.f);
+  PairWarp<MODEL> pwp;
+  pwp.set(p, 0.f, ccx, ccy);
 
   // rows [r0, r1) of tile t that belong to this warp's quad range
   const int t_first = quad_begin >> 2, t_last = (quad_end - 1) >> 2;
@@ -523,6 +630,7 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
       xf = (float)(x0 + lane);
       X = __fsub_rn(xf, ccx);
       lw.set(p, xf, X);
+      if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 3) pwp.set(p, xf, ccx, ccy);
     }
     const uint32_t colmask = q.colmask;
     if (q.staged) {
@@ -546,7 +654,36 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
       // 2.4x longer and the unrolled body overflowed the instruction cache (10 % no-instruction stalls).
 #define DIC_SHIFT()                                                                                  \
   _Pragma("unroll") for (int k_ = 0; k_ < 4; ++k_) { cw[0][k_] = cw[1][k_]; cw[1][k_] = cw[2][k_]; cw[2][k_] = cw[3][k_]; }
-      if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 2) {
+      if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 3) {
+        // two streams of nr / 2 rows (GRAN = 2 keeps nr even); one code path for full and partial units
+        const int half = nr >> 1;
+        int r = 0;
+        PairWindow win;
+#define DIC_PSTEP(SV)                                                                                        \
+  {                                                                                                          \
+    const f2 U = pk((float)up_a[(SV) * kUndW], (float)up_b[(SV) * kUndW]);                                      \
+    const f2 Mk = pk(((cm_a >> (SV)) & 1u) ? 1.f : 0.f, ((cm_b >> (SV)) & 1u) ? 1.f : 0.f);                      \
+    if (!parity_pair_step<MODEL, SV>(pwp, Yp, cw2, win, U, Mk, mom)) break;                                  \
+    Yp = add2(Yp, bc(1.f));                                                                                  \
+    if (++r >= half) break;                                                                                  \
+  }
+#pragma unroll 1
+        while (r < half) {
+          f2 cw2[4][4];
+          f2 Yp = pk((float)(y0 + r), (float)(y0 + half + r));
+          const uint8_t *up_a = ucol + r * kUndW, *up_b = ucol + (half + r) * kUndW;
+          uint32_t cm_a = colmask >> r, cm_b = colmask >> (half + r);
+          parity_pair_open<MODEL>(pwp, Yp, patch, px0, py0, cw2, win);
+#pragma unroll 1
+          while (true) {
+            DIC_PSTEP(0) DIC_PSTEP(1) DIC_PSTEP(2) DIC_PSTEP(3)
+            win.wp_a += 4 * kPatchW; win.wp_b += 4 * kPatchW;
+            up_a += 4 * kUndW; up_b += 4 * kUndW;
+            cm_a >>= 4; cm_b >>= 4;
+          }
+        }
+#undef DIC_PSTEP
+      } else if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 2) {
         // one code path for full and partial units (three selects per pixel buy half the instruction footprint)
         const uint8_t *wp = patch;
         int wsh = 0;
@@ -643,8 +780,17 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float 
 #ifndef DIC_BATCH_THREADS
 #define DIC_BATCH_THREADS 128
 #endif
-__host__ __device__ constexpr int tile_cta_threads(bool grid) { return grid ? kThreads : DIC_BATCH_THREADS; }
-__host__ __device__ constexpr int tile_ctas_for(int model, bool grid) { return tile_ctas_per_sm(model) * kThreads / tile_cta_threads(grid); }
+#ifndef DIC_GRID_THREADS
+#define DIC_GRID_THREADS kThreads
+#endif
+#ifndef DIC_BATCH_CTAS
+#define DIC_BATCH_CTAS (tile_ctas_per_sm(model) * kThreads / DIC_BATCH_THREADS)
+#endif
+#ifndef DIC_GRID_CTAS
+#define DIC_GRID_CTAS (tile_ctas_per_sm(model) * kThreads / DIC_GRID_THREADS)
+#endif
+__host__ __device__ constexpr int tile_cta_threads(bool grid) { return grid ? DIC_GRID_THREADS : DIC_BATCH_THREADS; }
+__host__ __device__ constexpr int tile_ctas_for(int model, bool grid) { return grid ? DIC_GRID_CTAS : DIC_BATCH_CTAS; }
 
 template <int MODEL, int MODE, bool GRID, int CL>
 __global__ void __launch_bounds__(tile_cta_threads(GRID), tile_ctas_for(MODEL, GRID))

@@ -65,7 +65,7 @@ EXPORTS = [
     "dic_device_count", "dic_create", "dic_destroy", "dic_last_error", "dic_set_max_iters",
     "dic_set_precision", "dic_set_fitting_model", "dic_set_interpolation_model",
     "dic_set_arith_mode", "dic_set_center_mode", "dic_set_kernel_variant", "dic_reset_image_pyramids",
-    "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_device",
+    "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_async", "dic_reset_next_pyramid_device",
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
     "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_rect_grid", "dic_set_cluster_mode", "dic_last_cluster_size", "dic_reset_polygon_points", "dic_set_polygon_center",
@@ -103,6 +103,7 @@ def load_library():
         "dic_reset_image_pyramids": (I, [P, P, P, P, I, I, I, I, I, I]),
         "dic_reset_image_pyramids_device": (I, [P, P, P, P, I, I, I, I, I, I]),
         "dic_reset_next_pyramid": (I, [P, P, I, I]),
+        "dic_reset_next_pyramid_async": (I, [P, P, I, I]),
         "dic_reset_next_pyramid_device": (I, [P, P, I, I, I]),
         "dic_reset_def_pyramid": (I, [P, P, I, I]),
         "dic_reset_def_pyramid_device": (I, [P, P, I, I, I]),

@@ -71,6 +71,11 @@ public:
     need_engine();
     return (errorEnum)dic_reset_next_pyramid(engine_, nxt, rows, cols);
   }
+  // extension: enqueue-only prefetch (no loader thread); nxt stays alive until makeDefPyramidFromNxt
+  errorEnum resetNextPyramidAsync(const uint8_t *nxt, int rows, int cols) {
+    need_engine();
+    return (errorEnum)dic_reset_next_pyramid_async(engine_, nxt, rows, cols);
+  }
 #ifdef DIC_WITH_OPENCV
   void resetImagePyramids(const std::string undPath, const std::string defPath, const std::string nxtPath,
                           colorEnum color_mode, const int start, const int step, const int stop) {

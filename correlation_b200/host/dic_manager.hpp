@@ -44,6 +44,10 @@ struct Config {
   float global_initial_guess[DIC_MAX_PARAMS] = {0};
   int arith_mode = DIC_MODE_PARITY;
   bool batch_sectors = false; // extension: all sectors of a frame in one launch
+  // extension: prefetch the next frame by ENQUEUEING its upload + pyramid on the engine's image stream instead of
+  // running them on a per-frame loader thread (manager_class.cpp:1438-1447). Requires frame buffers that stay
+  // alive and unchanged for the run (true for perform_multiframe_correlation's raw-buffer frames).
+  bool async_next_image = true;
 };
 
 // the part of frame_results (domains.hpp:59-108) the GPU path reads or reports
@@ -393,14 +397,17 @@ public:
       }
       std::future<errorEnum> loader; // :1438-1447: next image upload + pyramid while this frame correlates
       const bool prefetch = frame + 2 < (int)frames.size() && frame > 0;
-      if (prefetch)
+      errorEnum enqueue_rc = error_none;
+      if (prefetch && cfg_.async_next_image)
+        enqueue_rc = cuda_.resetNextPyramidAsync(frames[frame + 2], rows, cols); // stream-ordered, no thread
+      else if (prefetch)
         loader = std::async(std::launch::async, [&, frame] { return cuda_.resetNextPyramid(frames[frame + 2], rows, cols); });
       switch (cfg_.domain_type) {
       case domain_rectangular: error = frame_rectangular(frame); break;
       case domain_annular: error = frame_annular(frame); break;
       default: error = frame_blob(frame); break;
       }
-      if (prefetch && loader.get() != error_none) error = error_ = true; // :1469-1474 (error_multiThread)
+      if (prefetch && (cfg_.async_next_image ? enqueue_rc : loader.get()) != error_none) error = error_ = true; // :1469-1474 (error_multiThread)
       addFrameToReport(frame, name(cfg_.referenceImage == refImage_First ? 0 : frame), name(frame + 1));
       frames_done_ = frame + 1;
       if (error && cfg_.error_handling_mode == errorMode_stopAll) break; // :1493

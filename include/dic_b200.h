@@ -118,12 +118,17 @@ int dic_set_kernel_variant(dic_engine *e, int variant);
 int dic_reset_image_pyramids(dic_engine *e, const uint8_t *und, const uint8_t *def,
                              const uint8_t *nxt, int rows, int cols, int channels,
                              int pyramid_start, int pyramid_step, int pyramid_stop);
-/* same, but the level-0 images already live in device memory (pitch in bytes) */
+/* same, but the level-0 images already live in device memory (pitch in bytes). The call drains the device first
+ * (the images may have been produced on any stream); the per-frame _device variants below do NOT: the caller
+ * orders the producer of nxt_dev / def_dev before the call (stream or event synchronisation). */
 int dic_reset_image_pyramids_device(dic_engine *e, const void *und_dev, const void *def_dev,
                                     const void *nxt_dev, int rows, int cols, int pitch,
                                     int pyramid_start, int pyramid_step, int pyramid_stop);
 /* ---- CudaClass::resetNextPyramid(nxtPath) (cuda_class.cu:498-510) */
 int dic_reset_next_pyramid(dic_engine *e, const uint8_t *nxt, int rows, int cols);
+/* extension: enqueue only -- returns once the copy and the pyramid build are queued on the image stream; `nxt` must
+ * stay alive and unchanged until dic_make_def_pyramid_from_nxt (which orders the solve behind them) */
+int dic_reset_next_pyramid_async(dic_engine *e, const uint8_t *nxt, int rows, int cols);
 int dic_reset_next_pyramid_device(dic_engine *e, const void *nxt_dev, int rows, int cols, int pitch);
 /* replace only the deformed image (host convenience for frame loops without a nxt slot) */
 int dic_reset_def_pyramid(dic_engine *e, const uint8_t *def, int rows, int cols);

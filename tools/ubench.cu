@@ -7,6 +7,16 @@
 #define ITERS 4096
 #define UNROLL 16
 
+__device__ __forceinline__ void fadd2(float2 &d, float2 a) {
+  unsigned long long da = *reinterpret_cast<unsigned long long *>(&d), aa = *reinterpret_cast<unsigned long long *>(&a);
+  asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(da) : "l"(aa));
+  d = *reinterpret_cast<float2 *>(&da);
+}
+__device__ __forceinline__ void fmul2(float2 &d, float2 a) {
+  unsigned long long da = *reinterpret_cast<unsigned long long *>(&d), aa = *reinterpret_cast<unsigned long long *>(&a);
+  asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(da) : "l"(aa));
+  d = *reinterpret_cast<float2 *>(&da);
+}
 __device__ __forceinline__ void ffma2(float2 &d, float2 a, float2 b) {
   unsigned long long da, aa, bb;
   aa = *reinterpret_cast<unsigned long long *>(&a);
@@ -36,6 +46,12 @@ template <int MODE> __global__ void k(float *out, float a, float b, long long *c
       if (MODE == 4) acc[i] += (float)(__float_as_uint(acc[i]) & 0xff);
       if (MODE == 5) acc[i] += sm[(threadIdx.x + i * 32 + __float_as_uint(acc[i]) ) & 1023];
       if (MODE == 6) acc[i] = __fadd_rn(acc[i], a);
+      if (MODE == 7) fadd2(acc2[i], make_float2(a, b));
+      if (MODE == 8) fmul2(acc2[i], make_float2(a, b));
+      if (MODE == 9) { if (i & 1) fadd2(acc2[i], make_float2(a, b)); else acc[i] = __fadd_rn(acc[i], a); }          // 1 packed : 1 scalar
+      if (MODE == 10) { fadd2(acc2[i], make_float2(a, b)); iacc[i] = iacc[i] + (iacc[i] >> 3) + 7u; }                // packed + ALU (IADD3 / SHF)
+      if (MODE == 11) { if ((i & 3) == 3) acc[i] = __fadd_rn(acc[i], a); else fmul2(acc2[i], make_float2(a, b)); }  // 3 packed : 1 scalar
+      if (MODE == 12) { fmul2(acc2[i], make_float2(a, b)); iacc[i] = __byte_perm(iacc[i], 0x4B000000u, 0x7650u | (iacc[i] & 3)); }
     }
   }
   long long t1 = clock64();
@@ -68,6 +84,12 @@ int main() {
   run<4>("I2F + LOP + FADD", 3);
   run<5>("LDS.32 + addr + FADD", 4);
   run<6>("FADD", 1);
+  run<7>("FADD2 (add.rn.f32x2)", 1);
+  run<8>("FMUL2 (mul.rn.f32x2)", 1);
+  run<9>("FADD2 : FADD 1:1", 1);
+  run<10>("FADD2 + SHF + IADD3", 3);
+  run<11>("FMUL2 : FADD 3:1", 1);
+  run<12>("FMUL2 + LOP + PRMT", 3);
   cudaError_t e = cudaGetLastError();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
