@@ -694,7 +694,26 @@ def single_domain_parity(run, last, threads):
     blk = parity_block(last["params"], last["chi"], last["iterations"], dres["params"], dres["chi"], dres["iterations"],
                        gpu_evals=[last["evaluations"][:8]], want_evals=[dres["evaluations"][:8]])
     blk["evaluations"] = [last["evaluations"][: w["pyramid"][2] + 1], dres["evaluations"][: w["pyramid"][2] + 1]]
-    return {"vs_oracle": blk}
+    out = {"vs_oracle": blk}
+    # the reference's own arithmetic (fp32 accumulators in NUMBER_OF_THREADS = 20 chunks, defines.hpp:10) against the
+    # same fp64-accumulator oracle: how far the CPU engine sits from exact sums on this domain
+    try:
+        orf = oracle.OracleEngine(model=oracle.FM_QUAD if w["model"] == "quad" else oracle.FM_AFFINE, n_threads=20,
+                                  pyramid=w["pyramid"], accum_double=False)
+        orf.set_image("und", und)
+        orf.set_image("def", dfm)
+        if d[0] == "rect":
+            rres = orf.correlate(np.zeros(n_par, np.float32), oracle.rect_points(*d[1:]), center=((d[1] + d[3]) / 2.0, (d[2] + d[4]) / 2.0))
+        else:
+            rres = orf.correlate(np.zeros(n_par, np.float32), oracle.annulus_points(*d[1:]))
+        sp = parity_block(rres["params"], rres["chi"], rres["iterations"], dres["params"], dres["chi"], dres["iterations"],
+                          gpu_evals=[rres["evaluations"][:8]], want_evals=[dres["evaluations"][:8]])
+        sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same domain"
+        out["reference_self_spread"] = sp
+        out["chi_within_reference_self_spread"] = bool(blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], sp["max_rel_dchi"]))
+    except Exception as ex:
+        out["reference_self_spread"] = {"error": repr(ex)}
+    return out
 
 
 def other_workload_c2(args, peaks):
@@ -776,6 +795,27 @@ def other_workload_c5(args, dist, rank, world, local_rank, peaks):
 
 # ------------------------------------------------------------------------------ main
 
+def bind_near_gpu(local_rank):
+    """Pin this rank's threads to the CPU cores next to its GPU (nvmlDeviceGetCpuAffinity) BEFORE any pinned buffer is
+    allocated, so that the buffers land on that socket's memory (first touch). With eight ranks streaming images out of
+    host memory at once, round 1 measured one shared ceiling of ~165 GB/s when every rank ran wherever the scheduler
+    put it. Returns a description for the bench line, or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(local_rank))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus or len(cpus) == len(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cores next to the GPU (nvmlDeviceGetCpuAffinity), set before the pinned buffers are allocated"
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -853,9 +893,12 @@ def main():
         pass
     if w["domain"][0] == "rowsplit" and world == 1 and not args.no_others:
         args.no_others = True
+    affinity = bind_near_gpu(local_rank) if world > 1 else None
     run = Run(args, w, dist, rank, world, local_rank)
     m = run.measure(args.steps, args.warmup)
     line = record_for(args, run, m, args.steps, peaks) if rank == 0 else None
+    if rank == 0 and affinity:
+        line["config"]["cpu_affinity"] = affinity
     d = w["domain"]
 
     # ---- parity (top level of the line)

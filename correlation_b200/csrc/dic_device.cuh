@@ -72,6 +72,8 @@ struct GridWork {
   int abort;               // set when a grid-barrier wait timed out (never expected)
   unsigned int slow_units; // units of the last launch that took the per-pixel (non-staged) path
   int img_error;           // set by the pyramid kernel when a TMA transfer never landed (sticky until read by the host)
+  unsigned int next_sector;    // batch form: ticket counter of the sector queue ...
+  unsigned int batch_departed; // ... and the CTAs that have left (the last one zeroes both)
   double acc[3][96];       // grid-wide sums of evaluations e % 3 (fp64 atomics)
   // row-split of one domain over several GPUs: CTA 0 of every rank adds the rank's sums to
   // every peer's mailbox over NVLink, then all ranks add the rows in rank order (bitwise identical)
@@ -93,6 +95,7 @@ struct SolveSettings {
   int start, step, stop;
   int max_iters;
   float precision;
+  unsigned int opaque_zero; // always 0; a value the compiler cannot know (dic_f32x2.cuh, mul2_sep)
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -180,14 +183,14 @@ __device__ __forceinline__ void hermite_to_monomial(float f1, float f2, float d1
   c[3] = 2.f * f1 - 2.f * f2 + d1 + d2;
 }
 
-// hermite_to_monomial(p1, p2, (p2 - p0) / 2, (p3 - p1) / 2) written with differences: 13 operations
-// instead of 20, identical results because every intermediate is exact (see above).
+// hermite_to_monomial(p1, p2, (p2 - p0) / 2, (p3 - p1) / 2) written with differences: 11 operations
+// instead of 20 (c0 and c2 from the cubic's value and slope at s = 1), identical results because every intermediate is exact (see above).
 __device__ __forceinline__ void monomial_from_samples(float p0, float p1, float p2, float p3, float c[4]) {
   const float a = p1 - p2, b = p3 - p0, d = p1 - p0;
-  c[3] = 0.5f * b + 1.5f * a;
-  c[0] = p0 - b - 3.f * a;
-  c[1] = 2.5f * b + 8.f * a + 1.5f * d;
-  c[2] = -2.f * b - 6.5f * a - 0.5f * d;
+  c[3] = fmaf(1.5f, a, 0.5f * b);
+  c[0] = fmaf(-2.f, c[3], p0);                  // p0 - b - 3 a
+  c[1] = fmaf(1.5f, d, fmaf(8.f, a, 2.5f * b));
+  c[2] = (c[3] + d) - c[1];                     // -2 b - 6.5 a - 0.5 d
 }
 
 // The 40 terms of interpolation_class.cpp:108-126 in the reference's order, unfused mul / add.

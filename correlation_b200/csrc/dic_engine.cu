@@ -681,8 +681,8 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   memset(&maps, 0, sizeof(maps));
   for (int l = 0; l <= e->stop; ++l) { maps.def[l] = d.tm_patch[l]; maps.und[l] = u.tm_tile[l]; }
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
-  const size_t smem = tiles_dyn_smem(NACC, grid_mode);
-  constexpr int NTB = tile_cta_threads(false), NTG = tile_cta_threads(true); // threads per CTA of the batch / grid form
+  constexpr int NTB = tile_cta_threads(MODEL, false), NTG = tile_cta_threads(MODEL, true); // threads per CTA of the batch / grid form
+  const size_t smem = tiles_dyn_smem(NACC, grid_mode ? NTG : NTB);
   if (grid_mode) {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, true, 1>;
     static int per_sm_cached[16] = {0}; // per device: attribute + occupancy queried once, not per launch
@@ -692,8 +692,8 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
       CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTG, smem));
     }
     if (per_sm < 1) { set_error(e, "gn_solve_tiles_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }
-    // one warp per ~2 finest-level tiles at most, never more CTAs than are co-resident
-    long nt = e->sectors[first].tl[e->start].n_tiles;
+    // at least four quads (16 rows of a strip) per warp at the finest level, never more CTAs than are co-resident
+    long nt = (long)e->sectors[first].tl[e->start].n_tiles * kQuadsPerTile / 4;
     int want = (int)std::min<long>((nt + NTG / 32 - 1) / (NTG / 32), (long)per_sm * e->num_sms);
     int grid = std::max(1, std::min(want, e->max_grid));
     int one = 1;

@@ -19,6 +19,16 @@
 #include "dic_kernels.cuh"
 #include "dic_f32x2.cuh"
 
+#ifndef DIC_PAIR_LATE_BRANCH
+#define DIC_PAIR_LATE_BRANCH 0 // measured: the late branch costs registers and is slower (c2 +9 %, c5 +10 %)
+#endif
+#ifndef DIC_BATCH_QUEUE
+#define DIC_BATCH_QUEUE 1
+#endif
+#ifndef DIC_BATCH_TIMELINE
+#define DIC_BATCH_TIMELINE 0 // diagnostics only
+#endif
+
 namespace dic {
 
 // Resident CTAs per SM the tile kernel is compiled for. 2 CTAs = 16 warps per SM at 128 registers.
@@ -28,15 +38,26 @@ namespace dic {
 #define DIC_TILE_CTAS_AFFINE 2
 #endif
 __host__ __device__ constexpr int tile_ctas_per_sm(int model) { return model == DIC_FM_QUADRATIC ? 2 : DIC_TILE_CTAS_AFFINE; }
-constexpr int kTileW = 32, kTileH = 16;
+#ifndef DIC_TILE_H
+#define DIC_TILE_H 32
+#endif
+// 32 x kTileH pixels per tile. 32 rows (16 in round 1): a unit -- the rows of one tile a warp walks between two
+// plan / stage / window-open sequences -- is then up to 32 rows, i.e. 16 steps of the two-stream parity loop instead
+// of 8; the per-unit work (~330 instructions and one L2 round trip for the tile record) was 15 % of the kernel's
+// instructions with 16-row tiles.
+constexpr int kTileW = 32, kTileH = DIC_TILE_H;
+constexpr int kQuadsPerTile = kTileH / 4;
+static_assert(kTileH == 16 || kTileH == 32, "a column of the membership mask is one 32-bit word");
+__host__ __device__ constexpr uint32_t low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 // Per-warp staging, filled by TMA (cp.async.bulk.tensor.2d) one unit ahead of the arithmetic:
 //   the deformed-image footprint of a unit as u8, kPatchW x kPatchH bytes,
 //   the reference-image pixels of the unit's tile, kUndW x kTileH bytes.
 // The innermost TMA coordinate must be a multiple of 16 bytes (measured on B200: any other value
 // faults with "illegal instruction"), so both boxes start at x & ~15 and carry 15 spare columns:
-// 64 = 15 + 32 + 3 halo + 1 + 13 for strain / rotation across the unit; 48 = 15 + 32 + 1.
+// 64 = 15 + 32 + 3 halo + 1 + 13 for strain / rotation across the unit; 48 = 15 + 32 + 1. Rows: kTileH + 3 halo + 5 (9)
+// for strain / rotation.
 // Two buffers of each per warp and one mbarrier per buffer.
-constexpr int kPatchW = 64, kPatchH = 24, kUndW = 48;
+constexpr int kPatchW = 64, kPatchH = kTileH == 32 ? 44 : 24, kUndW = 48;
 constexpr int kPatchBytes = kPatchW * kPatchH, kUndBytes = kUndW * kTileH;
 constexpr int kStageBytes = kPatchBytes + kUndBytes;          // one buffer: 2304 B = 18 x 128
 constexpr int kWarpStageBytes = 2 * kStageBytes;              // per warp
@@ -59,7 +80,7 @@ struct WarpStage {
 struct Tile {
   int x0, y0;             // level coordinates of the tile's first pixel
   uint32_t rows[kTileH];  // bit l of rows[r] <=> pixel (x0 + l, y0 + r) belongs to the domain
-  uint16_t cols[kTileW];  // the same membership transposed: bit r of cols[l]
+  uint32_t cols[kTileW];  // the same membership transposed: bit r of cols[l]
   uint32_t full_rows;     // bit r set <=> rows[r] == 0xffffffff
   uint32_t pad;
 };
@@ -75,7 +96,7 @@ __device__ __forceinline__ void tile_finish(Tile &t) {
     uint32_t c = 0;
 #pragma unroll
     for (int r = 0; r < kTileH; ++r) c |= ((t.rows[r] >> l) & 1u) << r;
-    t.cols[l] = (uint16_t)c;
+    t.cols[l] = c;
   }
 }
 
@@ -250,11 +271,12 @@ __device__ __forceinline__ void row_coeffs_u8(uint32_t win, float c[4]) {
   const float f2 = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7652u));
   const float f3 = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7653u));
   if (MODE == DIC_MODE_PARITY) {
+    // 12 exact operations: c0 = p0 - 2 c3 and c2 = c3 + d - c1 (value and slope of the cubic at s = 1)
     const float a = f1 - f2, b = f3 - f0, d = f1 - f0, p0 = f0 - 8388608.0f;
-    c[3] = 0.5f * b + 1.5f * a;
-    c[0] = p0 - b - 3.f * a;
-    c[1] = 2.5f * b + 8.f * a + 1.5f * d;
-    c[2] = -2.f * b - 6.5f * a - 0.5f * d;
+    c[3] = fmaf(1.5f, a, 0.5f * b);
+    c[0] = fmaf(-2.f, c[3], p0);
+    c[1] = fmaf(1.5f, d, fmaf(8.f, a, 2.5f * b));
+    c[2] = (c[3] + d) - c[1];
   } else {
     const float d0 = f0 - f1, d2 = f2 - f1, d3 = f3 - f1;
     c[0] = f1 - 8388608.0f;
@@ -375,15 +397,16 @@ __device__ __forceinline__ bool parity_slide_step(const float *pw, float xf, flo
   return true;
 }
 
-// ---- parity mode, third form of the inner loop (DIC_PARITY_LOOP == 3, the default): TWO pixels per step in the two
+// ---- parity mode, third form of the inner loop (DIC_PARITY_LOOP == 3, an option): TWO pixels per step in the two
 // halves of packed fp32 pairs (dic_f32x2.cuh). A unit of nr rows (nr even) is walked as two streams of nr / 2 rows,
 // stream A = rows [0, nr/2) in the lo halves, stream B = rows [nr/2, nr) in the hi halves; each stream has its own
 // sliding window (rotating slots, as in the second form), and one step
 //   warps both pixels, floors, tests "did every lane's two windows move down by exactly one row?", reads one new
 //   window row per stream, converts both with ONE set of packed operations, runs the y pass and the 40-term
 //   polynomial once on pairs, and adds both pixels to the lane's moments.
-// Per pixel the operations and their operands are those of the second form, so every w, dw/dx, dw/dy is bit-identical;
-// the issue slots per pixel fall from ~270 to ~140 and the loop becomes bound by the FMA pipe instead.
+// Per pixel the operations and their operands are those of the second form, so every w, dw/dx, dw/dy is bit-identical
+// (once the products that feed additions are protected from ptxas's contraction, see mul2_sep); the issue slots per
+// pixel fall from ~263 to ~166 and the loop becomes bound by the FMA pipe instead -- which is why it does not win.
 template <int MODEL> struct PairWarp {
   // the reference's left-to-right warp expression (model_class.cpp:150-202; warp_point<MODEL, PARITY>) with the
   // prefix that does not depend on y evaluated once per strip
@@ -401,14 +424,15 @@ template <int MODEL> struct PairWarp {
       qx = p7x = h8 = qy = p10x = h11 = 0.f;
     }
   }
-  __device__ __forceinline__ void point(f2 Y, f2 &XD, f2 &YD, f2 &DY) const {
+  // zero: see mul2_sep -- every product here is rounded before it is added, as in the reference's expression
+  __device__ __forceinline__ void point(f2 Y, uint32_t zero, f2 &XD, f2 &YD, f2 &DY) const {
     static_assert(MODEL == DIC_FM_UVUxUyVxVy || MODEL == DIC_FM_QUADRATIC, "tile kernel models");
     DY = sub2(Y, bc(cy));
-    f2 tx = add2(bc(kx), mul2(bc(p3), DY));
-    f2 ty = add2(add2(add2(Y, bc(p1)), bc(q4)), mul2(bc(p5), DY));
+    f2 tx = add2(bc(kx), mul2_sep(bc(p3), DY, zero));
+    f2 ty = add2(add2(add2(Y, bc(p1)), bc(q4)), mul2_sep(bc(p5), DY, zero));
     if (MODEL == DIC_FM_QUADRATIC) {
-      tx = add2(tx, bc(qx)); tx = add2(tx, mul2(bc(p7x), DY)); tx = add2(tx, mul2(mul2(bc(h8), DY), DY));
-      ty = add2(ty, bc(qy)); ty = add2(ty, mul2(bc(p10x), DY)); ty = add2(ty, mul2(mul2(bc(h11), DY), DY));
+      tx = add2(tx, bc(qx)); tx = add2(tx, mul2_sep(bc(p7x), DY, zero)); tx = add2(tx, mul2_sep(mul2(bc(h8), DY), DY, zero));
+      ty = add2(ty, bc(qy)); ty = add2(ty, mul2_sep(bc(p10x), DY, zero)); ty = add2(ty, mul2_sep(mul2(bc(h11), DY), DY, zero));
     }
     XD = tx; YD = ty;
   }
@@ -423,10 +447,10 @@ struct PairWindow {
 };
 
 template <int MODEL>
-__device__ __forceinline__ void parity_pair_open(const PairWarp<MODEL> &pwp, f2 Y, const uint8_t *patch, int px0, int py0,
-                                                 f2 (&cw)[4][4], PairWindow &win) {
+__device__ __forceinline__ void parity_pair_open(const PairWarp<MODEL> &pwp, f2 Y, uint32_t zero, const uint8_t *patch,
+                                                 int px0, int py0, f2 (&cw)[4][4], PairWindow &win) {
   f2 XD, YD, DY;
-  pwp.point(Y, XD, YD, DY);
+  pwp.point(Y, zero, XD, YD, DY);
   const f2 MX = add2_rd(XD, bc(8388608.0f)), MY = add2_rd(YD, bc(8388608.0f));
   const int ixa = lo_bits(MX) & 0x7fffff, ixb = hi_bits(MX) & 0x7fffff;
   const int iya = lo_bits(MY) & 0x7fffff, iyb = hi_bits(MY) & 0x7fffff;
@@ -446,15 +470,20 @@ __device__ __forceinline__ void parity_pair_open(const PairWarp<MODEL> &pwp, f2 
 
 // U = reference pixels of the two rows, M = 1 / 0 membership of the two pixels
 template <int MODEL, int S>
-__device__ __forceinline__ bool parity_pair_step(const PairWarp<MODEL> &pwp, f2 Y, f2 (&cw)[4][4], PairWindow &win,
-                                                 f2 U, f2 M, float *mom) {
+__device__ __forceinline__ bool parity_pair_step(const PairWarp<MODEL> &pwp, f2 Y, uint32_t zero, f2 (&cw)[4][4],
+                                                 PairWindow &win, f2 U, f2 M, float *mom) {
   constexpr int NP = model_nparams(MODEL);
   f2 XD, YD, DY;
-  pwp.point(Y, XD, YD, DY);
+  pwp.point(Y, zero, XD, YD, DY);
   const f2 MX = add2_rd(XD, bc(8388608.0f)), MY = add2_rd(YD, bc(8388608.0f));
   const bool slide = lo_bits(MX) == win.mx_a && hi_bits(MX) == win.mx_b && lo_bits(MY) == win.my_a && hi_bits(MY) == win.my_b;
-  if (!__all_sync(0xffffffffu, slide)) return false;
-  win.my_a = lo_bits(MY) + 1u; win.my_b = hi_bits(MY) + 1u;
+  // The vote is taken here but (DIC_PAIR_LATE_BRANCH) acted upon only before the moments are touched: everything in
+  // between is register arithmetic on a scratch row, so a failed step has no side effect and the ~60 cycles of
+  // compare -> vote -> branch latency overlap the polynomial instead of preceding it.
+  const bool ok = __all_sync(0xffffffffu, slide);
+#if !DIC_PAIR_LATE_BRANCH
+  if (!ok) return false;
+#endif
   {
     const uint32_t *wa = reinterpret_cast<const uint32_t *>(win.wp_a + (S + 1) * kPatchW);
     const uint32_t *wb = reinterpret_cast<const uint32_t *>(win.wp_b + (S + 1) * kPatchW);
@@ -471,16 +500,28 @@ __device__ __forceinline__ bool parity_pair_step(const PairWarp<MODEL> &pwp, f2 
   const f2 FX = sub2(MX, bc(8388608.0f)), FY = sub2(MY, bc(8388608.0f));
   const f2 dxf = add2(sub2(XD, FX), bc(1.f)), dyf = add2(sub2(YD, FY), bc(1.f));
   f2 W, WX, WY;
-  parity_eval_x2(a, dxf, dyf, W, WX, WY);
+  parity_eval_x2(a, dxf, dyf, zero, W, WX, WY);
   const f2 V = mul2(sub2(U, W), M);
   WX = mul2(WX, M); WY = mul2(WY, M);
+#if DIC_PAIR_LATE_BRANCH
+  if (!ok) return false;
+#endif
+  win.my_a = lo_bits(MY) + 1u; win.my_b = hi_bits(MY) + 1u;
   accumulate_moments<NP>(mom, lo(V), lo(WX), lo(WY), lo(DY));
   accumulate_moments<NP>(mom, hi(V), hi(WX), hi(WY), hi(DY));
   return true;
 }
 
+// Default: the second form. Measured on B200 (c4, 4096 subsets, 32-row tiles, ticket queue): second form 2.20 ms,
+// third form 2.42 ms. The packed form halves the issue slots (166 instead of 263 per pixel) but not the FMA-pipe
+// passes (206 instead of 210 per pixel: a packed instruction is two passes), the pipe is what bounds the unfused
+// reference arithmetic, and the packed form pays 33 XORs per step to keep ptxas from contracting its products
+// (dic_f32x2.cuh) plus spills at the 128-register budget. Kept as a compile-time option (-DDIC_PARITY_LOOP=3).
 #ifndef DIC_PARITY_LOOP
 #define DIC_PARITY_LOOP 2
+#endif
+#ifndef DIC_PAIR_UNROLL
+#define DIC_PAIR_UNROLL 1
 #endif
 
 // What a warp needs to know about a work unit before touching its pixels. A unit is a run of consecutive
@@ -501,16 +542,16 @@ __device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int t, int r0
   const int lane = threadIdx.x & 31;
   UnitPlan q;
   const Tile *tp = tl.tiles + t;
-  uint32_t col = ((uint32_t)__ldg(&tp->cols[lane]) >> r0) & ((1u << (r1 - r0)) - 1u);
+  uint32_t col = (__ldg(&tp->cols[lane]) >> r0) & low_bits(r1 - r0);
   const uint32_t any = __reduce_or_sync(0xffffffffu, col); // rows of the range some lane owns
   if (any == 0u) { q.nr = 0; q.x0 = q.y0 = q.px0 = q.py0 = 0; q.colmask = 0; q.full = q.staged = false; return q; }
   int lo = __ffs(any) - 1, hi = 32 - __clz(any);
   if (GRAN > 1) { lo &= ~(GRAN - 1); hi = (hi + GRAN - 1) & ~(GRAN - 1); }
   r0 += lo;
   q.nr = hi - lo;
-  q.colmask = (col >> lo) & ((1u << q.nr) - 1u);
+  q.colmask = (col >> lo) & low_bits(q.nr);
   q.x0 = __ldg(&tp->x0); q.y0 = __ldg(&tp->y0) + r0;
-  const uint32_t unit_rows = ((1u << q.nr) - 1u) << r0;
+  const uint32_t unit_rows = low_bits(q.nr) << r0;
   q.full = (__ldg(&tp->full_rows) & unit_rows) == unit_rows;
   // footprint of the unit under the current parameters: one corner per lane (lanes 0-3), min / max by
   // shuffle, widened for the curvature of the quadratic model
@@ -601,10 +642,10 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   pwp.set(p, 0.f, ccx, ccy);
 
   // rows [r0, r1) of tile t that belong to this warp's quad range
-  const int t_first = quad_begin >> 2, t_last = (quad_end - 1) >> 2;
+  const int t_first = quad_begin / kQuadsPerTile, t_last = (quad_end - 1) / kQuadsPerTile;
   auto rows_of = [&](int t, int &r0, int &r1) {
-    r0 = t == t_first ? (quad_begin & 3) * 4 : 0;
-    r1 = t == t_last ? ((quad_end - 1) & 3) * 4 + 4 : kTileH;
+    r0 = t == t_first ? (quad_begin % kQuadsPerTile) * 4 : 0;
+    r1 = t == t_last ? ((quad_end - 1) % kQuadsPerTile) * 4 + 4 : kTileH;
   };
   UnitPlan nxt;
   nxt.nr = 0;
@@ -659,21 +700,26 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
         const int half = nr >> 1;
         int r = 0;
         PairWindow win;
-#define DIC_PSTEP(SV)                                                                                        \
-  {                                                                                                          \
-    const f2 U = pk((float)up_a[(SV) * kUndW], (float)up_b[(SV) * kUndW]);                                      \
-    const f2 Mk = pk(((cm_a >> (SV)) & 1u) ? 1.f : 0.f, ((cm_b >> (SV)) & 1u) ? 1.f : 0.f);                      \
-    if (!parity_pair_step<MODEL, SV>(pwp, Yp, cw2, win, U, Mk, mom)) break;                                  \
-    Yp = add2(Yp, bc(1.f));                                                                                  \
-    if (++r >= half) break;                                                                                  \
-  }
+        // ONE copy of the step (DIC_PAIR_UNROLL == 1, the default): the window rows move between registers, 12 pair
+        // copies per step -- issue slots the packed loop has to spare. The statically rotated four-step form of the
+        // scalar loop (DIC_PAIR_UNROLL == 4) is 26 KB of code here and stalled 1.3 cycles per issue on instruction
+        // fetch (profiles/r2_pair_loop_unrolled_ncu_full.txt).
 #pragma unroll 1
         while (r < half) {
           f2 cw2[4][4];
           f2 Yp = pk((float)(y0 + r), (float)(y0 + half + r));
           const uint8_t *up_a = ucol + r * kUndW, *up_b = ucol + (half + r) * kUndW;
           uint32_t cm_a = colmask >> r, cm_b = colmask >> (half + r);
-          parity_pair_open<MODEL>(pwp, Yp, patch, px0, py0, cw2, win);
+          parity_pair_open<MODEL>(pwp, Yp, cfg.opaque_zero, patch, px0, py0, cw2, win);
+#if DIC_PAIR_UNROLL == 4
+#define DIC_PSTEP(SV)                                                                                        \
+  {                                                                                                          \
+    const f2 U = pk((float)up_a[(SV) * kUndW], (float)up_b[(SV) * kUndW]);                                      \
+    const f2 Mk = pk(((cm_a >> (SV)) & 1u) ? 1.f : 0.f, ((cm_b >> (SV)) & 1u) ? 1.f : 0.f);                      \
+    if (!parity_pair_step<MODEL, SV>(pwp, Yp, cfg.opaque_zero, cw2, win, U, Mk, mom)) break;                                  \
+    Yp = add2(Yp, bc(1.f));                                                                                  \
+    if (++r >= half) break;                                                                                  \
+  }
 #pragma unroll 1
           while (true) {
             DIC_PSTEP(0) DIC_PSTEP(1) DIC_PSTEP(2) DIC_PSTEP(3)
@@ -681,8 +727,22 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
             up_a += 4 * kUndW; up_b += 4 * kUndW;
             cm_a >>= 4; cm_b >>= 4;
           }
-        }
 #undef DIC_PSTEP
+#else
+#pragma unroll 1
+          do {
+            const f2 U = pk((float)*up_a, (float)*up_b);
+            const f2 Mk = pk((cm_a & 1u) ? 1.f : 0.f, (cm_b & 1u) ? 1.f : 0.f);
+            if (!parity_pair_step<MODEL, 0>(pwp, Yp, cfg.opaque_zero, cw2, win, U, Mk, mom)) break;
+#pragma unroll
+            for (int k_ = 0; k_ < 4; ++k_) { cw2[0][k_] = cw2[1][k_]; cw2[1][k_] = cw2[2][k_]; cw2[2][k_] = cw2[3][k_]; }
+            win.wp_a += kPatchW; win.wp_b += kPatchW;
+            up_a += kUndW; up_b += kUndW;
+            cm_a >>= 1; cm_b >>= 1;
+            Yp = add2(Yp, bc(1.f));
+          } while (++r < half);
+#endif
+        }
       } else if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 2) {
         // one code path for full and partial units (three selects per pixel buy half the instruction footprint)
         const uint8_t *wp = patch;
@@ -783,17 +843,22 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float 
 #ifndef DIC_GRID_THREADS
 #define DIC_GRID_THREADS kThreads
 #endif
-#ifndef DIC_BATCH_CTAS
-#define DIC_BATCH_CTAS (tile_ctas_per_sm(model) * kThreads / DIC_BATCH_THREADS)
+#ifndef DIC_BATCH_REGS
+#define DIC_BATCH_REGS 128 // register budget per thread the batch form is compiled for (CTAs per SM = 64 K / regs / threads)
 #endif
 #ifndef DIC_GRID_CTAS
 #define DIC_GRID_CTAS (tile_ctas_per_sm(model) * kThreads / DIC_GRID_THREADS)
 #endif
-__host__ __device__ constexpr int tile_cta_threads(bool grid) { return grid ? DIC_GRID_THREADS : DIC_BATCH_THREADS; }
-__host__ __device__ constexpr int tile_ctas_for(int model, bool grid) { return grid ? DIC_GRID_CTAS : DIC_BATCH_CTAS; }
+// the 12-parameter model needs one thread per accumulator (92) in a few places: its CTAs keep four warps
+__host__ __device__ constexpr int tile_cta_threads(int model, bool grid) {
+  return grid ? DIC_GRID_THREADS : (model == DIC_FM_QUADRATIC && DIC_BATCH_THREADS < 128 ? 128 : DIC_BATCH_THREADS);
+}
+__host__ __device__ constexpr int tile_ctas_for(int model, bool grid) {
+  return grid ? DIC_GRID_CTAS : 65536 / DIC_BATCH_REGS / tile_cta_threads(model, false);
+}
 
 template <int MODEL, int MODE, bool GRID, int CL>
-__global__ void __launch_bounds__(tile_cta_threads(GRID), tile_ctas_for(MODEL, GRID))
+__global__ void __launch_bounds__(tile_cta_threads(MODEL, GRID), tile_ctas_for(MODEL, GRID))
 gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps maps,
                       const SectorDev *__restrict__ sectors, const SectorTiles *__restrict__ sector_tiles,
                       const float *guesses, const GuessParam guess0, dic_result *__restrict__ results, int first_sector,
@@ -801,7 +866,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   static_assert(!GRID || CL == 1, "clusters are a batch-mode feature");
-  constexpr int NT = tile_cta_threads(GRID), NW = NT / 32; // threads, warps of this CTA
+  constexpr int NT = tile_cta_threads(MODEL, GRID), NW = NT / 32; // threads, warps of this CTA
   static_assert(Acc<NP>::kN <= NT && kMaxParams <= NT, "one thread per accumulator / parameter");
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   uint8_t *s_stage = dyn_smem;                                                    // [warps][kWarpStageBytes]
@@ -828,7 +893,13 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   if (CL == 2) cluster_sync_all(); // the partner's shared memory exists from here on
   const int group = GRID ? 0 : (int)blockIdx.x / CL, n_groups = GRID ? 1 : (int)gridDim.x / CL;
 
-  for (int si = group; si < n_sectors; si += GRID ? n_sectors : n_groups) {
+  // Batch form, one CTA per sector: the first sector is the CTA's own index, every further one comes from a launch-wide
+  // ticket counter (the sectors of a batch differ in LM iterations, and n_sectors is rarely a multiple of the CTA
+  // slots: with a static stride the launch ends when the unluckiest CTA does). A sector is still solved by ONE CTA
+  // with the same instruction sequence whichever CTA that is, so the records do not depend on the assignment.
+  constexpr bool kQueue = DIC_BATCH_QUEUE && !GRID && CL == 1;
+  __shared__ int s_next_sector;
+  for (int si = group; si < n_sectors;) {
     const SectorDev *sec = sectors + first_sector + si;
     const SectorTiles *stl = sector_tiles + first_sector + si;
     const float *guess = guesses + (size_t)(first_sector + si) * kMaxParams;
@@ -837,13 +908,19 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
     if (tid < kMaxLevels) s_tiles.lev[tid] = stl->lev[tid];
     if (tid == kMaxLevels) { s_center[0] = sec->cx; s_center[1] = sec->cy; }
     begin_sector<MODEL, GRID>(sh, cfg, sec, guess, guess0, work, my_gen); // ends with a CTA barrier
+#if DIC_BATCH_TIMELINE
+    int dbg_mark = 0; // diagnostics build: CTA 0 records the phases of its LAST sector's evaluations (tools/probe_batch_tl.py)
+#endif
     while (true) {
       const int level = sh.level;
+#if DIC_BATCH_TIMELINE
+      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) work->marks[dbg_mark][0] = global_ns();
+#endif
       for (int k = lane; k < NACC; k += 32) warp_acc[k] = 0.f;
       __syncwarp();
       const TileLevel tl = s_tiles.lev[level];
       // quads of the level over the warps that take part: at least one quad per active warp
-      const int n_quads = tl.n_tiles * 4;
+      const int n_quads = tl.n_tiles * kQuadsPerTile;
       const int ctas = GRID ? (int)gridDim.x : CL;
       const int n_active = max(1, min((n_quads + NW - 1) / NW, ctas));
       const int cta = GRID ? (int)blockIdx.x : crank;
@@ -859,7 +936,13 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
         if (tl.n_extra > 0 && wg == 0)
           evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);
       }
+#if DIC_BATCH_TIMELINE
+      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) work->marks[dbg_mark][1] = global_ns();
+#endif
       __syncthreads();
+#if DIC_BATCH_TIMELINE
+      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) work->marks[dbg_mark][2] = global_ns();
+#endif
       for (int k = tid; k < NACC; k += NT) {
         float s = 0.f;
 #pragma unroll
@@ -868,15 +951,27 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
       }
       __syncthreads();
       reduce_and_step<MODEL, GRID, CL>(sh, active, n_active, cfg, sec, result, work, my_gen);
+#if DIC_BATCH_TIMELINE
+      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) { work->marks[dbg_mark][3] = global_ns(); work->n_marks = ++dbg_mark; }
+#endif
       if (sh.done) break;
     }
+    if (kQueue && tid == 0) s_next_sector = n_groups + (int)atomicAdd(&work->next_sector, 1u);
     __syncthreads();
+    si = GRID ? n_sectors : kQueue ? s_next_sector : si + n_groups;
   }
   if (GRID) grid_depart<NACC>(work, sh.rs_seq, sh.rowsplit != 0);
+  if (kQueue && tid == 0) { // the last CTA to leave re-arms the ticket counter for the next launch
+    __threadfence();
+    if (atomicAdd(&work->batch_departed, 1u) == gridDim.x - 1) {
+      work->next_sector = 0; work->batch_departed = 0;
+      __threadfence();
+    }
+  }
 }
 
-constexpr size_t tiles_dyn_smem(int nacc, bool grid) {
-  return (size_t)(tile_cta_threads(grid) / 32) * kWarpStageBytes + sizeof(float) * (size_t)(tile_cta_threads(grid) / 32) * nacc;
+constexpr size_t tiles_dyn_smem(int nacc, int threads) {
+  return (size_t)(threads / 32) * kWarpStageBytes + sizeof(float) * (size_t)(threads / 32) * nacc;
 }
 
 // ------------------------------------------------------------------ tile construction
