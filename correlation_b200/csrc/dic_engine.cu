@@ -76,7 +76,7 @@ struct dic_engine {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr, img_stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_img = nullptr, ev_gn = nullptr, ev_copy = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_img = nullptr, ev_gn = nullptr, ev_copy = nullptr, ev_copy_und = nullptr;
   cudaEvent_t ev_rot = nullptr; // correlation-stream position at the last pyramid rotation (see dic_reset_next_pyramid)
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr; // around the whole GPU side of a correlate (copies included)
   float last_step_ms = 0.f;
@@ -833,6 +833,7 @@ dic_engine *dic_create(int device) {
             cudaStreamCreateWithFlags(&e->img_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_copy_und, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
             cudaEventCreate(&e->ev_step0) == cudaSuccess && cudaEventCreate(&e->ev_step1) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming) == cudaSuccess &&
@@ -876,6 +877,7 @@ void dic_destroy(dic_engine *e) {
   if (e->ev_gn) cudaEventDestroy(e->ev_gn);
   if (e->ev_rot) cudaEventDestroy(e->ev_rot);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+  if (e->ev_copy_und) cudaEventDestroy(e->ev_copy_und);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->img_stream) cudaStreamDestroy(e->img_stream);
@@ -1054,11 +1056,13 @@ static int stage_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def
       CU_TRY(e, cudaMemcpyAsync(dst, src, (size_t)nr * cols, cudaMemcpyHostToDevice, e->copy_stream));
     else
       CU_TRY(e, cudaMemcpy2DAsync(dst, s.lev[0].pitch, src, cols, cols, nr, cudaMemcpyHostToDevice, e->copy_stream));
+    // one event per image: the reference image's pyramid is built while the deformed image is still on the bus
+    CU_TRY(e, cudaEventRecord(k == 0 ? e->ev_copy_und : e->ev_copy, e->copy_stream));
   }
-  CU_TRY(e, cudaEventRecord(e->ev_copy, e->copy_stream));
-  CU_TRY(e, cudaStreamWaitEvent(e->img_stream, e->ev_copy, 0));
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 2; ++k) {
+    CU_TRY(e, cudaStreamWaitEvent(e->img_stream, k == 0 ? e->ev_copy_und : e->ev_copy, 0));
     if ((rc = build_levels(e, e->pyr[e->role[3 + k]], e->stop, e->img_stream, row_begin, row_end))) return rc;
+  }
   return DIC_OK;
 }
 int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols) {

@@ -25,6 +25,9 @@
 #ifndef DIC_BATCH_QUEUE
 #define DIC_BATCH_QUEUE 1
 #endif
+#ifndef DIC_FAST_UNROLL_BATCH
+#define DIC_FAST_UNROLL_BATCH 1 // fast mode, batch form: pixel steps per loop trip (4: static window rotation; 1: one copy + register moves)
+#endif
 #ifndef DIC_BATCH_TIMELINE
 #define DIC_BATCH_TIMELINE 0 // diagnostics only
 #endif
@@ -607,7 +610,7 @@ __device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, con
 // (12 % of a pass spent waiting at the barrier); coarse levels and small subsets spread the same way until every
 // warp has at least one quad. A warp walks its range tile by tile (first and last tile possibly partial); the
 // staging of the next unit is in flight while the current one is evaluated.
-template <int MODEL, int MODE>
+template <int MODEL, int MODE, bool BATCH>
 __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const TileMaps &maps, float cx0, float cy0,
                                                const TileLevel tl, int level, const float *p,
                                                int quad_begin, int quad_end, WarpStage &st,
@@ -769,6 +772,13 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
 #pragma unroll 1
           for (int r = 0; r < nr; ++r) { DIC_STEP(false, 0, r); DIC_SHIFT(); }
         }
+      } else if (BATCH && DIC_FAST_UNROLL_BATCH == 1) {
+        // fast mode, batch form: ONE copy of the pixel step, the window rows move between registers. Four CTAs per SM
+        // at four different places of the statically rotated four-step loop stalled 1.65 cycles per issue on
+        // instruction fetch (profiles/r2_c4_batch_tiles_fast_ncu_full.txt): 2.00 -> 1.75 ms on c4. The grid form (two
+        // CTAs per SM walking in step) keeps the four-step loop: it is 7 % / 15 % faster there (c2 / c5).
+#pragma unroll 1
+        for (int r = 0; r < nr; ++r) { DIC_STEP(false, 0, r); DIC_SHIFT(); }
       } else if (q.full) {
 #pragma unroll 1
         for (int r = 0; r < nr; r += 4) { DIC_STEP(true, 0, r); DIC_STEP(true, 1, r + 1); DIC_STEP(true, 2, r + 2); DIC_STEP(true, 3, r + 3); }
@@ -931,7 +941,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
         // balanced contiguous ranges: the first (n_quads % nw) warps take one quad more
         const int base = n_quads / nw, rem = n_quads - base * nw;
         const int qb = wg * base + min(wg, rem), qe = qb + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, qb, qe, st,
+        evaluate_tiles<MODEL, MODE, !GRID>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, qb, qe, st,
                                     warp_acc, GRID ? &work->slow_units : nullptr, &sh.timed_out);
         if (tl.n_extra > 0 && wg == 0)
           evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);

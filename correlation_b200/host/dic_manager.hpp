@@ -11,6 +11,7 @@
 // Frames are raw u8 buffers (the reference decodes files with cv::imread; decoding is out of scope).
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <future>
 #include <sstream>
 #include <string>
@@ -47,7 +48,10 @@ struct Config {
   // extension: prefetch the next frame by ENQUEUEING its upload + pyramid on the engine's image stream instead of
   // running them on a per-frame loader thread (manager_class.cpp:1438-1447). Requires frame buffers that stay
   // alive and unchanged for the run (true for perform_multiframe_correlation's raw-buffer frames).
-  bool async_next_image = true;
+  // Measured on c3 (100 frames of 2048^2, B200): 2770 frames/s with the enqueue-only prefetch against 4170 with the
+  // loader thread -- the pyramid kernels of frame k + 2, enqueued before frame k's solve, delay that solve's
+  // cooperative launch (it needs all of its CTAs resident at once). Off by default; DIC_ASYNC_NEXT_IMAGE=1 turns it on.
+  bool async_next_image = false;
 };
 
 // the part of frame_results (domains.hpp:59-108) the GPU path reads or reports
@@ -368,6 +372,7 @@ public:
     cuda_.set_fitting_model(cfg.model);
     cuda_.set_interpolation_model(cfg.interpolation);
     cuda_.set_arith_mode(cfg.arith_mode);
+    if (const char *v = std::getenv("DIC_ASYNC_NEXT_IMAGE")) cfg_.async_next_image = v[0] == '1';
   }
   CudaClass &engine() { return cuda_; }
   int frames_done() const { return frames_done_; } // frame pairs that reached the report (stopAll ends early)

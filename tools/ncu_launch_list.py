@@ -14,7 +14,8 @@ for r in rows[hi + 1:]:
     if r[mu] == "ns": v /= 1e3
     elif r[mu] == "ms": v *= 1e3
     a = agg.setdefault(r[kn], [0, 0.0]); a[0] += 1; a[1] += v
-ours = {k: v for k, v in agg.items() if "dic::" in k or k.startswith("void dic") or "gn_solve" in k or "pyramid_level" in k}
+OURS = ("dic::", "gn_solve", "pyramid_level", "rect_grid", "rect_fill", "rect_tiles", "compact_", "tiles_scatter", "expand_spans", "bbox_kernel", "copy_rows")
+ours = {k: v for k, v in agg.items() if k.startswith("void dic") or any(t in k for t in OURS)}
 tot = sum(v[1] for v in ours.values()); all_t = sum(v[1] for v in agg.values())
 print(f"# our kernels: {tot/1e3:.3f} ms of {all_t/1e3:.3f} ms profiled")
 print("# kernel | launches | total us | share of our kernels")
