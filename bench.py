@@ -166,7 +166,7 @@ class ClockSampler:
         # every rank samples its own GPU; the period grows with the number of ranks so that the box-wide
         # rate of driver queries stays the same (NVML calls serialise on a driver lock shared by all GPUs)
         self.index, self.samples, self.stop = index, [], False
-        self.period = 0.02 * max(1, world)
+        self.period = 0.005 * max(1, world)
         self.t = threading.Thread(target=self._run, daemon=True)
         self.nvml = self.handle = None
         try:

@@ -28,6 +28,9 @@
 #ifndef DIC_FAST_UNROLL_BATCH
 #define DIC_FAST_UNROLL_BATCH 1 // fast mode, batch form: pixel steps per loop trip (4: static window rotation; 1: one copy + register moves)
 #endif
+#ifndef DIC_YSTAGE_PACKED
+#define DIC_YSTAGE_PACKED 1
+#endif
 #ifndef DIC_BATCH_TIMELINE
 #define DIC_BATCH_TIMELINE 0 // diagnostics only
 #endif
@@ -342,19 +345,90 @@ __device__ __forceinline__ void staged_pixel(const float *pw, const LaneWarp<mod
 
 // ---- parity mode, second form of the inner loop (DIC_PARITY_LOOP == 2, the default).
 // The window state of a lane: cw = x-direction cubic coefficients of the four window rows in ROTATING slots,
-// (wix, wiy) = the window's pixel, wp = address of the aligned 32-bit word that holds the first byte of the window's
-// LAST row in the staged patch, wsh = bit shift of that byte inside the word (the same for every row of a window,
-// because the patch pitch is a multiple of four).
-//   parity_window_open   (cold: first row of a unit, or a lane's window did not simply move down one row)
-//                        positions the window ONE ROW ABOVE the pixel: rows 0..2 of the pixel's window go to slots
-//                        0..2, so that the very next slide step -- at the same pixel -- loads row 3 and evaluates;
-//   parity_slide_step<S> (hot) one pixel: warp, floor, "did every lane's window move down by exactly one row?"; if
-//                        not, returns false without side effects (the caller reopens the window at this pixel). Else
-//                        one row is read (wp += pitch: no address arithmetic from ix, iy), converted, and the pixel
-//                        is evaluated on slots (S, S+1, S+2, S+3) mod 4. Four steps with S = 0, 1, 2, 3 in a row
-//                        rotate the slots back: the window never moves between registers (the first form shifted
-//                        12 registers per pixel and paid ~7 more copies to merge its two branches).
+// (wix, wiy) = the window's pixel as the bit patterns the floor trick produces (2^23 + ix, and the 2^23 + iy expected
+// at the next step), wp = address of the aligned 32-bit word that holds the first byte of the window's LAST row in
+// the staged patch, wsh = bit shift of that byte inside the word (the same for every row of a window, because the
+// patch pitch is a multiple of four).
+//   parity_window_open          (cold: first row of a unit, or a lane's window did not simply move down one row)
+//                               positions the window ONE ROW ABOVE the pixel: rows 0..2 of the pixel's window go to
+//                               slots 0..2, so that the very next step -- at the same pixel -- loads row 3 and evaluates;
+//   parity_slide_step_trip<S>   (hot) one pixel: warp, floor, "did every lane's window move down by exactly one row?";
+//                               if not, returns false without side effects (the caller reopens the window at this
+//                               pixel). Else one row is read (immediate offset from wp: no address arithmetic from ix,
+//                               iy), converted, and the pixel is evaluated on slots (S, S+1, S+2, S+3) mod 4. Four steps
+//                               with S = 0, 1, 2, 3 in a row rotate the slots back: the window never moves between
+//                               registers (the first form shifted 12 registers per pixel and paid ~7 more copies to
+//                               merge its two branches), and the loop-carried values advance once per four pixels.
 // The per-pixel results are bit-identical to the first form: same operations on the same values.
+// Packed y pass (DIC_YSTAGE_PACKED, the default): the window rows hold their four x-direction coefficients as TWO
+// fp32 pairs (c0, c1), (c2, c3), and the y pass of the coefficient stage -- the same 11 exact operations for each of
+// the four columns -- runs as 2 x 11 packed instructions (dic_f32x2.cuh) instead of 4 x 11 scalar ones: 22 issue
+// slots less per pixel in a loop that is bound by issue slots, the same FMA-pipe passes. Every value of this stage
+// is exact in fp32 (multiples of 1/4 below 2^17), so neither the packing nor any contraction ptxas applies to it can
+// change a bit; the 40-term polynomial stays scalar and unfused.
+__device__ __forceinline__ void row_coeffs_u8_pairs(uint32_t win, f2 (&row)[2]) {
+  float c[4];
+  row_coeffs_u8<DIC_MODE_PARITY>(win, c);
+  row[0] = pk(c[0], c[1]); row[1] = pk(c[2], c[3]);
+}
+__device__ __forceinline__ void bicubic_parity_rows_pairs(const f2 (&r0)[2], const f2 (&r1)[2], const f2 (&r2)[2],
+                                                          const f2 (&r3)[2], float xdef, float ydef, float fix, float fiy,
+                                                          float &w, float &wx, float &wy) {
+  float a[4][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    f2 c[4];
+    monomial_from_rows_x2(r0[h], r1[h], r2[h], r3[h], c);
+#pragma unroll
+    for (int jk = 0; jk < 4; ++jk) { a[jk][2 * h] = lo(c[jk]); a[jk][2 * h + 1] = hi(c[jk]); }
+  }
+  parity_eval_f(a, xdef, ydef, fix, fiy, w, wx, wy);
+}
+
+template <int MODEL>
+__device__ __forceinline__ void parity_window_open_pairs(const float *pw, float xf, float yf, float ccx, float ccy,
+                                                         const uint8_t *patch, int px0, int py0, f2 (&cw)[4][2],
+                                                         int &wix, int &wiy, const uint8_t *&wp, int &wsh) {
+  float xd, yd, dxx, dyy;
+  warp_point<MODEL, DIC_MODE_PARITY>(pw, xf, yf, ccx, ccy, xd, yd, dxx, dyy);
+  int ix, iy;
+  floor_magic(xd, ix);
+  floor_magic(yd, iy);
+  const int o = (iy - 1 - py0) * kPatchW + (ix - 1 - px0); // byte offset of the window's first row
+  wsh = (o & 3) * 8;
+  const uint8_t *b = patch + (o & ~3);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(b + k * kPatchW);
+    row_coeffs_u8_pairs(__funnelshift_r(w[0], w[1], wsh), cw[k]);
+  }
+  wp = b + 2 * kPatchW;
+  wix = __float_as_int(__fadd_rd(xd, 8388608.0f)); wiy = __float_as_int(__fadd_rd(yd, 8388608.0f));
+}
+
+template <int MODEL, int S>
+__device__ __forceinline__ bool parity_slide_step_trip_pairs(const float *pw, float xf, float yf, float ccx, float ccy,
+                                                             f2 (&cw)[4][2], int wix_bits, int &wiy_next_bits,
+                                                             const uint8_t *wp, int wsh, float und_w, bool member, float *mom) {
+  constexpr int NP = model_nparams(MODEL);
+  float xd, yd, dxx, Y;
+  warp_point<MODEL, DIC_MODE_PARITY>(pw, xf, S == 0 ? yf : yf + (float)S, ccx, ccy, xd, yd, dxx, Y);
+  const float mx = __fadd_rd(xd, 8388608.0f), my = __fadd_rd(yd, 8388608.0f);
+  if (!__all_sync(0xffffffffu, __float_as_int(mx) == wix_bits && __float_as_int(my) == wiy_next_bits)) return false;
+  wiy_next_bits = __float_as_int(my) + 1;
+  const float fx = mx - 8388608.0f, fy = my - 8388608.0f;
+  {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(wp + (S + 1) * kPatchW);
+    row_coeffs_u8_pairs(__funnelshift_r(w[0], w[1], wsh), cw[(3 + S) & 3]);
+  }
+  float w, wx, wy;
+  bicubic_parity_rows_pairs(cw[(0 + S) & 3], cw[(1 + S) & 3], cw[(2 + S) & 3], cw[(3 + S) & 3], xd, yd, fx, fy, w, wx, wy);
+  float V = und_w - w;
+  V = member ? V : 0.f; wx = member ? wx : 0.f; wy = member ? wy : 0.f;
+  accumulate_moments<NP>(mom, V, wx, wy, Y);
+  return true;
+}
+
 template <int MODEL>
 __device__ __forceinline__ void parity_window_open(const float *pw, float xf, float yf, float ccx, float ccy,
                                                    const uint8_t *patch, int px0, int py0, float (&cw)[4][4],
@@ -373,23 +447,28 @@ __device__ __forceinline__ void parity_window_open(const float *pw, float xf, fl
     row_coeffs_u8<DIC_MODE_PARITY>(__funnelshift_r(w[0], w[1], wsh), cw[k]);
   }
   wp = b + 2 * kPatchW;
-  wix = ix; wiy = iy - 1;
+  // the window sits one row above the pixel: the next step is at this same pixel (see parity_slide_step_trip)
+  wix = __float_as_int(__fadd_rd(xd, 8388608.0f)); wiy = __float_as_int(__fadd_rd(yd, 8388608.0f));
 }
 
+// Trip-static form of the step (what the loop below uses): four steps S = 0..3 share one set of loop-carried values
+// (yf, wp, the reference-pixel pointer, the membership word), each step addresses its row with an immediate offset,
+// and the window's pixel is kept as the BIT PATTERNS of 2^23 + ix and of the 2^23 + iy expected next, so that the
+// slide test is two integer compares on the floor trick's own output (no mask, no + 1 on the critical path).
+// yf is the row of step 0 of the trip; wp the word holding the first byte of the window's last row before step 0.
 template <int MODEL, int S>
-__device__ __forceinline__ bool parity_slide_step(const float *pw, float xf, float yf, float ccx, float ccy,
-                                                  float (&cw)[4][4], int wix, int &wiy, const uint8_t *&wp, int wsh,
-                                                  float und_w, bool member, float *mom) {
+__device__ __forceinline__ bool parity_slide_step_trip(const float *pw, float xf, float yf, float ccx, float ccy,
+                                                       float (&cw)[4][4], int wix_bits, int &wiy_next_bits,
+                                                       const uint8_t *wp, int wsh, float und_w, bool member, float *mom) {
   constexpr int NP = model_nparams(MODEL);
   float xd, yd, dxx, Y;
-  warp_point<MODEL, DIC_MODE_PARITY>(pw, xf, yf, ccx, ccy, xd, yd, dxx, Y);
-  int ix, iy;
-  const float fx = floor_magic(xd, ix), fy = floor_magic(yd, iy);
-  if (!__all_sync(0xffffffffu, ix == wix && iy == wiy + 1)) return false;
-  wp += kPatchW;
-  wiy = iy;
+  warp_point<MODEL, DIC_MODE_PARITY>(pw, xf, S == 0 ? yf : yf + (float)S, ccx, ccy, xd, yd, dxx, Y);
+  const float mx = __fadd_rd(xd, 8388608.0f), my = __fadd_rd(yd, 8388608.0f); // floor_magic, integer part in the low bits
+  if (!__all_sync(0xffffffffu, __float_as_int(mx) == wix_bits && __float_as_int(my) == wiy_next_bits)) return false;
+  wiy_next_bits = __float_as_int(my) + 1;
+  const float fx = mx - 8388608.0f, fy = my - 8388608.0f;
   {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(wp);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(wp + (S + 1) * kPatchW);
     row_coeffs_u8<DIC_MODE_PARITY>(__funnelshift_r(w[0], w[1], wsh), cw[(3 + S) & 3]);
   }
   float w, wx, wy;
@@ -539,13 +618,26 @@ struct UnitPlan {
 
 // Rows [r0, r1) of tile `t`. GRAN = 4 keeps the trimmed range on multiples of four rows (fast mode walks four
 // pixels per trip), GRAN = 1 trims to the exact first / last owned row.
+// What plan_unit reads of a tile record, fetched ONE UNIT EARLIER than it is needed: the record comes from L2
+// (~0.4 us), and a warp that loads it at planning time stalls for that long once per unit (5 % of a 32-row unit).
+struct TileHead {
+  int x0, y0;
+  uint32_t col, full_rows; // col: this lane's column of the membership mask
+};
+__device__ __forceinline__ TileHead load_tile_head(const TileLevel &tl, int t) {
+  const Tile *tp = tl.tiles + t;
+  TileHead h;
+  h.col = __ldg(&tp->cols[threadIdx.x & 31]);
+  h.x0 = __ldg(&tp->x0); h.y0 = __ldg(&tp->y0); h.full_rows = __ldg(&tp->full_rows);
+  return h;
+}
+
 template <int NP, int GRAN>
-__device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int t, int r0, int r1, const float *p,
+__device__ __forceinline__ UnitPlan plan_unit(const TileHead &th, int r0, int r1, const float *p,
                                               float ccx, float ccy, const LevelImage &def) {
   const int lane = threadIdx.x & 31;
   UnitPlan q;
-  const Tile *tp = tl.tiles + t;
-  uint32_t col = (__ldg(&tp->cols[lane]) >> r0) & low_bits(r1 - r0);
+  uint32_t col = (th.col >> r0) & low_bits(r1 - r0);
   const uint32_t any = __reduce_or_sync(0xffffffffu, col); // rows of the range some lane owns
   if (any == 0u) { q.nr = 0; q.x0 = q.y0 = q.px0 = q.py0 = 0; q.colmask = 0; q.full = q.staged = false; return q; }
   int lo = __ffs(any) - 1, hi = 32 - __clz(any);
@@ -553,9 +645,9 @@ __device__ __forceinline__ UnitPlan plan_unit(const TileLevel &tl, int t, int r0
   r0 += lo;
   q.nr = hi - lo;
   q.colmask = (col >> lo) & low_bits(q.nr);
-  q.x0 = __ldg(&tp->x0); q.y0 = __ldg(&tp->y0) + r0;
+  q.x0 = th.x0; q.y0 = th.y0 + r0;
   const uint32_t unit_rows = low_bits(q.nr) << r0;
-  q.full = (__ldg(&tp->full_rows) & unit_rows) == unit_rows;
+  q.full = (th.full_rows & unit_rows) == unit_rows;
   // footprint of the unit under the current parameters: one corner per lane (lanes 0-3), min / max by
   // shuffle, widened for the curvature of the quadratic model
   float bx0, bx1, by0, by1;
@@ -655,16 +747,19 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   if (quad_begin < quad_end) {
     int r0, r1;
     rows_of(t_first, r0, r1);
-    nxt = plan_unit<NP, GRAN>(tl, t_first, r0, r1, p, ccx, ccy, def);
+    nxt = plan_unit<NP, GRAN>(load_tile_head(tl, t_first), r0, r1, p, ccx, ccy, def);
     issue_unit(st, nxt, map_def, map_und);
   }
+  TileHead head_next = {0, 0, 0u, 0u}; // record of tile t + 1, in flight while tile t - 1 ... t is evaluated
+  if (quad_begin < quad_end && t_first + 1 <= t_last) head_next = load_tile_head(tl, t_first + 1);
   for (int t = t_first; quad_begin < quad_end && t <= t_last; ++t) {
     const UnitPlan q = nxt;
     if (t + 1 <= t_last) {
       int r0, r1;
       rows_of(t + 1, r0, r1);
-      nxt = plan_unit<NP, GRAN>(tl, t + 1, r0, r1, p, ccx, ccy, def);
+      nxt = plan_unit<NP, GRAN>(head_next, r0, r1, p, ccx, ccy, def);
       issue_unit(st, nxt, map_def, map_und);
+      if (t + 2 <= t_last) head_next = load_tile_head(tl, t + 2);
     }
     if (q.nr == 0) continue;
     const int x0 = q.x0, y0 = q.y0, nr = q.nr;
@@ -748,20 +843,37 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
         }
       } else if (MODE == DIC_MODE_PARITY && DIC_PARITY_LOOP == 2) {
         // one code path for full and partial units (three selects per pixel buy half the instruction footprint)
-        const uint8_t *wp = patch;
-        int wsh = 0;
-        float yf = (float)y0;       // exact: small integers; yf += 1 replaces an int -> float conversion per pixel
-        const uint8_t *up = ucol;   // reference pixel of the current row
-        uint32_t cm = q.full ? 0xffffffffu : colmask;
+        const uint32_t members = q.full ? 0xffffffffu : colmask;
         int r = 0;
-#define DIC_PSTEP(SV)                                                                                        \
-  if (!parity_slide_step<MODEL, SV>(pw, xf, yf, ccx, ccy, cw, wix, wiy, wp, wsh, (float)*up, (cm & 1u) != 0, mom)) break; \
-  yf += 1.f; up += kUndW; cm >>= 1; if (++r >= nr) break;
+#if DIC_YSTAGE_PACKED
+        f2 cwp[4][2];
+#define DIC_PSTEP(SV)                                                                                              \
+  if (!parity_slide_step_trip_pairs<MODEL, SV>(pw, xf, yf, ccx, ccy, cwp, wix, wiy, wp, wsh, (float)up[(SV) * kUndW], \
+                                               ((cm >> (SV)) & 1u) != 0, mom)) { r += (SV); break; }               \
+  if (left <= (SV) + 1) { r = nr; break; }
+#else
+#define DIC_PSTEP(SV)                                                                                              \
+  if (!parity_slide_step_trip<MODEL, SV>(pw, xf, yf, ccx, ccy, cw, wix, wiy, wp, wsh, (float)up[(SV) * kUndW],      \
+                                         ((cm >> (SV)) & 1u) != 0, mom)) { r += (SV); break; }                     \
+  if (left <= (SV) + 1) { r = nr; break; }
+#endif
 #pragma unroll 1
         while (r < nr) {
+          // (re)open the window at row r; the loop-carried values of a trip follow from r
+          float yf = (float)(y0 + r);
+          const uint8_t *wp, *up = ucol + r * kUndW; // wp: window rows in the patch; up: reference pixel of the row
+          int wsh, left = nr - r;
+          uint32_t cm = members >> r;
+#if DIC_YSTAGE_PACKED
+          parity_window_open_pairs<MODEL>(pw, xf, yf, ccx, ccy, patch, px0, py0, cwp, wix, wiy, wp, wsh);
+#else
           parity_window_open<MODEL>(pw, xf, yf, ccx, ccy, patch, px0, py0, cw, wix, wiy, wp, wsh);
+#endif
 #pragma unroll 1
-          while (true) { DIC_PSTEP(0) DIC_PSTEP(1) DIC_PSTEP(2) DIC_PSTEP(3) }
+          while (true) {
+            DIC_PSTEP(0) DIC_PSTEP(1) DIC_PSTEP(2) DIC_PSTEP(3)
+            r += 4; left -= 4; yf += 4.f; wp += 4 * kPatchW; up += 4 * kUndW; cm >>= 4;
+          }
         }
 #undef DIC_PSTEP
       } else if (MODE == DIC_MODE_PARITY) {
