@@ -105,7 +105,8 @@ struct dic_engine {
   int rs_rank = 0, rs_world = 1;
   float *d_guess = nullptr;
   dic_result *d_results = nullptr;
-  dic_result *h_results = nullptr; // pinned
+  dic_result *h_results = nullptr; // pinned and mapped: the kernels write the records straight into it
+  dic_result *h_results_dev = nullptr; // the same block as the device sees it
   float *h_guess = nullptr;        // pinned + mapped: batch kernels read their guesses from here (zero-copy)
   float *h_guess_dev = nullptr;    // device-side address of h_guess
   int cluster_mode = 0;            // batch launches: 0 auto, 1 one CTA per sector, 2 one CTA pair per sector
@@ -336,7 +337,7 @@ int ensure_sector_capacity(dic_engine *e, int n) {
   CU_TRY(e, cudaMalloc(&dt, sizeof(SectorTiles) * cap));
   CU_TRY(e, cudaMemset(dt, 0, sizeof(SectorTiles) * cap));
   CU_TRY(e, cudaMalloc(&dr, sizeof(dic_result) * cap));
-  CU_TRY(e, cudaMallocHost(&hr, sizeof(dic_result) * cap));
+  CU_TRY(e, cudaHostAlloc(&hr, sizeof(dic_result) * cap, cudaHostAllocMapped | cudaHostAllocPortable));
   CU_TRY(e, cudaHostAlloc(&hg, sizeof(float) * kMaxParams * cap, cudaHostAllocMapped | cudaHostAllocPortable));
   CU_TRY(e, cudaMallocHost(&hs, sizeof(SectorDev) * cap));
   CU_TRY(e, cudaMallocHost(&ht, sizeof(SectorTiles) * cap));
@@ -366,6 +367,9 @@ int ensure_sector_capacity(dic_engine *e, int n) {
   void *hg_dev = nullptr;
   CU_TRY(e, cudaHostGetDevicePointer(&hg_dev, hg, 0));
   e->h_guess_dev = static_cast<float *>(hg_dev);
+  void *hr_dev = nullptr;
+  CU_TRY(e, cudaHostGetDevicePointer(&hr_dev, hr, 0));
+  e->h_results_dev = static_cast<dic_result *>(hr_dev);
   // the memsets / copies above ran on the legacy default stream, which the engine's non-blocking streams do
   // not wait for: drain the device once (this path runs only when the sector table grows)
   CU_TRY(e, cudaDeviceSynchronize());
@@ -639,7 +643,7 @@ int launch_solve(dic_engine *e, bool grid_mode, int first, int count) {
   const SectorDev *sectors = e->d_sectors;
   const float *guesses = e->h_guess_dev;
   GuessParam g0 = guess_param(e, first);
-  dic_result *results = e->d_results;
+  dic_result *results = e->h_results_dev; // zero-copy: 176 B per sector, written once when its pyramid ends
   GridWork *work = e->d_work;
   if (grid_mode) {
     auto kern = gn_solve_kernel<MODEL, INTERP, MODE, true>;
@@ -675,7 +679,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   const SectorTiles *stiles = e->d_sector_tiles;
   const float *guesses = e->h_guess_dev;
   GuessParam g0 = guess_param(e, first);
-  dic_result *results = e->d_results;
+  dic_result *results = e->h_results_dev; // zero-copy: 176 B per sector, written once when its pyramid ends
   GridWork *work = e->d_work;
   TileMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -1709,8 +1713,8 @@ static int enqueue_correlate(dic_engine *e, int first, int count, const float *g
   if (rc) return rc;
   CU_TRY(e, cudaEventRecord(e->ev1, e->stream));
   e->timing_pending = true;
-  CU_TRY(e, cudaMemcpyAsync(e->h_results + first, e->d_results + first, sizeof(dic_result) * count,
-                            cudaMemcpyDeviceToHost, e->stream));
+  // no download: the result records are written by the kernel into the pinned, mapped block the host reads after
+  // the stream has drained (a D2H copy of 176 B cost ~10 us of copy-engine latency per correlate)
   CU_TRY(e, cudaEventRecord(e->ev_step1, e->stream));
   return DIC_OK;
 }
