@@ -2,12 +2,12 @@
 //
 // Integer-grid domains (rectangles, annuli, blobs: everything the reference's builders produce,
 // manager_class.cpp:1596-1614 / :816-940, polygon_class.cpp) are stored per pyramid level as
-// 32 x 16 pixel tiles with one 32-bit membership mask per row, ordered COLUMN-major so that a warp
+// 32 x 32 pixel tiles with one 32-bit membership mask per row, ordered COLUMN-major so that a warp
 // walks down one 32-pixel-wide strip: lane <-> x, loop <-> y. That layout buys three things the
 // pixel-list kernel cannot have:
 //   1. coalesced u8 traffic: a warp-row of the reference image is one 32-byte sector, and the
-//      deformed-image footprint of a whole tile (about 40 x 24 pixels) is staged ONCE into shared
-//      memory as fp32 (u8 -> float conversion per deformed pixel, not 16x per domain pixel);
+//      deformed-image footprint of a whole unit (about 40 x 40 pixels) is staged ONCE into shared
+//      memory by TMA; a window row is converted once per pixel of the column, not four times;
 //   2. dx = x - cx is a per-lane constant, so J^T J / J^T r are accumulated as moments in dy only
 //      (sum g g' dy^b, sum V g dy^b): 15 + 6 + 2 registers for the 12-parameter model instead of
 //      92, 9 + 4 + 2 instead of 29 for the affine one, and 3-4x fewer FMAs per pixel;
