@@ -711,6 +711,10 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     if (per_sm == 0) {
       CU_TRY(e, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU_TRY(e, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // all of the SM's unified L1 / shared memory as shared memory: the staging buffers (35 KB per CTA) decide how
+      // many CTAs are resident, the kernel's global reads are tile records and parameters only
+      CU_TRY(e, cudaFuncSetAttribute(kern1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU_TRY(e, cudaFuncSetAttribute(kern2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern1, NTB, smem));
     }
     const long slots = (long)std::max(1, per_sm) * e->num_sms;

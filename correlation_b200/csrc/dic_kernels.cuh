@@ -35,6 +35,10 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifndef DIC_BATCH_TIMELINE
+#define DIC_BATCH_TIMELINE 0 // diagnostics only (tools/probe_batch_tl.py)
+#endif
+
 // ------------------------------------------------------------------ LM state machine
 
 // scratch of warp_solve (NP * NP) followed by the step dp (NP): lm_step puts dp at kDpOffset
@@ -455,7 +459,13 @@ __device__ __forceinline__ void reduce_and_step(SolveShared<model_nparams(MODEL)
       writer = me == 0;
     }
     if (warp == 0) {
+#if DIC_BATCH_TIMELINE
+      if (blockIdx.x == 0 && lane == 0 && sh.mark < kMaxMarks) work->marks[sh.mark][2] = global_ns();
+#endif
       lm_step<MODEL>(&sh.state, sh.tot, cfg, sec, result, sh.solve, writer);
+#if DIC_BATCH_TIMELINE
+      if (blockIdx.x == 0 && lane == 0 && sh.mark < kMaxMarks) work->marks[sh.mark][3] = global_ns();
+#endif
       if (lane == 0 && sh.timed_out) { sh.state.done = 1; if (writer) result->errorCode = DIC_ERROR_CUDA; }
       __syncwarp();
       if (lane < NP) sh.p[lane] = sh.state.p[lane];

@@ -1058,12 +1058,10 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
         if (tl.n_extra > 0 && wg == 0)
           evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);
       }
-#if DIC_BATCH_TIMELINE
-      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) work->marks[dbg_mark][1] = global_ns();
-#endif
       __syncthreads();
 #if DIC_BATCH_TIMELINE
-      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) work->marks[dbg_mark][2] = global_ns();
+      // diagnostics: [0] pass started, [1] every warp's pass done, [2] LM step started, [3] LM step done (reduce_and_step)
+      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) { work->marks[dbg_mark][1] = global_ns(); sh.mark = dbg_mark; }
 #endif
       for (int k = tid; k < NACC; k += NT) {
         float s = 0.f;
@@ -1074,7 +1072,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
       __syncthreads();
       reduce_and_step<MODEL, GRID, CL>(sh, active, n_active, cfg, sec, result, work, my_gen);
 #if DIC_BATCH_TIMELINE
-      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) { work->marks[dbg_mark][3] = global_ns(); work->n_marks = ++dbg_mark; }
+      if (!GRID && blockIdx.x == 0 && tid == 0 && dbg_mark < kMaxMarks) work->n_marks = ++dbg_mark;
 #endif
       if (sh.done) break;
     }

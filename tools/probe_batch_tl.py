@@ -17,8 +17,9 @@ for _ in range(3):
     rs = eng.correlate_batch(0, zero)
 t = eng.timeline()
 print(f"batch n={n}: {eng.last_correlate_ms():.3f} ms")
-print("  eval: own-pass  wait-warps  sum+LM+solve  (us)   since first")
+print("  eval:  pass(all warps)  sum->LM start  LM step  LM end->next pass   (us)")
 for i, m in enumerate(t):
-    print(f"  {i:3d}  {(m[1]-m[0])/1e3:8.2f} {(m[2]-m[1])/1e3:8.2f} {(m[3]-m[2])/1e3:8.2f}   {(m[3]-t[0][0])/1e3:8.1f}")
+    nxt = t[i + 1][0] if i + 1 < len(t) else m[3]
+    print(f"  {i:3d}  {(m[1]-m[0])/1e3:8.2f} {(m[2]-m[1])/1e3:8.2f} {(m[3]-m[2])/1e3:8.2f} {(nxt-m[3])/1e3:8.2f}")
 tot = (t[-1][3] - t[0][0]) / 1e3
-print(f"  subset total {tot:.1f} us: pass {sum(m[1]-m[0] for m in t)/1e3:.1f}, wait {sum(m[2]-m[1] for m in t)/1e3:.1f}, serial {sum(m[3]-m[2] for m in t)/1e3:.1f}, between evaluations {tot - sum(m[3]-m[0] for m in t)/1e3:.1f}")
+print(f"  subset total {tot:.1f} us: pass {sum(m[1]-m[0] for m in t)/1e3:.1f}, sum->LM {sum(m[2]-m[1] for m in t)/1e3:.1f}, LM step {sum(m[3]-m[2] for m in t)/1e3:.1f}, LM end->next pass {sum(t[i+1][0]-t[i][3] for i in range(len(t)-1))/1e3:.1f}")
