@@ -685,7 +685,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
   memset(&maps, 0, sizeof(maps));
   for (int l = 0; l <= e->stop; ++l) { maps.def[l] = d.tm_patch[l]; maps.und[l] = u.tm_tile[l]; }
   constexpr int NACC = Acc<model_nparams(MODEL)>::kN;
-  constexpr int NTB = tile_cta_threads(MODEL, false), NTG = tile_cta_threads(MODEL, true); // threads per CTA of the batch / grid form
+  constexpr int NTB = tile_cta_threads(MODEL, MODE, false), NTG = tile_cta_threads(MODEL, MODE, true); // threads per CTA of the batch / grid form
   const size_t smem = tiles_dyn_smem(NACC, grid_mode ? NTG : NTB);
   if (grid_mode) {
     auto kern = gn_solve_tiles_kernel<MODEL, MODE, true, 1>;
@@ -693,6 +693,7 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
     int &per_sm = per_sm_cached[e->device & 15];
     if (per_sm == 0) {
       CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       CU_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTG, smem));
     }
     if (per_sm < 1) { set_error(e, "gn_solve_tiles_kernel does not fit on an SM"); return DIC_ERROR_CUDA; }

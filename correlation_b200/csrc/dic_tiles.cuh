@@ -972,15 +972,30 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float 
 #define DIC_GRID_CTAS (tile_ctas_per_sm(model) * kThreads / DIC_GRID_THREADS)
 #endif
 // the 12-parameter model needs one thread per accumulator (92) in a few places: its CTAs keep four warps
-__host__ __device__ constexpr int tile_cta_threads(int model, bool grid) {
-  return grid ? DIC_GRID_THREADS : (model == DIC_FM_QUADRATIC && DIC_BATCH_THREADS < 128 ? 128 : DIC_BATCH_THREADS);
+// Grid form of the 12-parameter model: ONE CTA of 384 threads per SM (up to 168 registers: no spills) instead of two
+// of 256 at 128 registers (DIC_GRID_QUAD_ONE_CTA). Measured on c2 (B200): 0.569 ms with 2 x 256, 0.545 with 3 x 128,
+// 0.516 with 1 x 384, 0.560 with 1 x 512. Besides the registers, the warps of ONE CTA are the same age for the warp
+// scheduler and finish a pass within 9 % of each other; with several CTAs per SM the oldest CTA is served first and the
+// youngest ends 25-40 % later (tools/probe_tl.py, per-CTA end times), which every other CTA then waits for at the
+// grid barrier -- and the barrier has 148 participants instead of 296 / 444. The affine grid form keeps two CTAs of
+// 256: c1 (few quads per warp) is 13-27 % slower with one big CTA and c5 within 2 % either way.
+#ifndef DIC_GRID_QUAD_ONE_CTA
+#define DIC_GRID_QUAD_ONE_CTA 1
+#endif
+__host__ __device__ constexpr bool tile_grid_one_cta(int model, int mode) {
+  return DIC_GRID_QUAD_ONE_CTA && model == DIC_FM_QUADRATIC && mode >= 0;
 }
-__host__ __device__ constexpr int tile_ctas_for(int model, bool grid) {
-  return grid ? DIC_GRID_CTAS : 65536 / DIC_BATCH_REGS / tile_cta_threads(model, false);
+__host__ __device__ constexpr int tile_cta_threads(int model, int mode, bool grid) {
+  return grid ? (tile_grid_one_cta(model, mode) ? 384 : DIC_GRID_THREADS)
+              : (model == DIC_FM_QUADRATIC && DIC_BATCH_THREADS < 128 ? 128 : DIC_BATCH_THREADS);
+}
+__host__ __device__ constexpr int tile_ctas_for(int model, int mode, bool grid) {
+  return grid ? (tile_grid_one_cta(model, mode) ? 1 : DIC_GRID_CTAS)
+              : 65536 / DIC_BATCH_REGS / tile_cta_threads(model, mode, false);
 }
 
 template <int MODEL, int MODE, bool GRID, int CL>
-__global__ void __launch_bounds__(tile_cta_threads(MODEL, GRID), tile_ctas_for(MODEL, GRID))
+__global__ void __launch_bounds__(tile_cta_threads(MODEL, MODE, GRID), tile_ctas_for(MODEL, MODE, GRID))
 gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps maps,
                       const SectorDev *__restrict__ sectors, const SectorTiles *__restrict__ sector_tiles,
                       const float *guesses, const GuessParam guess0, dic_result *__restrict__ results, int first_sector,
@@ -988,7 +1003,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   constexpr int NP = model_nparams(MODEL);
   constexpr int NACC = Acc<NP>::kN;
   static_assert(!GRID || CL == 1, "clusters are a batch-mode feature");
-  constexpr int NT = tile_cta_threads(MODEL, GRID), NW = NT / 32; // threads, warps of this CTA
+  constexpr int NT = tile_cta_threads(MODEL, MODE, GRID), NW = NT / 32; // threads, warps of this CTA
   static_assert(Acc<NP>::kN <= NT && kMaxParams <= NT, "one thread per accumulator / parameter");
   extern __shared__ __align__(128) uint8_t dyn_smem[];
   uint8_t *s_stage = dyn_smem;                                                    // [warps][kWarpStageBytes]
