@@ -375,11 +375,30 @@ def run_c3(args, w, with_cpu=True):
         line["cpu_baseline"] = {"value": nf / cs, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"first {nf} frame pairs of the sequence (pyramid + Newton_Raphson each)"}
         gp = np.array([[rows[k][f"parameter_{q}"] for q in range(6)] for k in range(nf)])
-        line["parity"] = {"vs_oracle_first_frames": parity_block(
+        blk = parity_block(
             gp, [rows[k]["chi"] for k in range(nf)], [rows[k]["iterations"] for k in range(nf)],
-            [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want]),
+            [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want])
+        line["parity"] = {"vs_oracle_first_frames": blk,
             "note": "GPU values are the 6-significant-digit CSV report rows of the first frames (constant-velocity guesses "
-                    "included); the oracle runs the same sequence with fp64 accumulators"}
+                    "included); the oracle runs the same sequence with fp64 accumulators. " + SELF_SPREAD_NOTE}
+        try:  # the reference's own arithmetic on the same frames (fp32 accumulators, 20 chunks), same guesses as the fp64 run
+            R = oracle.OracleEngine(n_threads=20, pyramid=w["pyramid"], accum_double=False)
+            R.set_image("und", frames[0])
+            refs = []
+            p, p_prev = np.zeros(6, np.float32), np.zeros(6, np.float32)
+            for k in range(nf):
+                R.set_image("def", frames[k + 1])
+                guess = p + (p - p_prev) if k else p
+                p_prev = p
+                refs.append(R.correlate(guess, xy))
+                p = want[k]["params"]
+            sp = parity_block([r["params"] for r in refs], [r["chi"] for r in refs], [r["iterations"] for r in refs],
+                              [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want])
+            sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same frames and guesses"
+            line["parity"]["reference_self_spread"] = sp
+            line["parity"]["chi_within_reference_self_spread"] = bool(blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * sp["max_rel_dchi"]))
+        except Exception as ex:
+            line["parity"]["reference_self_spread"] = {"error": repr(ex)}
     return line
 
 
@@ -860,7 +879,7 @@ def main():
                          "instructions, more accurate than the reference's own rounding noise, which is why its chi can sit "
                          "1e-5 away from the reference's); it is reported beside the headline, labelled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-records (c2 at N = 1, c5 at N > 1)")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-records (c2 and c3 at N = 1, c5 at N > 1)")
     ap.add_argument("--parity-sample", type=int, default=64, help="subsets compared with the oracle in the bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -992,6 +1011,12 @@ def main():
                 others["c2"] = other_workload_c2(args, peaks)
             except Exception as ex:
                 others["c2"] = {"error": repr(ex)}
+            try:  # frames/s, the second half of BASELINE's metric: the 100-frame sequence through the C++ host loop
+                sub = argparse.Namespace(**vars(args))
+                sub.steps, sub.warmup = max(2, min(args.steps, 4)), 1
+                others["c3"] = run_c3(sub, workload("c3"), with_cpu=not args.no_cpu_baseline)
+            except Exception as ex:
+                others["c3"] = {"error": repr(ex)}
         else:
             try:
                 rec = other_workload_c5(args, dist, rank, world, local_rank, peaks)
