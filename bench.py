@@ -117,8 +117,32 @@ def stratified_sample(n_units, n_sample):
 
 SELF_SPREAD_NOTE = ("within_tolerance applies the north-star numbers literally against the oracle with fp64 accumulators; "
                     "chi_within_reference_self_spread asks instead whether the GPU's chi is at most 1.5 x as far from that oracle as the "
-                    "reference's own fp32 arithmetic (20 thread chunks) is on the same input: chi of a large domain is not defined to 1e-5 by "
-                    "the reference (DESIGN.md section 5)")
+                    "reference's own fp32 arithmetic is on the same input in either of two builds (sums cut into 20 chunks, its default "
+                    "NUMBER_OF_THREADS, or into one): chi of a large domain is not defined to 1e-5 by the reference (DESIGN.md section 5)")
+
+
+def reference_spread(run_ref, want, gpu_block, what):
+    """The reference's OWN arithmetic against the fp64-accumulator oracle results `want` (list of result dicts):
+    run_ref(n_chunks) -> list of result dicts of the restatement with fp32 accumulators cut into n_chunks pieces, i.e. the
+    reference built with NUMBER_OF_THREADS = n_chunks (defines.hpp:10; 20 is its default, 1 a single-threaded build).
+    Returns the keys to merge into a parity record."""
+    cols = lambda rs: ([r["params"] for r in rs], [r["chi"] for r in rs], [r["iterations"] for r in rs])
+    evs = lambda rs: [r["evaluations"][:8] for r in rs]
+    out, worst = {}, 0.0
+    for chunks, key in ((20, "reference_self_spread"), (1, "reference_self_spread_one_chunk")):
+        try:
+            rs = run_ref(chunks)
+            sp = parity_block(*cols(rs), *cols(want), gpu_evals=evs(rs), want_evals=evs(want))
+            sp.pop("within_tolerance", None)
+            sp["what"] = (f"oracle with the reference's fp32 accumulators in {chunks} chunk(s) (NUMBER_OF_THREADS = {chunks}) vs the "
+                          f"oracle with fp64 accumulators, {what}")
+            out[key] = sp
+            worst = max(worst, sp["max_rel_dchi"])
+        except Exception as ex:
+            out[key] = {"error": repr(ex)}
+    out["chi_within_reference_self_spread"] = bool(gpu_block["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * worst))
+    out["note"] = SELF_SPREAD_NOTE
+    return out
 
 
 def parity_block(gpu_params, gpu_chi, gpu_iters, want_params, want_chi, want_iters, gpu_evals=None, want_evals=None, n_grad_to=6):
@@ -380,25 +404,20 @@ def run_c3(args, w, with_cpu=True):
             [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want])
         line["parity"] = {"vs_oracle_first_frames": blk,
             "note": "GPU values are the 6-significant-digit CSV report rows of the first frames (constant-velocity guesses "
-                    "included); the oracle runs the same sequence with fp64 accumulators. " + SELF_SPREAD_NOTE}
-        try:  # the reference's own arithmetic on the same frames (fp32 accumulators, 20 chunks), same guesses as the fp64 run
-            R = oracle.OracleEngine(n_threads=20, pyramid=w["pyramid"], accum_double=False)
+                    "included); the oracle runs the same sequence with fp64 accumulators"}
+        def ref_frames(chunks):  # the same frames and the fp64 run's guesses, fp32 accumulators
+            R = oracle.OracleEngine(n_threads=chunks, pyramid=w["pyramid"], accum_double=False)
             R.set_image("und", frames[0])
             refs = []
-            p, p_prev = np.zeros(6, np.float32), np.zeros(6, np.float32)
+            q, q_prev = np.zeros(6, np.float32), np.zeros(6, np.float32)
             for k in range(nf):
                 R.set_image("def", frames[k + 1])
-                guess = p + (p - p_prev) if k else p
-                p_prev = p
+                guess = q + (q - q_prev) if k else q
+                q_prev = q
                 refs.append(R.correlate(guess, xy))
-                p = want[k]["params"]
-            sp = parity_block([r["params"] for r in refs], [r["chi"] for r in refs], [r["iterations"] for r in refs],
-                              [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want])
-            sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same frames and guesses"
-            line["parity"]["reference_self_spread"] = sp
-            line["parity"]["chi_within_reference_self_spread"] = bool(blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * sp["max_rel_dchi"]))
-        except Exception as ex:
-            line["parity"]["reference_self_spread"] = {"error": repr(ex)}
+                q = want[k]["params"]
+            return refs
+        line["parity"].update(reference_spread(ref_frames, want, blk, "same frames and guesses"))
     return line
 
 
@@ -618,32 +637,29 @@ class Run:
         und, dfm = self.und_pin.numpy(), self.dfm_pin.numpy()
         kw = dict(model=oracle.FM_AFFINE, pyramid=w["pyramid"])
         o64 = oracle.OracleEngine(n_threads=os.cpu_count() or 1, accum_double=True, real_threads=True, **kw)
-        o32 = oracle.OracleEngine(n_threads=20, accum_double=False, real_threads=False, **kw)
-        for o in (o64, o32):
-            o.set_image("und", und)
-            o.set_image("def", dfm)
+        o64.set_image("und", und)
+        o64.set_image("def", dfm)
         ids = stratified_sample(len(self.all_boxes), n_sample)
-        want, ref = [], []
+        inputs = []
         for i in ids:
             bx = self.all_boxes[i]
-            args = (np.zeros(6, np.float32), oracle.rect_points(*bx))
-            c = ((bx[0] + bx[2]) / 2.0, (bx[1] + bx[3]) / 2.0)
-            want.append(o64.correlate(*args, center=c))
-            ref.append(o32.correlate(*args, center=c))
-        cols = lambda rs: ([r["params"] for r in rs], [r["chi"] for r in rs], [r["iterations"] for r in rs])
+            inputs.append(((np.zeros(6, np.float32), oracle.rect_points(*bx)), ((bx[0] + bx[2]) / 2.0, (bx[1] + bx[3]) / 2.0)))
+        want = [o64.correlate(*a, center=c) for a, c in inputs]
         evs = lambda rs: [r["evaluations"][:8] for r in rs]
-        blk = parity_block(records["resultingParameters"][ids, :6], records["chi"][ids], records["iterations"][ids], *cols(want),
+        blk = parity_block(records["resultingParameters"][ids, :6], records["chi"][ids], records["iterations"][ids],
+                           [r["params"] for r in want], [r["chi"] for r in want], [r["iterations"] for r in want],
                            gpu_evals=records["evaluationsPerLevel"][ids], want_evals=evs(want))
         blk["errors"] = [int((records["errorCode"][ids] != 0).sum()), int(sum(r["error_code"] != 0 for r in want))]
         blk["sample"] = f"{len(ids)} of {len(self.all_boxes)} subsets, stratified over the sector ids"
-        spread = parity_block(*cols(ref), *cols(want), gpu_evals=evs(ref), want_evals=evs(want))
-        spread.pop("within_tolerance")
-        spread["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same subsets"
-        chi_ok = blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * spread["max_rel_dchi"])
-        return {"vs_oracle": blk, "reference_self_spread": spread,
-                "chi_within_reference_self_spread": bool(chi_ok),
-                "note": "within_tolerance applies the north-star numbers literally; chi of a small subset is reproducible only to the "
-                        "reference's own spread (see reference_self_spread and DESIGN.md section 5)"}
+
+        def ref_subsets(chunks):
+            o32 = oracle.OracleEngine(n_threads=chunks, accum_double=False, real_threads=False, **kw)
+            o32.set_image("und", und)
+            o32.set_image("def", dfm)
+            return [o32.correlate(*a, center=c) for a, c in inputs]
+        out = {"vs_oracle": blk}
+        out.update(reference_spread(ref_subsets, want, blk, "same subsets"))
+        return out
 
     def close(self):
         try:
@@ -732,25 +748,15 @@ def single_domain_parity(run, last, threads):
                        gpu_evals=[last["evaluations"][:8]], want_evals=[dres["evaluations"][:8]])
     blk["evaluations"] = [last["evaluations"][: w["pyramid"][2] + 1], dres["evaluations"][: w["pyramid"][2] + 1]]
     out = {"vs_oracle": blk}
-    # the reference's own arithmetic (fp32 accumulators in NUMBER_OF_THREADS = 20 chunks, defines.hpp:10) against the
-    # same fp64-accumulator oracle: how far the CPU engine sits from exact sums on this domain
-    try:
-        orf = oracle.OracleEngine(model=oracle.FM_QUAD if w["model"] == "quad" else oracle.FM_AFFINE, n_threads=20,
+    def ref_domain(chunks):
+        orf = oracle.OracleEngine(model=oracle.FM_QUAD if w["model"] == "quad" else oracle.FM_AFFINE, n_threads=chunks,
                                   pyramid=w["pyramid"], accum_double=False)
         orf.set_image("und", und)
         orf.set_image("def", dfm)
         if d[0] == "rect":
-            rres = orf.correlate(np.zeros(n_par, np.float32), oracle.rect_points(*d[1:]), center=((d[1] + d[3]) / 2.0, (d[2] + d[4]) / 2.0))
-        else:
-            rres = orf.correlate(np.zeros(n_par, np.float32), oracle.annulus_points(*d[1:]))
-        sp = parity_block(rres["params"], rres["chi"], rres["iterations"], dres["params"], dres["chi"], dres["iterations"],
-                          gpu_evals=[rres["evaluations"][:8]], want_evals=[dres["evaluations"][:8]])
-        sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same domain"
-        out["reference_self_spread"] = sp
-        out["chi_within_reference_self_spread"] = bool(blk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * sp["max_rel_dchi"]))
-        out["note"] = SELF_SPREAD_NOTE
-    except Exception as ex:
-        out["reference_self_spread"] = {"error": repr(ex)}
+            return [orf.correlate(np.zeros(n_par, np.float32), oracle.rect_points(*d[1:]), center=((d[1] + d[3]) / 2.0, (d[2] + d[4]) / 2.0))]
+        return [orf.correlate(np.zeros(n_par, np.float32), oracle.annulus_points(*d[1:]))]
+    out.update(reference_spread(ref_domain, [dres], blk, "same domain"))
     return out
 
 
@@ -823,17 +829,12 @@ def other_workload_c5(args, dist, rank, world, local_rank, peaks):
             sblk["region"] = f"central {2 * hw + 1}^2 px of the 16384^2 pair, 5 levels, one GPU vs the oracle with fp64 accumulators"
             sblk["evaluations"] = [g["evaluations"][:5], want["evaluations"][:5]]
             rec["parity"]["sample_region_vs_oracle"] = sblk
-            # the reference's own arithmetic (fp32 accumulators, NUMBER_OF_THREADS = 20 chunks) on the same region
-            o32 = oracle.OracleEngine(model=oracle.FM_AFFINE, n_threads=20, pyramid=w["pyramid"], accum_double=False)
-            o32.set_image("und", run.und_pin.numpy())
-            o32.set_image("def", run.dfm_pin.numpy())
-            ref = o32.correlate(np.zeros(6, np.float32), oracle.rect_points(*box), center=(float(cx), float(cy)))
-            sp = parity_block(ref["params"], ref["chi"], ref["iterations"], want["params"], want["chi"], want["iterations"],
-                              gpu_evals=[ref["evaluations"][:8]], want_evals=[want["evaluations"][:8]])
-            sp["what"] = "oracle with the reference's fp32 accumulators (20 thread chunks) vs the oracle with fp64 accumulators, same region"
-            rec["parity"]["reference_self_spread"] = sp
-            rec["parity"]["chi_within_reference_self_spread"] = bool(sblk["max_rel_dchi"] <= max(TOLERANCES["rel_dchi"], 1.5 * sp["max_rel_dchi"]))
-            rec["parity"]["note"] = SELF_SPREAD_NOTE
+            def ref_region(chunks):
+                o32 = oracle.OracleEngine(model=oracle.FM_AFFINE, n_threads=chunks, pyramid=w["pyramid"], accum_double=False)
+                o32.set_image("und", run.und_pin.numpy())
+                o32.set_image("def", run.dfm_pin.numpy())
+                return [o32.correlate(np.zeros(6, np.float32), oracle.rect_points(*box), center=(float(cx), float(cy)))]
+            rec["parity"].update(reference_spread(ref_region, [want], sblk, "same region"))
         except Exception as ex:
             rec["parity"]["sample_region_vs_oracle"] = {"error": repr(ex)}
         e1.close()
