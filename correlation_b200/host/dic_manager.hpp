@@ -10,7 +10,9 @@
 //   initializeReport / addFrameToReport      :2473-2525, :2430-2471 (the CSV schema, verbatim columns)
 // Frames are raw u8 buffers (the reference decodes files with cv::imread; decoding is out of scope).
 #pragma once
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <future>
 #include <sstream>
@@ -395,11 +397,18 @@ public:
     bool error = false;
     error_ = false;
     const int total_frame_pairs = (int)frames.size() - 1;
+    // host-side phase times of the loop (DIC_HOST_PROFILE=1 prints them): rotation, prefetch start, the frame's
+    // sectors (guess + correlate + result), wait for the prefetch, report row
+    using clk = std::chrono::steady_clock;
+    double t_phase[5] = {0, 0, 0, 0, 0};
+    auto lap = [&](clk::time_point &t0, int k) { auto t1 = clk::now(); t_phase[k] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; };
     for (int frame = 0; frame < total_frame_pairs; ++frame) {
+      clk::time_point tp = clk::now();
       if (frame > 0) {
         if (cfg_.referenceImage == refImage_Previous) cuda_.makeUndPyramidFromDef(); // :192-195
         cuda_.makeDefPyramidFromNxt();                                               // :233-235
       }
+      lap(tp, 0);
       std::future<errorEnum> loader; // :1438-1447: next image upload + pyramid while this frame correlates
       const bool prefetch = frame + 2 < (int)frames.size() && frame > 0;
       errorEnum enqueue_rc = error_none;
@@ -407,16 +416,23 @@ public:
         enqueue_rc = cuda_.resetNextPyramidAsync(frames[frame + 2], rows, cols); // stream-ordered, no thread
       else if (prefetch)
         loader = std::async(std::launch::async, [&, frame] { return cuda_.resetNextPyramid(frames[frame + 2], rows, cols); });
+      lap(tp, 1);
       switch (cfg_.domain_type) {
       case domain_rectangular: error = frame_rectangular(frame); break;
       case domain_annular: error = frame_annular(frame); break;
       default: error = frame_blob(frame); break;
       }
+      lap(tp, 2);
       if (prefetch && (cfg_.async_next_image ? enqueue_rc : loader.get()) != error_none) error = error_ = true; // :1469-1474 (error_multiThread)
+      lap(tp, 3);
       addFrameToReport(frame, name(cfg_.referenceImage == refImage_First ? 0 : frame), name(frame + 1));
       frames_done_ = frame + 1;
+      lap(tp, 4);
       if (error && cfg_.error_handling_mode == errorMode_stopAll) break; // :1493
     }
+    if (std::getenv("DIC_HOST_PROFILE"))
+      std::fprintf(stderr, "dic_host phases over %d frame pairs (ms): rotate %.3f, prefetch start %.3f, sectors %.3f, prefetch wait %.3f, report %.3f\n",
+                   frames_done_, 1e3 * t_phase[0], 1e3 * t_phase[1], 1e3 * t_phase[2], 1e3 * t_phase[3], 1e3 * t_phase[4]);
     return error;
   }
 };
