@@ -613,6 +613,7 @@ struct UnitPlan {
   int nr;           // rows of the unit (0: nothing to do)
   uint32_t colmask; // this lane's column of the membership mask: bit r <=> pixel (x0 + lane, y0 + r)
   int px0, py0;     // origin of the staged deformed-image patch
+  int pxr, pxe, pye; // raw (un-aligned) first column, exclusive end column / row of the footprint the patch must hold
   bool full, staged;
 };
 
@@ -639,7 +640,7 @@ __device__ __forceinline__ UnitPlan plan_unit(const TileHead &th, int r0, int r1
   UnitPlan q;
   uint32_t col = (th.col >> r0) & low_bits(r1 - r0);
   const uint32_t any = __reduce_or_sync(0xffffffffu, col); // rows of the range some lane owns
-  if (any == 0u) { q.nr = 0; q.x0 = q.y0 = q.px0 = q.py0 = 0; q.colmask = 0; q.full = q.staged = false; return q; }
+  if (any == 0u) { q.nr = 0; q.x0 = q.y0 = q.px0 = q.py0 = q.pxr = q.pxe = q.pye = 0; q.colmask = 0; q.full = q.staged = false; return q; }
   int lo = __ffs(any) - 1, hi = 32 - __clz(any);
   if (GRAN > 1) { lo &= ~(GRAN - 1); hi = (hi + GRAN - 1) & ~(GRAN - 1); }
   r0 += lo;
@@ -675,9 +676,10 @@ __device__ __forceinline__ UnitPlan plan_unit(const TileHead &th, int r0, int r1
   }
   // staged window: columns [px0, px0 + kPatchW), rows [py0, py0 + kPatchH) must hold every 4 x 4 window
   const bool inside = bx0 > 1.f && by0 > 1.f && bx1 < (float)def.cols - 2.f && by1 < (float)def.rows - 2.f;
-  q.px0 = ((int)floorf(bx0) - 1) & ~15; q.py0 = (int)floorf(by0) - 1;
-  const int pxe = (int)floorf(bx1) + 3, pye = (int)floorf(by1) + 3; // exclusive
-  q.staged = inside && pxe - q.px0 <= kPatchW && pye - q.py0 <= kPatchH;
+  q.pxr = (int)floorf(bx0) - 1;
+  q.px0 = q.pxr & ~15; q.py0 = (int)floorf(by0) - 1;
+  q.pxe = (int)floorf(bx1) + 3; q.pye = (int)floorf(by1) + 3; // exclusive
+  q.staged = inside && q.pxe - q.px0 <= kPatchW && q.pye - q.py0 <= kPatchH;
   return q;
 }
 
@@ -696,6 +698,42 @@ __device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, con
   }
 }
 
+// ---- speculative staging of the NEXT evaluation's first unit (DIC_SPECULATE, OFF: measured, no gain).
+// An evaluation starts with a chain nothing can overlap: tile record from L2 (~0.4 us) -> plan -> TMA of the first unit
+// (~1 us) -> first pixel. It is paid 10-18 times per solve, and the small domains (c1, c3) and the coarse levels of
+// every domain spend a third of an evaluation in it. Most evaluations follow one at the SAME level with parameters that
+// moved by a fraction of a pixel, so at the end of a pass every warp stages the first unit of its range again, planned
+// with the parameters it has (box moved up by up to two rows / left by one 16-byte step where the footprint leaves
+// room). The next pass plans with the real parameters; if its footprint lies inside the box that is already in shared
+// memory it starts computing at once, otherwise (level change, large step, next sector) the copy is awaited and
+// dropped. The pixels read are the same either way: results do not change by a bit (GPU suite green with it on).
+// Measured on B200 with it on / off: c1 0.106 / 0.101 ms, c2 0.527 / 0.515, c3 0.137 / 0.134, c4 2.231 / 2.176, c5 4.98 / 5.06:
+// the chain it removes is shorter than it looked (the level data is L2-resident: a TMA lands in ~0.5 us) and the second
+// plan_unit plus the slot traffic sit on the same critical path, before the barrier. Kept as a compile-time option.
+#ifndef DIC_SPECULATE
+#define DIC_SPECULATE 0
+#endif
+struct SpecSlot {           // one per warp, in shared memory (keeps the hot loop's registers free)
+  int pending;              // a speculative copy was issued and has not been consumed or dropped
+  int level, quad_begin;    // what it was planned for
+  const Tile *tiles;        // identity of the sector's tile list at that level
+  int px0, py0;             // origin of the staged box
+  int x0, y0;               // TileHead of the first tile (col per lane below)
+  uint32_t full_rows;
+  uint32_t col[32];
+};
+__device__ __forceinline__ void spec_drop(WarpStage &st, SpecSlot *sp, int *timeout_flag) {
+  // warp-uniform: sp->pending is written by lane 0 and read after a __syncwarp
+  if (sp->pending) {
+    const bool landed = mbar_wait(st.bar + (st.consumed & 1), (st.consumed >> 1) & 1);
+    ++st.consumed;
+    if (!landed && (threadIdx.x & 31) == 0) atomicExch(timeout_flag, 1);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) sp->pending = 0;
+    __syncwarp();
+  }
+}
+
 // ---- one evaluation over a range of QUADS (4 consecutive rows of a tile; 4 quads per tile, tiles in column-major
 // strip order) of one level. The partition of a level over warps is in quads, so that every warp gets the same
 // number of pixel rows to within four -- a whole-tile granule left some warps with 8 tiles and others with 7
@@ -705,7 +743,7 @@ __device__ __forceinline__ void issue_unit(WarpStage &st, const UnitPlan &q, con
 template <int MODEL, int MODE, bool BATCH>
 __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const TileMaps &maps, float cx0, float cy0,
                                                const TileLevel tl, int level, const float *p,
-                                               int quad_begin, int quad_end, WarpStage &st,
+                                               int quad_begin, int quad_end, WarpStage &st, SpecSlot *spec,
                                                float *warp_acc, unsigned int *slow_counter, int *timeout_flag) {
   constexpr int NP = model_nparams(MODEL);
   constexpr int GRAN = MODE == DIC_MODE_PARITY ? (DIC_PARITY_LOOP == 3 ? 2 : 1) : 4;
@@ -744,11 +782,36 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
   };
   UnitPlan nxt;
   nxt.nr = 0;
-  if (quad_begin < quad_end) {
+  bool reuse = false;
+  if (DIC_SPECULATE && spec->pending) {
+    if (quad_begin < quad_end && spec->level == level && spec->quad_begin == quad_begin && spec->tiles == tl.tiles) {
+      int r0, r1;
+      rows_of(t_first, r0, r1);
+      TileHead h;
+      h.x0 = spec->x0; h.y0 = spec->y0; h.full_rows = spec->full_rows; h.col = spec->col[lane];
+      nxt = plan_unit<NP, GRAN>(h, r0, r1, p, ccx, ccy, def);
+      const int sx0 = spec->px0, sy0 = spec->py0;
+      // the footprint under the real parameters must lie inside the box that was staged (warp-uniform: plan values are)
+      if (nxt.nr > 0 && nxt.staged && nxt.pxr >= sx0 && nxt.pxe <= sx0 + kPatchW && nxt.py0 >= sy0 && nxt.pye <= sy0 + kPatchH) {
+        nxt.px0 = sx0; nxt.py0 = sy0;
+        reuse = true;
+        __syncwarp();
+        if (lane == 0) spec->pending = 0; // consumed by the unit loop below like any staged unit
+        __syncwarp();
+      }
+    }
+    if (!reuse) spec_drop(st, spec, timeout_flag);
+  }
+  if (!reuse && quad_begin < quad_end) {
     int r0, r1;
     rows_of(t_first, r0, r1);
-    nxt = plan_unit<NP, GRAN>(load_tile_head(tl, t_first), r0, r1, p, ccx, ccy, def);
+    const TileHead head_first = load_tile_head(tl, t_first);
+    nxt = plan_unit<NP, GRAN>(head_first, r0, r1, p, ccx, ccy, def);
     issue_unit(st, nxt, map_def, map_und);
+    if (DIC_SPECULATE) { // parked in the warp's slot for the end of this pass (not in registers across the pixel loop)
+      spec->col[lane] = head_first.col;
+      if (lane == 0) { spec->x0 = head_first.x0; spec->y0 = head_first.y0; spec->full_rows = head_first.full_rows; }
+    }
   }
   TileHead head_next = {0, 0, 0u, 0u}; // record of tile t + 1, in flight while tile t - 1 ... t is evaluated
   if (quad_begin < quad_end && t_first + 1 <= t_last) head_next = load_tile_head(tl, t_first + 1);
@@ -917,6 +980,26 @@ __device__ __forceinline__ void evaluate_tiles(const SolveSettings &cfg, const T
       }
     }
   }
+  if (DIC_SPECULATE && quad_begin < quad_end && !__shfl_sync(0xffffffffu, *(volatile int *)timeout_flag, 0)) {
+    // stage the first unit of this range again for the next evaluation (see SpecSlot), before the flush below
+    int r0, r1;
+    rows_of(t_first, r0, r1);
+    __syncwarp();
+    TileHead h;
+    h.x0 = spec->x0; h.y0 = spec->y0; h.full_rows = spec->full_rows; h.col = spec->col[lane];
+    UnitPlan q = plan_unit<NP, GRAN>(h, r0, r1, p, ccx, ccy, def);
+    if (q.nr > 0 && q.staged) {
+      const int room_y = kPatchH - (q.pye - q.py0);
+      q.py0 -= min(2, room_y >> 1);
+      if (q.pxr - q.px0 < 2 && q.pxe - (q.px0 - 16) <= kPatchW) q.px0 -= 16;
+      issue_unit(st, q, map_def, map_und);
+      if (lane == 0) {
+        spec->pending = 1; spec->level = level; spec->quad_begin = quad_begin; spec->tiles = tl.tiles;
+        spec->px0 = q.px0; spec->py0 = q.py0;
+      }
+      __syncwarp();
+    }
+  }
   if (cur_x0 != INT_MIN) flush_moments<NP>(mom, X, warp_acc);
 }
 
@@ -1010,6 +1093,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
   float *s_wacc = reinterpret_cast<float *>(dyn_smem + NW * kWarpStageBytes);     // [warps][NACC]
   __shared__ SolveShared<NP> sh;
   __shared__ __align__(8) uint64_t s_bar[NW][2];
+  __shared__ SpecSlot s_spec[NW];
   __shared__ SectorTiles s_tiles; // this sector's tile lists and centre: read once, not once per evaluation
   __shared__ float s_center[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1024,6 +1108,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (lane == 0) s_spec[warp].pending = 0;
   if (tid == 0) { sh.xch_count = 0; sh.timed_out = 0; } // timed_out is sticky for the rest of the launch
   __syncwarp();
   const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
@@ -1068,7 +1153,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
         // balanced contiguous ranges: the first (n_quads % nw) warps take one quad more
         const int base = n_quads / nw, rem = n_quads - base * nw;
         const int qb = wg * base + min(wg, rem), qe = qb + base + (wg < rem ? 1 : 0);
-        evaluate_tiles<MODEL, MODE, !GRID>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, qb, qe, st,
+        evaluate_tiles<MODEL, MODE, !GRID>(cfg, maps, s_center[0], s_center[1], tl, level, sh.p, qb, qe, st, &s_spec[warp],
                                     warp_acc, GRID ? &work->slow_units : nullptr, &sh.timed_out);
         if (tl.n_extra > 0 && wg == 0)
           evaluate_extras<MODEL, MODE>(cfg, s_center[0], s_center[1], tl, level, sh.p, warp_acc);
@@ -1095,6 +1180,7 @@ gn_solve_tiles_kernel(const SolveSettings cfg, const __grid_constant__ TileMaps 
     __syncthreads();
     si = GRID ? n_sectors : kQueue ? s_next_sector : si + n_groups;
   }
+  if (DIC_SPECULATE) spec_drop(st, &s_spec[warp], &sh.timed_out); // no bulk copy may be in flight when the CTA exits
   if (GRID) grid_depart<NACC>(work, sh.rs_seq, sh.rowsplit != 0);
   if (kQueue && tid == 0) { // the last CTA to leave re-arms the ticket counter for the next launch
     __threadfence();
