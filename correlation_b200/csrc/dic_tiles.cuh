@@ -1065,8 +1065,8 @@ __device__ __forceinline__ void evaluate_extras(const SolveSettings &cfg, float 
 #ifndef DIC_GRID_QUAD_ONE_CTA
 #define DIC_GRID_QUAD_ONE_CTA 1
 #endif
-__host__ __device__ constexpr bool tile_grid_one_cta(int model, int mode) {
-  return DIC_GRID_QUAD_ONE_CTA && model == DIC_FM_QUADRATIC && mode >= 0;
+__host__ __device__ constexpr bool tile_grid_one_cta(int model, int /*mode: both arithmetic modes gain*/) {
+  return DIC_GRID_QUAD_ONE_CTA && model == DIC_FM_QUADRATIC;
 }
 __host__ __device__ constexpr int tile_cta_threads(int model, int mode, bool grid) {
   return grid ? (tile_grid_one_cta(model, mode) ? 384 : DIC_GRID_THREADS)
