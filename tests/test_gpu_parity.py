@@ -707,6 +707,34 @@ def test_cta_pair_batch_equals_single_cta_batch(eng):
     eng.set_arith_mode(engine.MODE_PARITY)
 
 
+def test_batch_records_do_not_depend_on_the_cta_assignment(eng):
+    """More subsets than CTA slots (592 on a B200): every CTA takes its first subset by index and every further one
+    from the launch-wide ticket counter, so WHICH CTA solves a subset differs from launch to launch and from the
+    two half-size launches below -- the records must not: a subset is solved by one CTA with one instruction
+    sequence. (This is what makes the 8-GPU result of bench.py equal the 1-GPU result bit for bit.)"""
+    truth = (0.9, -0.4, 0.001, -0.0005, 0.0005, 0.001)
+    und, dfm = synth.make_pair(1536, 1536, 43, truth, center=(768, 768))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    boxes = [(40 + 48 * i, 40 + 48 * j, 40 + 48 * i + 46, 40 + 48 * j + 46) for i in range(30) for j in range(30)]  # 900 subsets of 47^2
+    assert eng.resetPolygonRectGrid(0, np.array(boxes, np.int32)) == 0
+    eng.set_cluster_mode(1)
+    try:
+        zero = np.zeros((len(boxes), 6), np.float32)
+        _, all_a = eng.correlate_batch_raw(0, zero)
+        _, all_b = eng.correlate_batch_raw(0, zero)
+        _, first = eng.correlate_batch_raw(0, zero[:450])
+        _, second = eng.correlate_batch_raw(450, zero[450:])
+    finally:
+        eng.set_cluster_mode(0)
+    assert (all_a["errorCode"] == 0).all()
+    assert all_a.tobytes() == all_b.tobytes()
+    assert all_a[:450].tobytes() == first.tobytes() and all_a[450:].tobytes() == second.tobytes()
+    d = np.abs(all_a["resultingParameters"][:, :2] - np.array(truth[:2]))  # every subset sees the field at its own centre
+    assert np.median(d.max(1)) < 0.8  # (|gradient| x |offset from the image centre| <= 0.73 px here)
+
+
 def test_flat_and_gradient_free_patches_follow_the_reference_qr(eng):
     """Rank-deficient normal equations (correlation_class.cpp:742-747, Eigen colPivHouseholderQr):
     * a textureless subset (A = 0, b = 0): Eigen does not truncate an all-zero matrix, the step is NaN, the next
