@@ -877,6 +877,43 @@ def test_full_size_c4_256_subsets_vs_oracle(eng):
     assert (rel_ref > TOL_CHI).sum() >= 1  # the spread is the algorithm's, not the GPU's: the reference shows it against itself
 
 
+def test_full_size_c5_whole_domain_and_sample_region_vs_oracle(eng):
+    """BASELINE config 5 at full size on one GPU: 16384^2 large-deformation pair, one 15361^2 domain (236 M pixels),
+    pyramid 0..4. (a) The whole domain recovers the truth of the synthetic field; (b) a sample region (central 1921^2,
+    3.7 M pixels, all five levels) against the oracle with fp64 accumulators -- the 64-bit restatement, because the
+    reference's own coefficient-cache index overflows at this image size (pyramid_class.cpp:180-187).
+    chi: the reference's fp32 arithmetic (20 chunks) sits 3.9e-5 from that oracle on this region (bench.py,
+    other_workloads.c5.parity.reference_self_spread), the GPU 4.2e-5 -- gated at 1e-4."""
+    import torch
+    import bench
+    w = bench.workload("c5")
+    und_t, dfm_t = bench.make_images(w, torch.device("cuda", 0))
+    n = w["rows"]
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramidsDevice(und_t.data_ptr(), dfm_t.data_ptr(), None, n, n, n, pyramid=w["pyramid"])
+    d = w["domain"]
+    try:
+        assert eng.resetPolygon(0, d[1], d[2], d[3], d[4]) == 0
+        whole = eng.correlate(0, np.zeros(6, np.float32))
+        assert whole["error_code"] == 0 and whole["number_of_points"] == (d[3] - d[1] + 1) * (d[4] - d[2] + 1)
+        truth = np.array(w["truth"], np.float32)
+        dt = np.abs(whole["params"] - truth)
+        assert dt[:2].max() < 5e-3 and dt[2:].max() < 2e-6, (whole["params"], truth)  # u8 quantisation of the field, not the solver
+        cx, cy = (d[1] + d[3]) // 2, (d[2] + d[4]) // 2
+        hw = (d[3] - d[1]) // 16
+        box = (cx - hw, cy - hw, cx + hw, cy + hw)
+        assert eng.resetPolygon(1, *box) == 0
+        got = eng.correlate(1, np.zeros(6, np.float32))
+    finally:
+        mono = np.zeros((64, 64), np.uint8)
+        eng.resetImagePyramids(mono, mono, pyramid=(0, 1, 2))  # give the 16384^2 pyramids back before the next test
+    o = make_oracle(und_t.cpu().numpy(), dfm_t.cpu().numpy(), n_threads=20, pyramid=w["pyramid"], accum_double=True, real_threads=True)
+    want = o.correlate(np.zeros(6), oracle.rect_points(*box), center=(float(cx), float(cy)))
+    assert got["evaluations"][:5] == want["evaluations"][:5], (got["evaluations"], want["evaluations"])
+    check_result(got, want, tol_chi=1e-4)
+
+
 # ---------------------------------------------------------------- three-channel colour images (SURVEY 8 f3)
 
 @pytest.mark.parametrize("iname,interp", [("nearest", engine.IM_NEAREST), ("bilinear", engine.IM_BILINEAR), ("bicubic", engine.IM_BICUBIC)])
