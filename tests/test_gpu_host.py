@@ -225,3 +225,26 @@ def test_error_handling_modes(mode, frames_done, sector3_done):
     assert int(last[2]["error_code"]) == 2
     assert (int(last[3]["number_of_points"]) > 0) == sector3_done
     assert int(last[0]["frame"]) == frames_done - 1
+
+
+def test_full_size_c3_sequence_vs_oracle_and_truth():
+    """BASELINE config 3 at full size through the C++ host loop (bench.run_c3): 100 frames of 2048^2, 64-vertex star
+    blob (1.54 M pixels), Eulerian + first-image reference, constant-velocity guesses. The first frame pairs against
+    the oracle run of the same sequence (fp64 accumulators; displacement / gradients / iterations at the BASELINE
+    tolerances, chi up to the reference's own spread over its two builds), the last pair against the truth of the
+    synthetic sequence, and no frame may report an error."""
+    import argparse
+    import bench
+    w = bench.workload("c3")
+    args = argparse.Namespace(steps=1, warmup=0, mode="parity")
+    line = bench.run_c3(args, w, with_cpu=True)
+    assert line["config"]["errors"] == 0 and line["config"]["frame_pairs"] == 99
+    blk = line["parity"]["vs_oracle_first_frames"]
+    assert blk["units_on_oracle_lm_path"] == blk["units_compared"] == 4
+    assert blk["max_abs_duv"] < 1e-4 and blk["max_abs_dgrad"] < 1e-6 and blk["max_abs_diterations"] <= 1, blk
+    assert line["parity"]["chi_within_reference_self_spread"], line["parity"]
+    got, truth = np.array(line["config"]["last_frame_params"]), np.array(line["config"]["last_frame_truth"])
+    # the parameters are about the reference's sequential-fp32 centre of the blob list, about a pixel off the geometric
+    # centre the synthetic field is defined about: u, v of a rotating field differ by (gradient x offset)
+    assert np.abs(got[:2] - truth[:2]).max() < 1.5 and np.abs(got[2:] - truth[2:]).max() < 2e-5, (got, truth)
+    assert line["value"] > 500.0  # frames / s end to end; the CPU oracle does ~10
