@@ -80,8 +80,11 @@ struct dic_engine {
   cudaEvent_t ev_rot = nullptr; // correlation-stream position at the last pyramid rotation (see dic_reset_next_pyramid)
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr; // around the whole GPU side of a correlate (copies included)
   float last_step_ms = 0.f;
-  PyramidSlot pyr[5];
-  int role[5] = {0, 1, 2, 3, 4}; // role (0 und, 1 def, 2 nxt, 3 / 4 staged und / def of the next pair) -> slot
+  PyramidSlot pyr[7];
+  // role (0 und, 1 def, 2 nxt, 3 / 4 staged und / def of the next pair, 5 / 6 of the pair after it) -> slot
+  int role[7] = {0, 1, 2, 3, 4, 5, 6};
+  int staged = 0;                      // pairs staged and not yet advanced to (0..2)
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}; // image-stream position behind the pyramid build of staged pair 0 / 1
   int start = 0, step = 1, stop = 0;
   int max_iters = 50;
   float precision = 1e-3f;
@@ -110,6 +113,12 @@ struct dic_engine {
   float *h_guess = nullptr;        // pinned + mapped: batch kernels read their guesses from here (zero-copy)
   float *h_guess_dev = nullptr;    // device-side address of h_guess
   int cluster_mode = 0;            // batch launches: 0 auto, 1 one CTA per sector, 2 one CTA pair per sector
+  // diagnostics (dic_pipe_trace): device-time marks of the staged-pair pipeline
+  static constexpr int kTrace = 48;
+  bool trace_on = false;
+  int trace_stage = 0, trace_solve = 0;
+  cudaEvent_t trace_base = nullptr, trace_st[kTrace][4] = {}, trace_so[kTrace][2] = {};
+  int batch_queue = 0;             // batch launches: 0 auto, 1 resident CTAs + ticket queue, 2 one CTA per sector (dic_set_batch_queue)
   // device blocks shared by the sectors of one dic_reset_polygon_rect_grid call, keyed by its first sector id:
   // rebuilding the same range reuses (or regrows) its blocks, another range gets its own
   struct GridBlock { int first_id = 0; void *lists = nullptr, *tiles = nullptr, *desc = nullptr; size_t cap_lists = 0, cap_tiles = 0, cap_desc = 0; };
@@ -740,7 +749,13 @@ int launch_solve_tiles(dic_engine *e, bool grid_mode, int first, int count) {
       lc.attrs = at; lc.numAttrs = 1;
       CU_TRY(e, cudaLaunchKernelEx(&lc, kern2, cfg, maps, sectors, stiles, guesses, g0, results, first, count, work));
     } else {
-      int grid = (int)std::max(1L, std::min((long)count, slots));
+      // Resident CTAs with a ticket queue never leave before the launch ends, and they fill the register file: a
+      // kernel of another stream (the next pair's pyramid build) waits for the whole solve. One CTA per sector lets
+      // the block scheduler interleave it (the ticket of such a CTA is past the end: it leaves after its sector).
+      // Measured on c4 (tools/probe_pipe.py): with two pairs staged ahead the step is bound by the PCIe transfer
+      // either way (2.45 ms), and the resident kernel is within 1.5 % in both forms: the ticket queue stays the default.
+      const bool per_sector = e->batch_queue == 2;
+      int grid = (int)std::max(1L, per_sector ? (long)count : std::min((long)count, slots));
       kern1<<<grid, NTB, smem, e->stream>>>(cfg, maps, sectors, stiles, guesses, g0, results, first, count, work);
     }
     CU_TRY(e, cudaGetLastError());
@@ -838,8 +853,13 @@ dic_engine *dic_create(int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return nullptr; }
   e->num_sms = prop.multiProcessorCount;
-  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&e->img_stream, cudaStreamNonBlocking) == cudaSuccess &&
+  // The image stream outranks the correlation stream: when a batch solve runs one CTA per sector, the block scheduler
+  // hands freed CTA slots to the next pair's pyramid build first, so that build hides inside the solve instead of
+  // queueing behind it (dic_set_batch_queue).
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  bool ok = cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&e->img_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_copy_und, cudaEventDisableTiming) == cudaSuccess &&
@@ -847,7 +867,9 @@ dic_engine *dic_create(int device) {
             cudaEventCreate(&e->ev_step0) == cudaSuccess && cudaEventCreate(&e->ev_step1) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_gn, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_rot, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&e->ev_rot, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_ready[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_ready[1], cudaEventDisableTiming) == cudaSuccess;
   e->max_grid = e->num_sms * 8;
   ok = ok && cudaMalloc(&e->d_work, sizeof(GridWork)) == cudaSuccess &&
        cudaMemset(e->d_work, 0, sizeof(GridWork)) == cudaSuccess &&
@@ -883,8 +905,14 @@ void dic_destroy(dic_engine *e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_img) cudaEventDestroy(e->ev_img);
+  if (e->trace_base) {
+    cudaEventDestroy(e->trace_base);
+    for (auto &r : e->trace_st) for (auto &ev : r) cudaEventDestroy(ev);
+    for (auto &r : e->trace_so) for (auto &ev : r) cudaEventDestroy(ev);
+  }
   if (e->ev_gn) cudaEventDestroy(e->ev_gn);
   if (e->ev_rot) cudaEventDestroy(e->ev_rot);
+  for (auto &ev : e->ev_ready) if (ev) cudaEventDestroy(ev);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   if (e->ev_copy_und) cudaEventDestroy(e->ev_copy_und);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
@@ -929,6 +957,7 @@ static int set_pyramid_range(dic_engine *e, int start, int step, int stop) {
     // re-runs resetPolygon after a pyramid change as well, mainapp.cpp:900-912)
     for (auto &s : e->sectors) { s.kind = SK_NONE; clear_levels(s); }
     for (auto &p : e->pyr) p.valid = false;
+    e->staged = 0;
   }
   e->start = start; e->step = step; e->stop = stop;
   return DIC_OK;
@@ -1049,14 +1078,23 @@ static int stage_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def
   row_begin = std::max(0, row_begin); row_end = std::min(rows, row_end);
   if (row_end <= row_begin) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
-  // the staging slots may still be read by solves enqueued before the last dic_advance_pair
-  CU_TRY(e, cudaEventRecord(e->ev_gn, e->stream));
+  if (e->staged >= 2) {
+    set_error(e, "two pairs are staged already: dic_advance_pair first");
+    return DIC_ERROR_BAD_ARGUMENT;
+  }
+  const int pos = e->staged; // 0: roles 3 / 4, 1: roles 5 / 6
+  // The staging slots were the und / def slots until the last dic_advance_pair and may still be read by the solves
+  // enqueued before it: ev_gn was recorded there, in front of that call's wait for the image stream. (Recording it
+  // here instead made this pair's transfer wait for the previous pair's pyramid build as well, through the
+  // correlation stream: 0.11 ms of idle bus per c4 step.) An event never recorded is a no-op to wait for.
   CU_TRY(e, cudaStreamWaitEvent(e->copy_stream, e->ev_gn, 0));
+  const int ti = e->trace_on && e->trace_stage < dic_engine::kTrace ? e->trace_stage++ : -1;
+  if (ti >= 0) cudaEventRecord(e->trace_st[ti][0], e->copy_stream);
   // transfers on the copy stream, pyramid kernels on the image stream: the next pair's transfer does
   // not queue behind this pair's pyramid build
   int rc;
   for (int k = 0; k < 2; ++k) {
-    PyramidSlot &s = e->pyr[e->role[3 + k]];
+    PyramidSlot &s = e->pyr[e->role[3 + 2 * pos + k]];
     if ((rc = shape_slot(e, s, rows, cols, e->stop))) return rc;
     const uint8_t *src = (k == 0 ? und : def) + (size_t)row_begin * cols;
     uint8_t *dst = const_cast<uint8_t *>(s.lev[0].ptr) + (size_t)row_begin * s.lev[0].pitch;
@@ -1067,11 +1105,15 @@ static int stage_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *def
       CU_TRY(e, cudaMemcpy2DAsync(dst, s.lev[0].pitch, src, cols, cols, nr, cudaMemcpyHostToDevice, e->copy_stream));
     // one event per image: the reference image's pyramid is built while the deformed image is still on the bus
     CU_TRY(e, cudaEventRecord(k == 0 ? e->ev_copy_und : e->ev_copy, e->copy_stream));
+    if (ti >= 0) cudaEventRecord(e->trace_st[ti][1 + k], e->copy_stream);
   }
   for (int k = 0; k < 2; ++k) {
     CU_TRY(e, cudaStreamWaitEvent(e->img_stream, k == 0 ? e->ev_copy_und : e->ev_copy, 0));
-    if ((rc = build_levels(e, e->pyr[e->role[3 + k]], e->stop, e->img_stream, row_begin, row_end))) return rc;
+    if ((rc = build_levels(e, e->pyr[e->role[3 + 2 * pos + k]], e->stop, e->img_stream, row_begin, row_end))) return rc;
   }
+  CU_TRY(e, cudaEventRecord(e->ev_ready[pos], e->img_stream));
+  e->staged = pos + 1;
+  if (ti >= 0) cudaEventRecord(e->trace_st[ti][3], e->img_stream);
   return DIC_OK;
 }
 int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols) {
@@ -1084,16 +1126,23 @@ int dic_stage_next_pair_rows(dic_engine *e, const uint8_t *und, const uint8_t *d
 int dic_advance_pair(dic_engine *e) {
   if (!e) return DIC_ERROR_BAD_ARGUMENT;
   cudaSetDevice(e->device);
-  if (!e->pyr[e->role[3]].valid || !e->pyr[e->role[4]].valid) {
+  if (e->staged < 1 || !e->pyr[e->role[3]].valid || !e->pyr[e->role[4]].valid) {
     set_error(e, "dic_advance_pair without a staged pair");
     return DIC_ERROR_BAD_ARGUMENT;
   }
-  CU_TRY(e, cudaEventRecord(e->ev_img, e->img_stream));
-  CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_img, 0));
+  CU_TRY(e, cudaEventRecord(e->ev_gn, e->stream)); // every solve that reads the slots about to become staging slots
+  // the solves that follow wait for THIS pair's pyramids only, not for a second staged pair still on the bus
+  CU_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_ready[0], 0));
   std::swap(e->role[0], e->role[3]);
   std::swap(e->role[1], e->role[4]);
   e->pyr[e->role[3]].valid = false;
   e->pyr[e->role[4]].valid = false;
+  if (e->staged == 2) { // the second staged pair moves up; the released slots become the far staging pair
+    std::swap(e->role[3], e->role[5]);
+    std::swap(e->role[4], e->role[6]);
+    std::swap(e->ev_ready[0], e->ev_ready[1]);
+  }
+  e->staged--;
   return DIC_OK;
 }
 
@@ -1423,6 +1472,11 @@ int dic_reset_polygon_rect_grid(dic_engine *e, int first_id, int n, const int *b
 }
 
 int dic_last_cluster_size(const dic_engine *e) { return e ? e->last_cluster : 0; }
+int dic_set_batch_queue(dic_engine *e, int mode) {
+  if (!e || mode < 0 || mode > 2) return DIC_ERROR_BAD_ARGUMENT;
+  e->batch_queue = mode;
+  return DIC_OK;
+}
 int dic_set_cluster_mode(dic_engine *e, int mode) {
   if (!e || mode < 0 || mode > 2) return DIC_ERROR_BAD_ARGUMENT;
   e->cluster_mode = mode;
@@ -1713,10 +1767,13 @@ static int enqueue_correlate(dic_engine *e, int first, int count, const float *g
   }
   CU_TRY(e, cudaEventRecord(e->ev_step0, e->stream));
   CU_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  const int tj = e->trace_on && e->trace_solve < dic_engine::kTrace ? e->trace_solve++ : -1;
+  if (tj >= 0) cudaEventRecord(e->trace_so[tj][0], e->stream);
   rc = tiles_applicable(e, first, count) ? launch_solve_tiles_any(e, grid_mode, first, count)
                                          : launch_solve_any(e, grid_mode, first, count);
   if (rc) return rc;
   CU_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  if (tj >= 0) cudaEventRecord(e->trace_so[tj][1], e->stream);
   e->timing_pending = true;
   // no download: the result records are written by the kernel into the pinned, mapped block the host reads after
   // the stream has drained (a D2H copy of 176 B cost ~10 us of copy-engine latency per correlate)
@@ -1764,6 +1821,18 @@ int dic_correlate(dic_engine *e, int id, float *guess_inout, dic_result *out) {
   int rc = dic_correlate_async(e, id, guess_inout);
   if (rc) return rc;
   return collect(e, id, 1, guess_inout, out);
+}
+int dic_correlate_batch_async(dic_engine *e, int first, int n, const float *guesses) {
+  if (!e || !guesses || n <= 0) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  return enqueue_correlate(e, first, n, guesses, false);
+}
+int dic_correlate_batch_wait(dic_engine *e, int first, int n, float *guesses_out, dic_result *results) {
+  if (!e || n <= 0) return DIC_ERROR_BAD_ARGUMENT;
+  for (int i = 0; i < n; ++i)
+    if (!sector_ok(e, first + i)) return DIC_ERROR_BAD_ARGUMENT;
+  cudaSetDevice(e->device);
+  return collect(e, first, n, guesses_out, results);
 }
 int dic_correlate_batch(dic_engine *e, int first, int n, float *guesses_inout, dic_result *results) {
   if (!e || !guesses_inout || n <= 0) return DIC_ERROR_BAD_ARGUMENT;
@@ -1941,6 +2010,30 @@ int dic_solve_step(dic_engine *e, const float *A_upper, const float *b, float la
   return ok ? DIC_OK : DIC_ERROR_SOLVER;
 }
 
+int dic_pipe_trace(dic_engine *e, int on, float *stage_ms, float *solve_ms, int cap, int *n_solves) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  int n_st = 0;
+  if (e->trace_on && stage_ms && solve_ms) {
+    n_st = std::min(cap, e->trace_stage);
+    const int n_so = std::min(cap, e->trace_solve);
+    for (int i = 0; i < n_st; ++i)
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&stage_ms[4 * i + k], e->trace_base, e->trace_st[i][k]);
+    for (int i = 0; i < n_so; ++i)
+      for (int k = 0; k < 2; ++k) cudaEventElapsedTime(&solve_ms[2 * i + k], e->trace_base, e->trace_so[i][k]);
+    if (n_solves) *n_solves = n_so;
+  }
+  if (on && !e->trace_base) {
+    cudaEventCreate(&e->trace_base);
+    for (auto &r : e->trace_st) for (auto &ev : r) cudaEventCreate(&ev);
+    for (auto &r : e->trace_so) for (auto &ev : r) cudaEventCreate(&ev);
+  }
+  e->trace_on = on != 0;
+  e->trace_stage = e->trace_solve = 0;
+  if (on) { cudaEventRecord(e->trace_base, e->stream); cudaStreamSynchronize(e->stream); }
+  return n_st;
+}
 int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap) {
   if (!e || !marks) return 0;
   cudaSetDevice(e->device);

@@ -68,12 +68,12 @@ EXPORTS = [
     "dic_reset_image_pyramids_device", "dic_reset_next_pyramid", "dic_reset_next_pyramid_async", "dic_reset_next_pyramid_device",
     "dic_reset_def_pyramid", "dic_reset_def_pyramid_device", "dic_make_und_pyramid_from_def",
     "dic_make_def_pyramid_from_nxt", "dic_reset_polygon_rect", "dic_reset_polygon_annular",
-    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_rect_grid", "dic_set_cluster_mode", "dic_last_cluster_size", "dic_reset_polygon_points", "dic_set_polygon_center",
+    "dic_reset_polygon_blob", "dic_reset_polygon_rect_band", "dic_reset_polygon_rect_grid", "dic_set_cluster_mode", "dic_set_batch_queue", "dic_correlate_batch_async", "dic_correlate_batch_wait", "dic_last_cluster_size", "dic_reset_polygon_points", "dic_set_polygon_center",
     "dic_stage_next_pair", "dic_stage_next_pair_rows", "dic_advance_pair",
     "dic_update_polygon", "dic_rowsplit_mailbox_handle", "dic_rowsplit_connect", "dic_rowsplit_disconnect", "dic_correlate", "dic_correlate_batch", "dic_correlate_async",
     "dic_correlate_wait", "dic_get_und_xy0", "dic_get_def_xy0", "dic_get_pyramid_level",
     "dic_get_level_points", "dic_get_level_center", "dic_evaluate", "dic_solve_step",
-    "dic_last_correlate_ms", "dic_last_step_ms", "dic_get_timeline", "dic_get_cta_times", "dic_get_cta_smids", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
+    "dic_last_correlate_ms", "dic_last_step_ms", "dic_get_timeline", "dic_pipe_trace", "dic_get_cta_times", "dic_get_cta_smids", "dic_kernel_launches", "dic_correlation_stream", "dic_synchronize",
 ]
 
 
@@ -119,6 +119,10 @@ def load_library():
         "dic_reset_polygon_rect_band": (I, [P, I, I, I, I, I, I, I]),
         "dic_reset_polygon_rect_grid": (I, [P, I, I, P]),
         "dic_set_cluster_mode": (I, [P, I]),
+        "dic_set_batch_queue": (I, [P, I]),
+        "dic_pipe_trace": (I, [P, I, P, P, I, P]),
+        "dic_correlate_batch_async": (I, [P, I, I, P]),
+        "dic_correlate_batch_wait": (I, [P, I, I, P, P]),
         "dic_last_cluster_size": (I, [P]),
         "dic_rowsplit_mailbox_handle": (I, [P, P, I]),
         "dic_rowsplit_connect": (I, [P, I, I, P, I]),
@@ -288,6 +292,17 @@ class CudaEngine:
         """boxes: (n, 4) int array of x0, y0, x1, y1 -- n rectangles in one go (dic_reset_polygon_rect_grid)."""
         b = np.ascontiguousarray(boxes, np.int32).reshape(-1, 4)
         return self._ck(self.lib.dic_reset_polygon_rect_grid(self.h, int(first_sector), b.shape[0], _ptr(b)), soft=(4,))
+
+    def pipe_trace(self, on, read=True):
+        """Arm (on=True) / disarm the staged-pair pipeline marks; returns (stage_ms [n, 4], solve_ms [m, 2]) of the
+        marks armed before this call (dic_pipe_trace)."""
+        st = np.zeros((48, 4), np.float32); so = np.zeros((48, 2), np.float32); m = C.c_int(0)
+        n = self.lib.dic_pipe_trace(self.h, int(bool(on)), st.ctypes.data if read else None, so.ctypes.data if read else None, 48, C.byref(m))
+        return st[:n], so[:m.value]
+
+    def set_batch_queue(self, mode):
+        """0 automatic, 1 resident CTAs + ticket queue, 2 one CTA per sector (dic_set_batch_queue)"""
+        self._ck(self.lib.dic_set_batch_queue(self.h, int(mode)))
 
     def set_cluster_mode(self, mode):
         self._ck(self.lib.dic_set_cluster_mode(self.h, int(mode)))

@@ -138,7 +138,12 @@ int dic_reset_def_pyramid_device(dic_engine *e, const void *def_dev, int rows, i
  * host buffers must stay untouched until the dic_advance_pair that makes the staged pair current
  * (a stream-side wait, no host sync). A loop `advance; stage(k + 1); correlate(k)` overlaps the
  * PCIe transfer of pair k + 1 with the solve of pair k -- the same overlap the reference gets from
- * resetNextPyramid on its loader thread (manager_class.cpp:1438-1447), for both images. */
+ * resetNextPyramid on its loader thread (manager_class.cpp:1438-1447), for both images.
+ * Up to TWO pairs may be staged ahead (a third dic_stage_next_pair without a dic_advance_pair is refused):
+ * `advance; correlate_async(k); stage(k + 2); correlate_wait(k)` keeps the bus busy while the host waits for
+ * the solve -- with one pair ahead the transfer of pair k + 2 cannot be enqueued before the host has seen the
+ * end of solve k. dic_advance_pair makes the OLDEST staged pair current and waits (stream-side) for that
+ * pair's pyramids only. */
 int dic_stage_next_pair(dic_engine *e, const uint8_t *und, const uint8_t *def, int rows, int cols);
 int dic_advance_pair(dic_engine *e);
 /* same for a GPU that works on a band of the image only (sharded subsets, row-split domain): `und` and
@@ -199,12 +204,24 @@ int dic_correlate_batch(dic_engine *e, int first_sector, int n_sectors, float *g
  * shared memory) when there are too few sectors to occupy the GPU's CTA slots at all; 1 = always one CTA; 2 = always a pair.
  * Results are identical to ~1 ulp of the sums (the two halves are added in a fixed order). */
 int dic_set_cluster_mode(dic_engine *e, int mode);
+/* extension: how a one-CTA-per-sector batch occupies the GPU. 1 = resident CTAs (as many as fit at once) that draw
+ * further sectors from a launch-wide ticket counter; 2 = one CTA per sector, left to the hardware block scheduler,
+ * so that kernels of the higher-priority image stream (the NEXT pair's pyramid build, dic_stage_next_pair) are
+ * interleaved with the solve instead of waiting for all of it; 0 (default) = 1 (measured on BASELINE config 4: the
+ * staged-pair loop is bound by the PCIe transfer in both forms, the resident kernel is within 1.5 %). The records do
+ * not depend on the choice (one CTA, one instruction sequence per sector either way). */
+int dic_set_batch_queue(dic_engine *e, int mode);
 /* CTAs per sector the last dic_correlate_batch launch used (1 or 2) */
 int dic_last_cluster_size(const dic_engine *e);
 /* extension: enqueue only (no host sync); dic_correlate_wait collects. Lets a caller overlap
  * the next upload with the solve, and lets bench.py time the device alone. */
 int dic_correlate_async(dic_engine *e, int iSector, const float *guess);
 int dic_correlate_wait(dic_engine *e, int iSector, float *guess_out, dic_result *out);
+/* the same split for a batch: dic_correlate_batch == dic_correlate_batch_async + dic_correlate_batch_wait. A frame loop
+ * that calls `dic_advance_pair; dic_correlate_batch_async(k); dic_stage_next_pair(k + 1); dic_correlate_batch_wait(k)`
+ * keeps the host work of the staging call off the solve's critical path. guesses_out / results may be NULL. */
+int dic_correlate_batch_async(dic_engine *e, int first_sector, int n_sectors, const float *guesses);
+int dic_correlate_batch_wait(dic_engine *e, int first_sector, int n_sectors, float *guesses_out, dic_result *results);
 
 /* ---- extension: one domain row-split over `world` GPUs of one node (one process per GPU).
  *      Every evaluation ends with a sum of the normal equations over the ranks, done inside the
@@ -247,6 +264,12 @@ float dic_last_step_ms(dic_engine *e);
 /* CTA 0's timeline of the last single-sector correlate: per evaluation 4 device timestamps (ns):
  * pass start, own pass done, all CTAs arrived, LM step published. Returns the evaluation count. */
 int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap);
+/* diagnostics of the staged-pair pipeline. on != 0 arms device-time marks for the next (at most 48) dic_stage_next_pair*
+ * and correlate calls; every call first drains the device and, if marks were armed and the arrays are given, writes
+ * per staging call {transfer may start, reference image landed, deformed image landed, both pyramids built}
+ * (stage_ms, 4 floats each) and per correlate {kernel start, kernel end} (solve_ms, 2 floats each), in ms since the
+ * arming call. Returns the number of staging calls written (<= cap), *n_solves the correlates. */
+int dic_pipe_trace(dic_engine *e, int on, float *stage_ms, float *solve_ms, int cap, int *n_solves);
 /* load-balance probe: per CTA of the last single-sector correlate, the device time (ns) at which its
  * pass of the last evaluation ended. Returns the number of entries written (<= cap, <= 1024). */
 int dic_get_cta_times(dic_engine *e, unsigned long long *out, int cap);

@@ -604,6 +604,40 @@ def test_staged_pairs_double_buffer_equals_direct_upload(eng, golden):
         eng.advancePair()  # nothing staged any more
 
 
+def test_two_pairs_staged_ahead(eng, golden):
+    """Two pairs may be staged before a dic_advance_pair (a third is refused); they become current oldest first, and
+    a pair staged while the other is still waiting lands in the slots the last advance released."""
+    import torch
+    und_a, def_a = golden["A/und"], golden["A/def"]
+    rows, cols = und_a.shape
+    pairs = [(und_a, def_a)]
+    for seed, truth in ((77, (0.9, -1.1, 0.002, 0.001, -0.001, 0.003)), (78, (-0.7, 0.4, -0.001, 0.002, 0.001, -0.002))):
+        pairs.append(synth.make_pair(rows, cols, seed, truth, center=(95, 95)))
+    x0, y0, x1, y1 = (int(v) for v in golden["A/rect"])
+    want = []
+    for u, d in pairs:
+        eng.resetImagePyramids(u, d, pyramid=(0, 1, 2))
+        eng.resetPolygon(0, x0, y0, x1, y1)
+        want.append(eng.correlate(0, np.zeros(6, np.float32)))
+    pins = [[torch.from_numpy(np.ascontiguousarray(im)).pin_memory() for im in pr] for pr in pairs]
+    stage = lambda i: eng.stageNextPair(pins[i % 3][0].data_ptr(), pins[i % 3][1].data_ptr(), rows, cols)
+    stage(0)
+    stage(1)
+    with pytest.raises(engine.DicError):
+        stage(2)
+    for k in range(7):
+        eng.advancePair()
+        eng.correlate_async(0, np.zeros(6, np.float32))
+        stage(k + 2)
+        got = eng.correlate_wait(0)
+        w = want[k % 3]
+        assert np.array_equal(got["params"], w["params"]) and got["chi"] == w["chi"], (k, got, w)
+    eng.advancePair()
+    eng.advancePair()
+    with pytest.raises(engine.DicError):
+        eng.advancePair()
+
+
 def test_staged_row_band_equals_full_upload_inside_the_band(eng, golden):
     """dic_stage_next_pair_rows: only a band of rows is transferred and rebuilt; a domain well inside the
     band must give bit-identical results to a full upload even when the rest of the slot holds junk."""
@@ -733,6 +767,48 @@ def test_batch_records_do_not_depend_on_the_cta_assignment(eng):
     assert all_a[:450].tobytes() == first.tobytes() and all_a[450:].tobytes() == second.tobytes()
     d = np.abs(all_a["resultingParameters"][:, :2] - np.array(truth[:2]))  # every subset sees the field at its own centre
     assert np.median(d.max(1)) < 0.8  # (|gradient| x |offset from the image centre| <= 0.73 px here)
+
+
+def test_batch_forms_and_async_split_give_the_same_records(eng):
+    """dic_set_batch_queue: resident CTAs + ticket queue (1) and one CTA per sector under the hardware block scheduler
+    (2, the form that lets the next pair's pyramid build into the solve) are the same computation per subset; and
+    dic_correlate_batch == dic_correlate_batch_async + dic_correlate_batch_wait, also with a pair staged in between
+    (the order bench.py's end-to-end loop uses)."""
+    truth = (0.9, -0.4, 0.001, -0.0005, 0.0005, 0.001)
+    und, dfm = synth.make_pair(1536, 1536, 43, truth, center=(768, 768))
+    eng.set_fitting_model(engine.FM_UVUxUyVxVy)
+    eng.set_arith_mode(engine.MODE_PARITY)
+    eng.resetImagePyramids(und, dfm, pyramid=(0, 1, 2))
+    boxes = [(40 + 48 * i, 40 + 48 * j, 40 + 48 * i + 46, 40 + 48 * j + 46) for i in range(30) for j in range(30)]
+    assert eng.resetPolygonRectGrid(0, np.array(boxes, np.int32)) == 0
+    n = len(boxes)
+    zero = np.zeros((n, 6), np.float32)
+    import torch
+    und_pin = torch.from_numpy(und).pin_memory()
+    dfm_pin = torch.from_numpy(dfm).pin_memory()
+    try:
+        eng.set_batch_queue(1)
+        _, resident = eng.correlate_batch_raw(0, zero)
+        eng.set_batch_queue(2)
+        _, per_sector = eng.correlate_batch_raw(0, zero)
+        assert (resident["errorCode"] == 0).all()
+        assert resident.tobytes() == per_sector.tobytes()
+        for q in (1, 2, 0):
+            eng.set_batch_queue(q)
+            eng.stageNextPair(und_pin.data_ptr(), dfm_pin.data_ptr(), 1536, 1536)
+            for _ in range(2):
+                eng.advancePair()
+                out = np.zeros(n, engine.RESULT_DTYPE)
+                g = zero.copy()
+                assert eng.lib.dic_correlate_batch_async(eng.h, 0, n, g.ctypes.data) == 0
+                eng.stageNextPair(und_pin.data_ptr(), dfm_pin.data_ptr(), 1536, 1536)
+                eng.lib.dic_correlate_batch_wait(eng.h, 0, n, g.ctypes.data, out.ctypes.data)
+                assert out.tobytes() == resident.tobytes()
+                assert np.array_equal(g, resident["resultingParameters"][:, :6])
+            eng.advancePair()
+    finally:
+        eng.set_batch_queue(0)
+    assert eng.lib.dic_correlate_batch_wait(eng.h, 0, 0, None, None) == 8  # DIC_ERROR_BAD_ARGUMENT
 
 
 def test_flat_and_gradient_free_patches_follow_the_reference_qr(eng):
