@@ -1009,6 +1009,9 @@ def main():
                     eng = run.eng
                     pair_used = eng.last_cluster_size() == 2
                     n_all = len(run.all_boxes)
+                    # the end-to-end loop left only this rank's band of rows in the current slots: whole images again
+                    eng.resetImagePyramidsDevice(run.und_t.data_ptr(), run.dfm_t.data_ptr(), None, w["rows"], w["cols"],
+                                                 w["cols"], pyramid=w["pyramid"])
                     base = run.n_sectors
                     eng.resetPolygonRectGrid(base, np.array(run.all_boxes, np.int32))
                     eng.set_cluster_mode(2 if pair_used else 1)
