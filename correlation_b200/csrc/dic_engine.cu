@@ -858,6 +858,7 @@ dic_engine *dic_create(int device) {
   // queueing behind it (dic_set_batch_queue).
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (std::getenv("DIC_NO_STREAM_PRIORITY")) prio_hi = prio_lo; // diagnostics: both streams at the default priority
   bool ok = cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
             cudaStreamCreateWithPriority(&e->img_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&

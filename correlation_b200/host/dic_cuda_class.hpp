@@ -135,6 +135,23 @@ public:
     return dic_correlate_batch(engine_, firstSector, nSectors, guesses, reinterpret_cast<dic_result *>(out));
   }
 
+  // extension: the same as two calls -- the caller may stage the next pair or post-process the last records between them
+  int correlateBatchAsync(int firstSector, int nSectors, const float *guesses) {
+    need_engine();
+    return dic_correlate_batch_async(engine_, firstSector, nSectors, guesses);
+  }
+  int correlateBatchWait(int firstSector, int nSectors, float *guessesOut, CorrelationResult *out) {
+    need_engine();
+    return dic_correlate_batch_wait(engine_, firstSector, nSectors, guessesOut, reinterpret_cast<dic_result *>(out));
+  }
+  // extension: whole (und, def) pairs from pinned host memory, up to two pairs ahead of the one being solved; the
+  // loop `stage(k + 2); wait(k); advancePair(); correlateBatchAsync(k + 1)` keeps the PCIe bus busy all the time
+  errorEnum stageNextPair(const unsigned char *und, const unsigned char *def, int rows, int cols) {
+    need_engine();
+    return (errorEnum)dic_stage_next_pair(engine_, und, def, rows, cols);
+  }
+  errorEnum advancePair() { need_engine(); return (errorEnum)dic_advance_pair(engine_); }
+
   v_points getUndXY0ToCPU(int iSector) { return points(iSector, false); }
   v_points getDefXY0ToCPU(int iSector) { return points(iSector, true); }
 
