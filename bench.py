@@ -368,6 +368,7 @@ def run_c3(args, w, with_cpu=True):
                        "points": int(last["number_of_points"]), "errors": int(sum(int(r["error_code"]) != 0 for r in rows)),
                        "ms_per_frame": 1e3 * secs / (n - 1),
                        "ms_per_frame_spread": [1e3 * min(secs_all) / (n - 1), 1e3 * max(secs_all) / (n - 1)],
+                       "ms_per_frame_median_run": 1e3 * float(np.median(secs_all)) / (n - 1),
                        "last_frame_params": [float(v) for v in last["params"][:6]],
                        "last_frame_truth": [float(v) for v in truth_last],
                        "step": "one step = the whole 99-pair sequence through dic_host_run (C++ host loop)"},
