@@ -43,3 +43,55 @@ def test_upload_band_covers_domain_plus_halo_and_stays_inside_the_image():
     for lv in range(1, 5):
         lo, hi = (lo + 3) // 2, (hi - 3) // 2 + 1
         assert lo <= (4000 >> lv) - 2 and hi >= (5000 >> lv) + 3
+
+
+class _FakeStagingEngine:
+    """The staging rules of dic_stage_next_pair / dic_advance_pair / dic_correlate*_async / _wait
+    (include/dic_b200.h), without a device: at most two pairs staged, advance needs one, a wait needs an enqueue."""
+
+    def __init__(self):
+        self.staged = []      # pair ids staged and not yet current
+        self.current = None   # pair id the next solve reads
+        self.in_flight = None
+        self.next_id = 0
+        self.solved = []
+        self.max_staged = 0
+
+    def stage(self):
+        assert len(self.staged) < 2, "a third pair was staged without an advance"
+        self.staged.append(self.next_id)
+        self.next_id += 1
+        self.max_staged = max(self.max_staged, len(self.staged))
+
+    def advancePair(self):
+        assert self.staged, "advance without a staged pair"
+        assert self.in_flight is None, "advance while a solve still reads the current pair's records"
+        self.current = self.staged.pop(0)
+
+    def enqueue(self):
+        assert self.current is not None and self.in_flight is None
+        self.in_flight = self.current
+
+    def wait(self):
+        assert self.in_flight is not None, "wait without an enqueued solve"
+        self.solved.append(self.in_flight)
+        self.in_flight = None
+
+
+def test_e2e_loop_stages_two_pairs_ahead_and_solves_every_pair_once():
+    """bench.Run.e2e_loop on a fake engine: n steps stage n pairs, solve pairs 0..n-1 in order, keep two pairs
+    staged ahead once the pipeline is full, and leave nothing staged or in flight."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (1, 2, 3, 7, 32):
+        fake = _FakeStagingEngine()
+        run = bench.Run.__new__(bench.Run)
+        run.eng = fake
+        run.stage_pair = fake.stage
+        run.enqueue_step = fake.enqueue
+        run.wait_step = fake.wait
+        run.step_work = lambda: 1.0
+        assert run.e2e_loop(n) == float(n)
+        assert fake.solved == list(range(n)) and fake.next_id == n
+        assert fake.staged == [] and fake.in_flight is None
+        assert fake.max_staged == min(n, 2)
