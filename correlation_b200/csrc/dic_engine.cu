@@ -118,7 +118,7 @@ struct dic_engine {
   bool trace_on = false;
   int trace_stage = 0, trace_solve = 0;
   cudaEvent_t trace_base = nullptr, trace_st[kTrace][4] = {}, trace_so[kTrace][2] = {};
-  int batch_queue = 0;             // batch launches: 0 auto, 1 resident CTAs + ticket queue, 2 one CTA per sector (dic_set_batch_queue)
+  int batch_queue = 0;             // batch launches: 0 / 1 resident CTAs + ticket queue, 2 one CTA per sector (dic_set_batch_queue)
   // device blocks shared by the sectors of one dic_reset_polygon_rect_grid call, keyed by its first sector id:
   // rebuilding the same range reuses (or regrows) its blocks, another range gets its own
   struct GridBlock { int first_id = 0; void *lists = nullptr, *tiles = nullptr, *desc = nullptr; size_t cap_lists = 0, cap_tiles = 0, cap_desc = 0; };
@@ -2033,6 +2033,7 @@ int dic_pipe_trace(dic_engine *e, int on, float *stage_ms, float *solve_ms, int 
   e->trace_on = on != 0;
   e->trace_stage = e->trace_solve = 0;
   if (on) { cudaEventRecord(e->trace_base, e->stream); cudaStreamSynchronize(e->stream); }
+  cudaGetLastError(); // a mark that was never recorded (a call that failed half-way) must not surface in a later launch check
   return n_st;
 }
 int dic_get_timeline(dic_engine *e, unsigned long long *marks, int cap) {
