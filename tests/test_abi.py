@@ -59,3 +59,21 @@ def test_host_deform_points_restates_the_reference_distort_functions():
     for model, (wx, wy) in want.items():
         got = host.deform_points(model, p, (cx, cy), xy)
         assert np.array_equal(got[:, 0], wx.astype(np.float32)) and np.array_equal(got[:, 1], wy.astype(np.float32)), model
+
+
+def test_header_is_plain_c_and_the_cpp_facade_compiles_against_it(tmp_path):
+    """include/dic_b200.h is the drop-in boundary: it must be includable from C (no C++ or torch types in the
+    signatures), and the reference-side binding INTEGRATION.md documents (host/dic_cuda_class.hpp, incl. the pair
+    staging and async batch methods) must compile against it with nothing but the standard library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "dic_b200.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "use_facade.cpp"
+    src.write_text('#include "dic_cuda_class.hpp"\n'
+                   "int probe(CudaClass &c, const unsigned char *u, const unsigned char *d, float *g, CorrelationResult *r) {\n"
+                   "  c.stageNextPair(u, d, 64, 64); c.advancePair();\n"
+                   "  c.correlateBatchAsync(0, 4, g); return c.correlateBatchWait(0, 4, g, r);\n}\n")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "correlation_b200", "host"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
